@@ -1,0 +1,979 @@
+// bbq_api.cu — host side of libbbq_b200.so: the C ABI declared in include/bbq_b200.h.
+// Owns device memory, the stream and the launch sequence; no torch, no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bbq_b200.h"
+#include "bbq_kernels.cuh"
+
+using namespace bbqk;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static thread_local int64_t g_err_vec = -1, g_err_pos = -1;
+
+static int fail(int status, const std::string& msg, int64_t vec = -1, int64_t pos = -1) {
+  g_err = msg;
+  g_err_vec = vec;
+  g_err_pos = pos;
+  return status;
+}
+
+#define CU(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      const int _st = (_e == cudaErrorMemoryAllocation) ? BBQ_ERR_OOM : BBQ_ERR_CUDA;              \
+      return fail(_st, std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
+    }                                                                                              \
+  } while (0)
+
+#define TRY(expr)                 \
+  do {                            \
+    const int _s = (expr);        \
+    if (_s != BBQ_OK) return _s;  \
+  } while (0)
+
+struct DevBuf {  // grow-only device scratch
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return BBQ_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    CU(cudaMalloc(&p, bytes));
+    cap = bytes;
+    return BBQ_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct bbq_ctx {
+  bbq_config cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  uint64_t launches = 0;
+  bbq_stats stats{};
+  int force_path = -1;  // BBQ_FORCE_PATH: 1 sampled+filtered, 2 exact chunked (tests)
+  // build scratch
+  DevBuf T, stage, cacc;
+  // query scratch
+  DevBuf qrows, qT, qcodes, qcorr, planes, qterms, tau, dump, cand, cand_cnt, flag, lists_a, lists_b,
+      out_idx, out_score, dots;
+  uint32_t* h_flag = nullptr;  // pinned: [0..nq) candidate counts, [nq] overflow flag
+  // profiling (bbq_set_profiling): event pairs per kernel group, drained by bbq_get_stats
+  bool profiling = false;
+  struct EvPair { cudaEvent_t a, b; int kind; };
+  std::vector<EvPair> ev_pending;
+  std::vector<cudaEvent_t> ev_pool;
+};
+
+enum { PROF_SCAN = 0, PROF_QUANT = 1, PROF_SELECT = 2 };
+struct ProfScope {  // records an event pair around a group of launches when profiling is on
+  bbq_ctx* c;
+  cudaStream_t st;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int kind;
+  ProfScope(bbq_ctx* c_, cudaStream_t st_, int kind_) : c(c_), st(st_), kind(kind_) {
+    if (!c->profiling) return;
+    auto get = [&]() {
+      cudaEvent_t e = nullptr;
+      if (!c->ev_pool.empty()) {
+        e = c->ev_pool.back();
+        c->ev_pool.pop_back();
+      } else {
+        cudaEventCreate(&e);
+      }
+      return e;
+    };
+    a = get();
+    b = get();
+    cudaEventRecord(a, st);
+  }
+  ~ProfScope() {
+    if (!a) return;
+    cudaEventRecord(b, st);
+    c->ev_pending.push_back({a, b, kind});
+  }
+};
+
+struct bbq_index {
+  bbq_ctx* ctx = nullptr;
+  uint64_t n = 0;
+  uint32_t dim = 0;
+  int row_bytes = 0;
+  uint8_t* codes = nullptr;
+  double *lower = nullptr, *upper = nullptr, *addc = nullptr;
+  uint32_t* compsum = nullptr;
+  float* centroid = nullptr;  // device
+  std::vector<float> centroid_h;
+  double cdp = 0.0;
+  uint64_t base = 0;
+  uint64_t capacity = 0;  // rows allocated (== n except while a streaming build is in progress)
+};
+
+static constexpr int64_t BUILD_CHUNK = 32768;   // rows per build chunk (transposed scratch = dim*chunk*4 B)
+static constexpr uint32_t QUERY_BATCH = 1024;   // queries per internal pass
+static constexpr int64_t SAMPLE_TILES = 128;    // threshold sample = 128 tiles = 16384 rows
+static constexpr uint32_t CAND_CAP = SELECT_MAX;
+static constexpr uint32_t K_MAX = 4096;
+
+static inline int row_bytes_for(uint32_t dim) { return (int)((((dim + 7) / 8) + 15) / 16 * 16); }
+
+// ------------------------------------------------------------------------------------------------
+// lifecycle
+// ------------------------------------------------------------------------------------------------
+extern "C" int bbq_abi_version(void) { return BBQ_B200_ABI_VERSION; }
+extern "C" const char* bbq_last_error(void) { return g_err.c_str(); }
+extern "C" void bbq_last_error_pos(int64_t* vector, int64_t* position) {
+  if (vector) *vector = g_err_vec;
+  if (position) *position = g_err_pos;
+}
+
+extern "C" int bbq_create(const bbq_config* config, bbq_ctx** out_ctx) {
+  if (!config || !out_ctx) return fail(BBQ_ERR_NULL, "config/out_ctx is null");
+  *out_ctx = nullptr;
+  // src/binaryQuantizationFormat.ts:143-148
+  if (config->query_bits < 1 || config->query_bits > 8) return fail(BBQ_ERR_QUERY_BITS, "queryBits must be in 1..8");
+  if (config->index_bits < 1 || config->index_bits > 8) return fail(BBQ_ERR_INDEX_BITS, "indexBits must be in 1..8");
+  if (config->similarity > 2) return fail(BBQ_ERR_INVALID_ARG, "unknown similarity function");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(BBQ_ERR_NO_DEVICE, "no CUDA device: libbbq_b200 has no CPU fallback");
+  }
+  int dev = config->device;
+  if (dev < 0) CU(cudaGetDevice(&dev));
+  if (dev >= ndev) return fail(BBQ_ERR_NO_DEVICE, "device ordinal out of range");
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(BBQ_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                       "; this library is built for sm_100a (B200) only");
+  CU(cudaSetDevice(dev));
+  bbq_ctx* c = new bbq_ctx();
+  c->cfg = *config;
+  c->device = dev;
+  c->sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaMallocHost(&c->h_flag, (QUERY_BATCH + 1) * sizeof(uint32_t)));
+  if (const char* e = getenv("BBQ_FORCE_PATH")) c->force_path = atoi(e);
+  *out_ctx = c;
+  return BBQ_OK;
+}
+
+extern "C" void bbq_destroy(bbq_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (DevBuf* b : {&c->T, &c->stage, &c->cacc, &c->qrows, &c->qT, &c->qcodes, &c->qcorr, &c->planes, &c->qterms,
+                    &c->tau, &c->dump, &c->cand, &c->cand_cnt, &c->flag, &c->lists_a, &c->lists_b, &c->out_idx,
+                    &c->out_score, &c->dots})
+    b->release();
+  if (c->h_flag) cudaFreeHost(c->h_flag);
+  for (auto& p : c->ev_pending) {
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
+  }
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int bbq_get_stats(bbq_ctx* c, bbq_stats* out) {
+  if (!c || !out) return fail(BBQ_ERR_NULL, "null");
+  for (auto& p : c->ev_pending) {
+    float ms = 0.f;
+    CU(cudaEventSynchronize(p.b));
+    CU(cudaEventElapsedTime(&ms, p.a, p.b));
+    if (p.kind == PROF_SCAN) {
+      c->stats.scan_ms += ms;
+    } else if (p.kind == PROF_QUANT) {
+      c->stats.quantize_ms += ms;
+    } else {
+      c->stats.select_ms += ms;
+    }
+    c->ev_pool.push_back(p.a);
+    c->ev_pool.push_back(p.b);
+  }
+  c->ev_pending.clear();
+  *out = c->stats;
+  out->kernel_launches = c->launches;
+  return BBQ_OK;
+}
+extern "C" int bbq_set_profiling(bbq_ctx* c, int enabled) {
+  if (!c) return fail(BBQ_ERR_NULL, "null");
+  c->profiling = enabled != 0;
+  return BBQ_OK;
+}
+extern "C" int bbq_reset_profiling(bbq_ctx* c) {
+  if (!c) return fail(BBQ_ERR_NULL, "null");
+  bbq_stats tmp;
+  TRY(bbq_get_stats(c, &tmp));
+  c->stats.scan_launches = 0;
+  c->stats.scan_ms = c->stats.quantize_ms = c->stats.select_ms = 0.0;
+  return BBQ_OK;
+}
+
+#define LAUNCH(ctx, kernel, grid, block, smem, st, ...)       \
+  do {                                                        \
+    kernel<<<grid, block, smem, st>>>(__VA_ARGS__);           \
+    (ctx)->launches++;                                        \
+    CU(cudaGetLastError());                                   \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// index build
+// ------------------------------------------------------------------------------------------------
+static int index_alloc(bbq_ctx* c, uint64_t n, uint32_t dim, bbq_index** out) {
+  bbq_index* ix = new bbq_index();
+  ix->ctx = c;
+  ix->n = n;
+  ix->dim = dim;
+  ix->row_bytes = row_bytes_for(dim);
+  ix->capacity = n;
+  *out = ix;
+  CU(cudaMalloc(&ix->codes, (size_t)n * ix->row_bytes));
+  CU(cudaMalloc(&ix->lower, n * sizeof(double)));
+  CU(cudaMalloc(&ix->upper, n * sizeof(double)));
+  CU(cudaMalloc(&ix->addc, n * sizeof(double)));
+  CU(cudaMalloc(&ix->compsum, n * sizeof(uint32_t)));
+  CU(cudaMalloc(&ix->centroid, dim * sizeof(float)));
+  ix->centroid_h.resize(dim);
+  return BBQ_OK;
+}
+
+extern "C" void bbq_index_destroy(bbq_index* ix) {
+  if (!ix) return;
+  cudaSetDevice(ix->ctx->device);
+  cudaStreamSynchronize(ix->ctx->stream);
+  cudaFree(ix->codes);
+  cudaFree(ix->lower);
+  cudaFree(ix->upper);
+  cudaFree(ix->addc);
+  cudaFree(ix->compsum);
+  cudaFree(ix->centroid);
+  delete ix;
+}
+
+static int finish_centroid(bbq_index* ix) {
+  bbq_ctx* c = ix->ctx;
+  TRY(c->cacc.reserve(sizeof(double)));
+  LAUNCH(c, k_centroid_dp, 1, 32, 0, c->stream, ix->centroid, (int)ix->dim, c->cacc.as<double>());
+  CU(cudaMemcpyAsync(&ix->cdp, c->cacc.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(ix->centroid_h.data(), ix->centroid, ix->dim * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BBQ_OK;
+}
+
+// rows: host (is_host) or device pointer.  Processes chunk by chunk through the transposed scratch.
+static int build_impl(bbq_ctx* c, const float* rows, bool is_host, uint64_t n, uint32_t dim, const float* centroid,
+                      bbq_index** out_index) {
+  if (!c || !out_index) return fail(BBQ_ERR_NULL, "null ctx/out_index");
+  *out_index = nullptr;
+  if (!rows) return fail(BBQ_ERR_NULL, "rows is null");
+  if (n == 0) return fail(BBQ_ERR_EMPTY, "vector set must not be empty");
+  if (dim == 0) return fail(BBQ_ERR_INVALID_ARG, "dim must be > 0");
+  if (n > 0xFFFFFFF0ull) return fail(BBQ_ERR_UNSUPPORTED, "more than 2^32 rows per shard");
+  if (c->cfg.index_bits != 1)
+    return fail(BBQ_ERR_UNSUPPORTED,
+                "indexBits != 1: the reference's batch search path cannot run it (createDirectPackedBuffer throws); "
+                "only the 1-bit index is built on device");
+  CU(cudaSetDevice(c->device));
+  bbq_index* ix = nullptr;
+  int st = index_alloc(c, n, dim, &ix);
+  if (st != BBQ_OK) {
+    bbq_index_destroy(ix);
+    return st;
+  }
+  auto bail = [&](int s) {
+    bbq_index_destroy(ix);
+    return s;
+  };
+  const int sim = (int)c->cfg.similarity;
+  const int64_t R = (int64_t)std::min<uint64_t>(n, BUILD_CHUNK);
+  st = c->T.reserve((size_t)R * dim * sizeof(float));
+  if (st != BBQ_OK) return bail(st);
+  if (is_host) {
+    st = c->stage.reserve((size_t)R * dim * sizeof(float));
+    if (st != BBQ_OK) return bail(st);
+  }
+  float* T = c->T.as<float>();
+  auto stage_chunk = [&](int64_t off, int64_t rows_here) -> int {
+    const float* src = rows + off * (int64_t)dim;
+    if (is_host) {
+      CU(cudaMemcpyAsync(c->stage.p, src, (size_t)rows_here * dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+      src = c->stage.as<float>();
+    }
+    dim3 grid((unsigned)((rows_here + 31) / 32), (dim + 31) / 32), block(32, 8);
+    LAUNCH(c, k_transpose, grid, block, 0, c->stream, src, rows_here, (int)dim, T, R);
+    if (sim == BBQ_SIM_COSINE)
+      LAUNCH(c, k_normalize_T, (unsigned)((rows_here + 127) / 128), 128, 0, c->stream, T, R, rows_here, (int)dim, 1);
+    return BBQ_OK;
+  };
+  if (centroid) {
+    st = [&]() -> int {
+      CU(cudaMemcpyAsync(ix->centroid, centroid, dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+      return BBQ_OK;
+    }();
+    if (st != BBQ_OK) return bail(st);
+  } else {
+    for (int64_t off = 0; off < (int64_t)n; off += R) {
+      const int64_t rows_here = std::min<int64_t>(R, (int64_t)n - off);
+      st = stage_chunk(off, rows_here);
+      if (st != BBQ_OK) return bail(st);
+      st = [&]() -> int {
+        LAUNCH(c, k_centroid_accum, (dim + 63) / 64, 64, 0, c->stream, T, R, rows_here, (int)dim, ix->centroid,
+               off == 0 ? 1 : 0);
+        return BBQ_OK;
+      }();
+      if (st != BBQ_OK) return bail(st);
+    }
+    st = [&]() -> int {
+      LAUNCH(c, k_centroid_finish, (dim + 127) / 128, 128, 0, c->stream, ix->centroid, (int)dim, (double)n);
+      return BBQ_OK;
+    }();
+    if (st != BBQ_OK) return bail(st);
+  }
+  for (int64_t off = 0; off < (int64_t)n; off += R) {
+    const int64_t rows_here = std::min<int64_t>(R, (int64_t)n - off);
+    st = stage_chunk(off, rows_here);
+    if (st != BBQ_OK) return bail(st);
+    st = [&]() -> int {
+      LAUNCH(c, k_osq_index, (unsigned)((rows_here + 127) / 128), 128, 0, c->stream, T, R, rows_here, (int)dim,
+             ix->centroid, sim, c->cfg.lambda, (int)c->cfg.iters, ix->codes, ix->row_bytes, off, ix->lower, ix->upper,
+             ix->addc, ix->compsum);
+      return BBQ_OK;
+    }();
+    if (st != BBQ_OK) return bail(st);
+  }
+  st = finish_centroid(ix);
+  if (st != BBQ_OK) return bail(st);
+  *out_index = ix;
+  return BBQ_OK;
+}
+
+// Reference validation order: COSINE rows are normalised first (binaryQuantizationFormat.ts:174-176), so a
+// row holding NaN becomes all-NaN (first offender: position 0) and a row holding +-Inf (norm = Inf) turns
+// the Inf components into NaN; otherwise the first non-finite component is reported as NaN or Infinity
+// (:196-211).  Returns BBQ_OK or the status with (vector, position) set.
+static int validate_rows(const float* rows, uint64_t n, uint32_t dim, bool cosine) {
+  for (uint64_t i = 0; i < n; i++) {
+    const float* r = rows + i * (uint64_t)dim;
+    bool bad = false;
+    for (uint32_t j = 0; j < dim; j++) bad |= !std::isfinite(r[j]);
+    if (!bad) continue;
+    if (cosine) {
+      for (uint32_t j = 0; j < dim; j++)
+        if (std::isnan(r[j])) return fail(BBQ_ERR_NAN, "vector contains NaN", (int64_t)i, 0);
+      double n2 = 0;
+      for (uint32_t j = 0; j < dim; j++) n2 += (double)r[j] * (double)r[j];
+      (void)n2;  // norm is +Inf here: finite/Inf -> 0, Inf/Inf -> NaN
+      for (uint32_t j = 0; j < dim; j++)
+        if (std::isinf(r[j])) return fail(BBQ_ERR_NAN, "vector contains NaN", (int64_t)i, (int64_t)j);
+    } else {
+      for (uint32_t j = 0; j < dim; j++) {
+        if (std::isnan(r[j])) return fail(BBQ_ERR_NAN, "vector contains NaN", (int64_t)i, (int64_t)j);
+        if (std::isinf(r[j])) return fail(BBQ_ERR_INF, "vector contains Infinity", (int64_t)i, (int64_t)j);
+      }
+    }
+  }
+  return BBQ_OK;
+}
+
+extern "C" int bbq_index_build(bbq_ctx* c, const float* rows, uint64_t n, uint32_t dim, const float* centroid,
+                               bbq_index** out_index) {
+  if (!c || !out_index) return fail(BBQ_ERR_NULL, "null ctx/out_index");
+  *out_index = nullptr;
+  if (n == 0) return fail(BBQ_ERR_EMPTY, "vector set must not be empty");
+  if (!rows) return fail(BBQ_ERR_NULL, "rows is null");
+  TRY(validate_rows(rows, n, dim, c->cfg.similarity == BBQ_SIM_COSINE));
+  return build_impl(c, rows, true, n, dim, centroid, out_index);
+}
+
+extern "C" int bbq_index_build_device(bbq_ctx* c, const float* d_rows, uint64_t n, uint32_t dim,
+                                      const float* centroid, bbq_index** out_index) {
+  return build_impl(c, d_rows, false, n, dim, centroid, out_index);
+}
+
+// quantise rows [0, n) of `rows` into index rows [row0, row0+n) with the index's centroid
+static int append_impl(bbq_index* ix, const float* rows, bool is_host, uint64_t n) {
+  if (!ix) return fail(BBQ_ERR_NULL, "null index");
+  if (!rows) return fail(BBQ_ERR_NULL, "rows is null");
+  if (ix->n + n > ix->capacity) return fail(BBQ_ERR_INVALID_ARG, "append exceeds the reserved capacity");
+  bbq_ctx* c = ix->ctx;
+  CU(cudaSetDevice(c->device));
+  const uint32_t dim = ix->dim;
+  const int sim = (int)c->cfg.similarity;
+  const int64_t R = (int64_t)std::min<uint64_t>(std::max<uint64_t>(n, 1), BUILD_CHUNK);
+  TRY(c->T.reserve((size_t)R * dim * sizeof(float)));
+  if (is_host) TRY(c->stage.reserve((size_t)R * dim * sizeof(float)));
+  float* T = c->T.as<float>();
+  for (int64_t off = 0; off < (int64_t)n; off += R) {
+    const int64_t rows_here = std::min<int64_t>(R, (int64_t)n - off);
+    const float* src = rows + off * (int64_t)dim;
+    if (is_host) {
+      CU(cudaMemcpyAsync(c->stage.p, src, (size_t)rows_here * dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+      src = c->stage.as<float>();
+    }
+    dim3 grid((unsigned)((rows_here + 31) / 32), (dim + 31) / 32), block(32, 8);
+    LAUNCH(c, k_transpose, grid, block, 0, c->stream, src, rows_here, (int)dim, T, R);
+    if (sim == BBQ_SIM_COSINE)
+      LAUNCH(c, k_normalize_T, (unsigned)((rows_here + 127) / 128), 128, 0, c->stream, T, R, rows_here, (int)dim, 1);
+    LAUNCH(c, k_osq_index, (unsigned)((rows_here + 127) / 128), 128, 0, c->stream, T, R, rows_here, (int)dim,
+           ix->centroid, sim, c->cfg.lambda, (int)c->cfg.iters, ix->codes, ix->row_bytes, (int64_t)ix->n + off,
+           ix->lower, ix->upper, ix->addc, ix->compsum);
+    if (is_host) CU(cudaStreamSynchronize(c->stream));  // the staging buffer is reused by the next chunk
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  ix->n += n;
+  return BBQ_OK;
+}
+
+extern "C" int bbq_index_reserve(bbq_ctx* c, uint64_t capacity, uint32_t dim, const float* centroid,
+                                 bbq_index** out_index) {
+  if (!c || !out_index) return fail(BBQ_ERR_NULL, "null ctx/out_index");
+  *out_index = nullptr;
+  if (!centroid) return fail(BBQ_ERR_NULL, "a streaming build needs an explicit centroid");
+  if (capacity == 0) return fail(BBQ_ERR_EMPTY, "vector set must not be empty");
+  if (dim == 0) return fail(BBQ_ERR_INVALID_ARG, "dim must be > 0");
+  if (capacity > 0x7FFFFFF0ull) return fail(BBQ_ERR_UNSUPPORTED, "more than 2^31 rows per shard");
+  if (c->cfg.index_bits != 1) return fail(BBQ_ERR_UNSUPPORTED, "only the 1-bit index is built on device");
+  CU(cudaSetDevice(c->device));
+  bbq_index* ix = nullptr;
+  int st = index_alloc(c, capacity, dim, &ix);
+  if (st == BBQ_OK) {
+    ix->n = 0;
+    st = [&]() -> int {
+      CU(cudaMemcpy(ix->centroid, centroid, dim * sizeof(float), cudaMemcpyHostToDevice));
+      return finish_centroid(ix);
+    }();
+  }
+  if (st != BBQ_OK) {
+    bbq_index_destroy(ix);
+    return st;
+  }
+  *out_index = ix;
+  return BBQ_OK;
+}
+extern "C" int bbq_index_append(bbq_index* ix, const float* rows, uint64_t n) {
+  if (!ix) return fail(BBQ_ERR_NULL, "null index");
+  if (n == 0) return BBQ_OK;
+  if (!rows) return fail(BBQ_ERR_NULL, "rows is null");
+  TRY(validate_rows(rows, n, ix->dim, ix->ctx->cfg.similarity == BBQ_SIM_COSINE));
+  return append_impl(ix, rows, true, n);
+}
+extern "C" int bbq_index_append_device(bbq_index* ix, const float* d_rows, uint64_t n) {
+  if (n == 0) return BBQ_OK;
+  return append_impl(ix, d_rows, false, n);
+}
+
+extern "C" int bbq_index_from_quantized(bbq_ctx* c, const uint8_t* packed, const double* corr4, const float* centroid,
+                                        uint64_t n, uint32_t dim, bbq_index** out_index) {
+  if (!c || !out_index) return fail(BBQ_ERR_NULL, "null ctx/out_index");
+  *out_index = nullptr;
+  if (!packed || !corr4 || !centroid) return fail(BBQ_ERR_NULL, "null input");
+  if (n == 0) return fail(BBQ_ERR_EMPTY, "vector set must not be empty");
+  if (dim == 0) return fail(BBQ_ERR_INVALID_ARG, "dim must be > 0");
+  if (c->cfg.index_bits != 1) return fail(BBQ_ERR_UNSUPPORTED, "only 1-bit packed indexes can be adopted");
+  CU(cudaSetDevice(c->device));
+  bbq_index* ix = nullptr;
+  int st = index_alloc(c, n, dim, &ix);
+  if (st != BBQ_OK) {
+    bbq_index_destroy(ix);
+    return st;
+  }
+  const int P = (int)((dim + 7) / 8), RB = ix->row_bytes;
+  std::vector<uint8_t> codes((size_t)n * RB, 0);
+  std::vector<double> lo(n), up(n), ad(n);
+  std::vector<uint32_t> cs(n);
+  for (uint64_t i = 0; i < n; i++) {
+    memcpy(codes.data() + i * RB, packed + i * P, P);
+    if (dim & 7) codes[i * RB + P - 1] &= (uint8_t)(0xFF << (8 - (dim & 7)));  // tail bits are zero by contract
+    lo[i] = corr4[4 * i];
+    up[i] = corr4[4 * i + 1];
+    ad[i] = corr4[4 * i + 2];
+    cs[i] = (uint32_t)corr4[4 * i + 3];
+  }
+  st = [&]() -> int {
+    CU(cudaMemcpy(ix->codes, codes.data(), codes.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ix->lower, lo.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ix->upper, up.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ix->addc, ad.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ix->compsum, cs.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ix->centroid, centroid, dim * sizeof(float), cudaMemcpyHostToDevice));
+    return finish_centroid(ix);
+  }();
+  if (st != BBQ_OK) {
+    bbq_index_destroy(ix);
+    return st;
+  }
+  *out_index = ix;
+  return BBQ_OK;
+}
+
+extern "C" uint64_t bbq_index_size(const bbq_index* ix) { return ix ? ix->n : 0; }
+extern "C" uint32_t bbq_index_dim(const bbq_index* ix) { return ix ? ix->dim : 0; }
+extern "C" int bbq_index_centroid(const bbq_index* ix, float* out_centroid, double* out_cdp) {
+  if (!ix) return fail(BBQ_ERR_NULL, "null index");
+  if (out_centroid) memcpy(out_centroid, ix->centroid_h.data(), ix->dim * sizeof(float));
+  if (out_cdp) *out_cdp = ix->cdp;
+  return BBQ_OK;
+}
+extern "C" int bbq_index_set_base(bbq_index* ix, uint64_t base) {
+  if (!ix) return fail(BBQ_ERR_NULL, "null index");
+  if (base + ix->n > 0x7FFFFFFFull) return fail(BBQ_ERR_UNSUPPORTED, "global row ids must fit in int32");
+  ix->base = base;
+  return BBQ_OK;
+}
+
+extern "C" int bbq_index_export(const bbq_index* ix, uint64_t first, uint64_t count, uint8_t* packed, double* corr4) {
+  if (!ix) return fail(BBQ_ERR_NULL, "null index");
+  if (first + count > ix->n) return fail(BBQ_ERR_INVALID_ARG, "row range out of bounds");
+  if (count == 0) return BBQ_OK;
+  CU(cudaSetDevice(ix->ctx->device));
+  CU(cudaStreamSynchronize(ix->ctx->stream));
+  const int P = (int)((ix->dim + 7) / 8), RB = ix->row_bytes;
+  if (packed) {
+    std::vector<uint8_t> tmp((size_t)count * RB);
+    CU(cudaMemcpy(tmp.data(), ix->codes + first * RB, tmp.size(), cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < count; i++) memcpy(packed + i * P, tmp.data() + i * RB, P);
+  }
+  if (corr4) {
+    std::vector<double> lo(count), up(count), ad(count);
+    std::vector<uint32_t> cs(count);
+    CU(cudaMemcpy(lo.data(), ix->lower + first, count * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(up.data(), ix->upper + first, count * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(ad.data(), ix->addc + first, count * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(cs.data(), ix->compsum + first, count * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < count; i++) {
+      corr4[4 * i] = lo[i];
+      corr4[4 * i + 1] = up[i];
+      corr4[4 * i + 2] = ad[i];
+      corr4[4 * i + 3] = (double)cs[i];
+    }
+  }
+  return BBQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// search
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+static int launch_scan_nb(bbq_ctx* c, int nb, dim3 grid, size_t smem, cudaStream_t st, const ScanParams& p) {
+#define BBQ_SCAN_CASE(NB)                                                                                          \
+  case NB:                                                                                                         \
+    if (smem > 48 * 1024)                                                                                          \
+      CU(cudaFuncSetAttribute(k_scan<NB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+    LAUNCH(c, (k_scan<NB, MODE>), grid, TILE_ROWS, smem, st, p);                                                   \
+    break;
+  switch (nb) {
+    BBQ_SCAN_CASE(1)
+    BBQ_SCAN_CASE(2)
+    BBQ_SCAN_CASE(3)
+    BBQ_SCAN_CASE(4)
+    BBQ_SCAN_CASE(5)
+    BBQ_SCAN_CASE(6)
+    BBQ_SCAN_CASE(7)
+    BBQ_SCAN_CASE(8)
+    default:
+      return fail(BBQ_ERR_QUERY_BITS, "queryBits must be in 1..8");
+  }
+#undef BBQ_SCAN_CASE
+  return BBQ_OK;
+}
+
+// tiles [tile_first, tile_first + ntiles*tile_stride) step tile_stride, queries [0, nq)
+static int launch_scan(bbq_index* ix, int mode, ScanParams p, int64_t ntiles, cudaStream_t st) {
+  bbq_ctx* c = ix->ctx;
+  const int nb = (int)c->cfg.query_bits;
+  const int w4 = ix->row_bytes / 16, s4 = w4 | 1;
+  int qb = std::min(p.nq, 32);
+  auto smem_for = [&](int q) {
+    return (size_t)TILE_ROWS * s4 * 16 + (size_t)q * nb * w4 * 16 + (size_t)q * sizeof(bbqn::QueryTerms) +
+           (size_t)q * sizeof(float) + 16;
+  };
+  while (qb > 1 && smem_for(qb) > 160 * 1024) qb /= 2;
+  if (smem_for(qb) > 227 * 1024) return fail(BBQ_ERR_UNSUPPORTED, "dimension too large for the scan tile");
+  p.q_block = qb;
+  ProfScope prof(c, st, PROF_SCAN);
+  c->stats.scan_launches++;
+  dim3 grid((unsigned)ntiles, (unsigned)((p.nq + qb - 1) / qb));
+  if (mode == SCAN_DUMP) return launch_scan_nb<SCAN_DUMP>(c, nb, grid, smem_for(qb), st, p);
+  return launch_scan_nb<SCAN_FILTER>(c, nb, grid, smem_for(qb), st, p);
+}
+
+template <int MODE>
+static int launch_select(bbq_ctx* c, const SelectParams& p, uint32_t m_max, cudaStream_t st) {
+  uint32_t m2 = 2;
+  while (m2 < m_max || m2 < p.k) m2 <<= 1;
+  if (m2 > (uint32_t)SELECT_MAX) return fail(BBQ_ERR_UNSUPPORTED, "selection exceeds SELECT_MAX keys");
+  const size_t smem = (size_t)m2 * sizeof(uint64_t);
+  ProfScope prof(c, st, PROF_SELECT);
+  if (smem > 48 * 1024)
+    CU(cudaFuncSetAttribute(k_select<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LAUNCH(c, (k_select<MODE>), p.nq, SELECT_THREADS, smem, st, p, m2);
+  return BBQ_OK;
+}
+
+// K4 for nq queries already in device memory (row-major f32): fills ctx->planes / qterms (/qcodes,qcorr)
+static int quantize_queries(bbq_index* ix, const float* d_queries, int nq, cudaStream_t st) {
+  bbq_ctx* c = ix->ctx;
+  const int dim = (int)ix->dim, nb = (int)c->cfg.query_bits, words = ix->row_bytes / 4, code_ld = ix->row_bytes * 8;
+  TRY(c->qT.reserve((size_t)nq * dim * sizeof(float)));
+  TRY(c->qcodes.reserve((size_t)nq * code_ld));
+  TRY(c->qcorr.reserve((size_t)nq * 4 * sizeof(double)));
+  TRY(c->planes.reserve((size_t)nq * nb * words * sizeof(uint32_t)));
+  TRY(c->qterms.reserve((size_t)nq * sizeof(bbqn::QueryTerms)));
+  float* T = c->qT.as<float>();
+  ProfScope prof(c, st, PROF_QUANT);
+  dim3 grid((nq + 31) / 32, (dim + 31) / 32), block(32, 8);
+  LAUNCH(c, k_transpose, grid, block, 0, st, d_queries, (int64_t)nq, dim, T, (int64_t)nq);
+  if (c->cfg.similarity == BBQ_SIM_COSINE)
+    LAUNCH(c, k_normalize_T, (nq + 63) / 64, 64, 0, st, T, (int64_t)nq, (int64_t)nq, dim, 2);
+  LAUNCH(c, k_osq_query, (nq + 63) / 64, 64, 0, st, T, (int64_t)nq, nq, dim, ix->centroid, (int)c->cfg.similarity, nb,
+         c->cfg.lambda, (int)c->cfg.iters, c->qcodes.as<uint8_t>(), code_ld, c->qcorr.as<double>());
+  const int64_t total = (int64_t)nq * nb * words;
+  LAUNCH(c, k_query_planes, (unsigned)((total + 127) / 128), 128, 0, st, c->qcodes.as<uint8_t>(), code_ld,
+         c->qcorr.as<double>(), nq, nb, words, c->planes.as<uint32_t>(), c->qterms.as<bbqn::QueryTerms>());
+  return BBQ_OK;
+}
+
+static ScanParams base_scan_params(bbq_index* ix, int nq) {
+  bbq_ctx* c = ix->ctx;
+  ScanParams p{};
+  p.codes = ix->codes;
+  p.lower = ix->lower;
+  p.upper = ix->upper;
+  p.addc = ix->addc;
+  p.compsum = ix->compsum;
+  p.n = (int64_t)ix->n;
+  p.row_bytes = ix->row_bytes;
+  p.planes = c->planes.as<uint32_t>();
+  p.qterms = c->qterms.as<bbqn::QueryTerms>();
+  p.nq = nq;
+  p.dim = (double)ix->dim;
+  p.cdp = ix->cdp;
+  p.sim = (int)c->cfg.similarity;
+  p.one_bit_query = c->cfg.query_bits == 1 ? 1 : 0;
+  p.base = (uint32_t)ix->base;
+  p.tile_first = 0;
+  p.tile_stride = 1;
+  return p;
+}
+
+// Hierarchical deterministic merge of `lists` lists [lists][nq][k] held in (idx_a, score_a) into out.
+static int merge_lists(bbq_ctx* c, int32_t* idx_a, float* score_a, int32_t* idx_b, float* score_b, uint32_t lists,
+                       int nq, uint32_t k, int32_t* out_idx, float* out_score, cudaStream_t st) {
+  const uint32_t group = std::max<uint32_t>(2u, (uint32_t)SELECT_MAX / k);
+  while (true) {
+    const uint32_t ngroups = (lists + group - 1) / group;
+    for (uint32_t g = 0; g < ngroups; g++) {
+      const uint32_t l0 = g * group, ln = std::min(group, lists - l0);
+      SelectParams s{};
+      s.nq = nq;
+      s.k = k;
+      s.in_idx = idx_a + (size_t)l0 * nq * k;
+      s.in_score = score_a + (size_t)l0 * nq * k;
+      s.lists = ln;
+      s.k_in = k;
+      if (ngroups == 1) {
+        s.out_idx = out_idx;
+        s.out_score = out_score;
+      } else {
+        s.out_idx = idx_b + (size_t)g * nq * k;
+        s.out_score = score_b + (size_t)g * nq * k;
+      }
+      TRY(launch_select<SEL_PAIRS>(c, s, ln * k, st));
+    }
+    if (ngroups == 1) return BBQ_OK;
+    std::swap(idx_a, idx_b);
+    std::swap(score_a, score_b);
+    lists = ngroups;
+  }
+}
+
+// Exact chunked path: every chunk of <= SELECT_MAX rows is scored densely and selected; partial lists
+// are merged.  One chunk == the direct path for small indexes.
+static int search_exact_chunked(bbq_index* ix, int nq, uint32_t k, int32_t* d_out_idx, float* d_out_score,
+                                cudaStream_t st) {
+  bbq_ctx* c = ix->ctx;
+  const int64_t n = (int64_t)ix->n;
+  const int64_t chunk_rows = SELECT_MAX, chunk_tiles = chunk_rows / TILE_ROWS;
+  const int64_t ntiles = (n + TILE_ROWS - 1) / TILE_ROWS;
+  const uint32_t nchunks = (uint32_t)((n + chunk_rows - 1) / chunk_rows);
+  TRY(c->dump.reserve((size_t)nq * chunk_rows * sizeof(float)));
+  if (nchunks > 1) {
+    TRY(c->lists_a.reserve((size_t)nchunks * nq * k * (sizeof(int32_t) + sizeof(float))));
+    TRY(c->lists_b.reserve((size_t)nchunks * nq * k * (sizeof(int32_t) + sizeof(float))));
+  }
+  int32_t* la_idx = c->lists_a.as<int32_t>();
+  float* la_score = reinterpret_cast<float*>(la_idx + (size_t)nchunks * nq * k);
+  int32_t* lb_idx = c->lists_b.as<int32_t>();
+  float* lb_score = reinterpret_cast<float*>(lb_idx + (size_t)nchunks * nq * k);
+  for (uint32_t ch = 0; ch < nchunks; ch++) {
+    const int64_t t0 = (int64_t)ch * chunk_tiles, tn = std::min(chunk_tiles, ntiles - t0);
+    const int64_t rows_here = std::min(chunk_rows, n - t0 * TILE_ROWS);
+    ScanParams p = base_scan_params(ix, nq);
+    p.tile_first = t0;
+    p.dump = c->dump.as<float>();
+    p.dump_ld = chunk_rows;
+    TRY(launch_scan(ix, SCAN_DUMP, p, tn, st));
+    SelectParams s{};
+    s.nq = nq;
+    s.k = k;
+    s.scores = c->dump.as<float>();
+    s.ld = chunk_rows;
+    s.m = (uint32_t)rows_here;
+    s.tile_first = t0;
+    s.tile_stride = 1;
+    s.base = (uint32_t)ix->base;
+    if (nchunks == 1) {
+      s.out_idx = d_out_idx;
+      s.out_score = d_out_score;
+    } else {
+      s.out_idx = la_idx + (size_t)ch * nq * k;
+      s.out_score = la_score + (size_t)ch * nq * k;
+    }
+    TRY(launch_select<SEL_DENSE>(c, s, (uint32_t)rows_here, st));
+  }
+  if (nchunks > 1) TRY(merge_lists(c, la_idx, la_score, lb_idx, lb_score, nchunks, nq, k, d_out_idx, d_out_score, st));
+  return BBQ_OK;
+}
+
+// Sampled-threshold path: tau[q] = k-th best score over a strided sample of full tiles (a valid lower
+// bound of the final k-th best), then one filtered scan appends every row with score >= tau[q], then
+// the final selection.  *overflowed is set (after a sync) when a candidate list overflowed.
+static int search_filtered(bbq_index* ix, int nq, uint32_t k, int32_t* d_out_idx, float* d_out_score, cudaStream_t st,
+                           bool* overflowed) {
+  bbq_ctx* c = ix->ctx;
+  const int64_t n = (int64_t)ix->n;
+  const int64_t ntiles = (n + TILE_ROWS - 1) / TILE_ROWS, full_tiles = n / TILE_ROWS;
+  const int64_t stiles = std::min<int64_t>(SAMPLE_TILES, full_tiles);
+  const int64_t stride = std::max<int64_t>(1, full_tiles / stiles);
+  TRY(c->dump.reserve((size_t)nq * SELECT_MAX * sizeof(float)));
+  TRY(c->tau.reserve((size_t)nq * sizeof(float)));
+  TRY(c->cand.reserve((size_t)nq * CAND_CAP * sizeof(uint64_t)));
+  TRY(c->cand_cnt.reserve((size_t)(nq + 1) * sizeof(uint32_t)));
+  {
+    ScanParams p = base_scan_params(ix, nq);
+    p.tile_stride = stride;
+    p.dump = c->dump.as<float>();
+    p.dump_ld = SELECT_MAX;
+    TRY(launch_scan(ix, SCAN_DUMP, p, stiles, st));
+    SelectParams s{};
+    s.nq = nq;
+    s.k = k;
+    s.scores = c->dump.as<float>();
+    s.ld = SELECT_MAX;
+    s.m = (uint32_t)(stiles * TILE_ROWS);
+    s.tile_first = 0;
+    s.tile_stride = stride;
+    s.base = (uint32_t)ix->base;
+    s.tau_out = c->tau.as<float>();
+    TRY(launch_select<SEL_DENSE>(c, s, s.m, st));
+  }
+  uint32_t* cnt = c->cand_cnt.as<uint32_t>();
+  CU(cudaMemsetAsync(cnt, 0, (size_t)(nq + 1) * sizeof(uint32_t), st));
+  {
+    ScanParams p = base_scan_params(ix, nq);
+    p.tau = c->tau.as<float>();
+    p.cand = c->cand.as<uint64_t>();
+    p.cand_cnt = cnt;
+    p.cap = CAND_CAP;
+    p.overflow = cnt + nq;
+    TRY(launch_scan(ix, SCAN_FILTER, p, ntiles, st));
+  }
+  {
+    SelectParams s{};
+    s.nq = nq;
+    s.k = k;
+    s.keys = c->cand.as<uint64_t>();
+    s.cnt = cnt;
+    s.cap = CAND_CAP;
+    s.out_idx = d_out_idx;
+    s.out_score = d_out_score;
+    TRY(launch_select<SEL_KEYS>(c, s, CAND_CAP, st));
+  }
+  CU(cudaMemcpyAsync(c->h_flag, cnt, (size_t)(nq + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  *overflowed = c->h_flag[nq] != 0;
+  uint64_t tot = 0;
+  for (int q = 0; q < nq; q++) tot += c->h_flag[q];
+  c->stats.last_candidates = tot;
+  return BBQ_OK;
+}
+
+static int search_batch(bbq_index* ix, const float* d_queries, int nq, uint32_t k, int32_t* d_out_idx,
+                        float* d_out_score, cudaStream_t st) {
+  bbq_ctx* c = ix->ctx;
+  TRY(quantize_queries(ix, d_queries, nq, st));
+  int path = ((int64_t)ix->n <= SELECT_MAX) ? 0 : 1;
+  if (c->force_path == 2) path = 2;
+  if (c->force_path == 1 && (int64_t)ix->n >= TILE_ROWS) path = 1;
+  c->stats.last_overflow = 0;
+  if (path == 1) {
+    bool over = false;
+    TRY(search_filtered(ix, nq, k, d_out_idx, d_out_score, st, &over));
+    if (over) {
+      c->stats.last_overflow = 1;
+      path = 2;
+    }
+  }
+  if (path != 1) TRY(search_exact_chunked(ix, nq, k, d_out_idx, d_out_score, st));
+  c->stats.last_path = (uint32_t)path;
+  return BBQ_OK;
+}
+
+extern "C" int bbq_search_device(bbq_index* ix, const float* d_queries, uint32_t nq, uint32_t k, int32_t* d_out_idx,
+                                 float* d_out_score, void* stream) {
+  if (!ix) return fail(BBQ_ERR_NULL, "target vector set must not be null");
+  if (!d_queries || !d_out_idx || !d_out_score) return fail(BBQ_ERR_NULL, "query vector must not be null");
+  if (nq == 0 || k == 0) return BBQ_OK;
+  if (k > K_MAX) return fail(BBQ_ERR_UNSUPPORTED, "k > 4096 is not supported by the device top-k");
+  bbq_ctx* c = ix->ctx;
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  for (uint32_t q0 = 0; q0 < nq; q0 += QUERY_BATCH) {
+    const int nb = (int)std::min<uint32_t>(QUERY_BATCH, nq - q0);
+    TRY(search_batch(ix, d_queries + (size_t)q0 * ix->dim, nb, k, d_out_idx + (size_t)q0 * k,
+                     d_out_score + (size_t)q0 * k, st));
+  }
+  return BBQ_OK;
+}
+
+extern "C" int bbq_search(bbq_index* ix, const float* queries, uint32_t nq, int64_t k, int32_t* out_idx,
+                          float* out_score, uint32_t* out_count) {
+  if (out_count) *out_count = 0;
+  // src/binaryQuantizationFormat.ts:318-334
+  if (!queries) return fail(BBQ_ERR_NULL, "query vector must not be null");
+  if (!ix) return fail(BBQ_ERR_NULL, "target vector set must not be null");
+  if (k < 0) return fail(BBQ_ERR_NEGATIVE_K, "k must not be negative");
+  if (k == 0 || nq == 0) return BBQ_OK;
+  if (!out_idx || !out_score) return fail(BBQ_ERR_NULL, "output buffers must not be null");
+  bbq_ctx* c = ix->ctx;
+  // scalarQuantize validates the (normalised) query: optimizedScalarQuantizer.ts:138-148
+  for (uint32_t q = 0; q < nq; q++) {
+    const int s = validate_rows(queries + (size_t)q * ix->dim, 1, ix->dim, c->cfg.similarity == BBQ_SIM_COSINE);
+    if (s != BBQ_OK) {
+      g_err_vec = q;
+      return s;
+    }
+  }
+  const uint32_t kk = (uint32_t)std::min<int64_t>(k, (int64_t)ix->n);  // :385 k2 = min(k, vectorCount)
+  if (kk > K_MAX) return fail(BBQ_ERR_UNSUPPORTED, "k > 4096 is not supported by the device top-k");
+  CU(cudaSetDevice(c->device));
+  TRY(c->qrows.reserve((size_t)nq * ix->dim * sizeof(float)));
+  TRY(c->out_idx.reserve((size_t)nq * kk * sizeof(int32_t)));
+  TRY(c->out_score.reserve((size_t)nq * kk * sizeof(float)));
+  CU(cudaMemcpyAsync(c->qrows.p, queries, (size_t)nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  TRY(bbq_search_device(ix, c->qrows.as<float>(), nq, kk, c->out_idx.as<int32_t>(), c->out_score.as<float>(), c->stream));
+  // results are written with stride kk; the caller's rows have stride k
+  if ((int64_t)kk == k) {
+    CU(cudaMemcpyAsync(out_idx, c->out_idx.p, (size_t)nq * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(out_score, c->out_score.p, (size_t)nq * kk * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    CU(cudaMemcpy2DAsync(out_idx, (size_t)k * sizeof(int32_t), c->out_idx.p, (size_t)kk * sizeof(int32_t),
+                         (size_t)kk * sizeof(int32_t), nq, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpy2DAsync(out_score, (size_t)k * sizeof(float), c->out_score.p, (size_t)kk * sizeof(float),
+                         (size_t)kk * sizeof(float), nq, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  if (out_count) *out_count = kk;
+  return BBQ_OK;
+}
+
+extern "C" int bbq_merge_topk_device(bbq_ctx* c, const int32_t* d_idx, const float* d_score, uint32_t lists,
+                                     uint32_t nq, uint32_t k, int32_t* d_out_idx, float* d_out_score, void* stream) {
+  if (!c || !d_idx || !d_score || !d_out_idx || !d_out_score) return fail(BBQ_ERR_NULL, "null");
+  if (lists == 0 || nq == 0 || k == 0) return BBQ_OK;
+  if (k > K_MAX) return fail(BBQ_ERR_UNSUPPORTED, "k > 4096");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  const uint32_t group = std::max<uint32_t>(2u, (uint32_t)SELECT_MAX / k);
+  if (lists <= group) {
+    SelectParams s{};
+    s.nq = (int)nq;
+    s.k = k;
+    s.in_idx = d_idx;
+    s.in_score = d_score;
+    s.lists = lists;
+    s.k_in = k;
+    s.out_idx = d_out_idx;
+    s.out_score = d_out_score;
+    return launch_select<SEL_PAIRS>(c, s, lists * k, st);
+  }
+  // many shards: copy into scratch and merge hierarchically
+  const size_t cnt = (size_t)lists * nq * k;
+  TRY(c->lists_a.reserve(cnt * (sizeof(int32_t) + sizeof(float))));
+  TRY(c->lists_b.reserve(cnt * (sizeof(int32_t) + sizeof(float))));
+  int32_t* la_idx = c->lists_a.as<int32_t>();
+  float* la_score = reinterpret_cast<float*>(la_idx + cnt);
+  int32_t* lb_idx = c->lists_b.as<int32_t>();
+  float* lb_score = reinterpret_cast<float*>(lb_idx + cnt);
+  CU(cudaMemcpyAsync(la_idx, d_idx, cnt * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(la_score, d_score, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return merge_lists(c, la_idx, la_score, lb_idx, lb_score, lists, (int)nq, k, d_out_idx, d_out_score, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// parity / debug taps
+// ------------------------------------------------------------------------------------------------
+static int debug_prepare_query(bbq_index* ix, const float* query) {
+  if (!ix || !query) return fail(BBQ_ERR_NULL, "null");
+  bbq_ctx* c = ix->ctx;
+  CU(cudaSetDevice(c->device));
+  TRY(c->qrows.reserve((size_t)ix->dim * sizeof(float)));
+  CU(cudaMemcpyAsync(c->qrows.p, query, (size_t)ix->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  return quantize_queries(ix, c->qrows.as<float>(), 1, c->stream);
+}
+
+extern "C" int bbq_debug_quantize_query(bbq_index* ix, const float* query, uint8_t* codes, double* corr4) {
+  TRY(debug_prepare_query(ix, query));
+  bbq_ctx* c = ix->ctx;
+  if (codes) CU(cudaMemcpyAsync(codes, c->qcodes.p, ix->dim, cudaMemcpyDeviceToHost, c->stream));
+  if (corr4) CU(cudaMemcpyAsync(corr4, c->qcorr.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BBQ_OK;
+}
+
+static int debug_dense(bbq_index* ix, const float* query, int32_t* out_dots, float* out_scores) {
+  TRY(debug_prepare_query(ix, query));
+  bbq_ctx* c = ix->ctx;
+  const int64_t n = (int64_t)ix->n, ntiles = (n + TILE_ROWS - 1) / TILE_ROWS;
+  TRY(c->dump.reserve((size_t)ntiles * TILE_ROWS * sizeof(float)));
+  TRY(c->dots.reserve((size_t)n * sizeof(int32_t)));
+  ScanParams p = base_scan_params(ix, 1);
+  p.dump = c->dump.as<float>();
+  p.dump_ld = ntiles * TILE_ROWS;
+  p.dots = c->dots.as<int32_t>();
+  TRY(launch_scan(ix, SCAN_DUMP, p, ntiles, c->stream));
+  if (out_dots) CU(cudaMemcpyAsync(out_dots, c->dots.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (out_scores) CU(cudaMemcpyAsync(out_scores, c->dump.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BBQ_OK;
+}
+
+extern "C" int bbq_debug_qcdist(bbq_index* ix, const float* query, int32_t* out_dots) {
+  return debug_dense(ix, query, out_dots, nullptr);
+}
+extern "C" int bbq_debug_scores(bbq_index* ix, const float* query, float* out_scores) {
+  return debug_dense(ix, query, nullptr, out_scores);
+}

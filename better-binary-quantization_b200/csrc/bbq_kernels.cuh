@@ -1,0 +1,423 @@
+// bbq_kernels.cuh — sm_100a kernels of the brute-force quantized search path.
+//
+//   K5  k_osq_index      index-side OptimizedScalarQuantizer + MSB-first pack, SoA correctives
+//   K4  k_osq_query      query-side quantiser (COSINE: double normalisation), k_query_planes bit-planes
+//   K1  k_scan<NB,MODE>  4b x 1b scan: AND + POPC per query bit-plane, exact f64 corrective epilogue,
+//                        fused threshold filter (candidates) or score dump
+//   K3  k_select<MODE>   deterministic (score desc, row id asc) top-k: threshold / final / shard merge
+//
+// Reference lines each kernel replaces are cited at the kernel.  Compile with --fmad=false.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "bbq_numerics.cuh"
+
+namespace bbqk {
+
+constexpr int TILE_ROWS = 128;     // rows per scan tile == threads per scan CTA
+constexpr int SELECT_THREADS = 512;
+constexpr int SELECT_MAX = 16384;  // max keys one select CTA sorts (128 KB of shared memory)
+
+// ------------------------------------------------------------------------------------------------
+// Staging: row-major f32 rows -> transposed scratch T[dim][ld] so that one thread per vector walks its
+// components with coalesced loads (thread t reads T[i*ld + t]).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_transpose(const float* __restrict__ rows, int64_t nrows, int dim, float* __restrict__ T,
+                            int64_t ld) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int64_t r = r0 + j;
+    const int c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < nrows && c < dim) ? rows[r * dim + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j;
+    const int64_t r = r0 + threadIdx.x;
+    if (c < dim && r < nrows) T[(int64_t)c * ld + r] = tile[threadIdx.x][j];
+  }
+}
+
+struct TAcc {  // component accessor over the transposed scratch
+  const float* p;
+  int64_t ld;
+  __device__ __forceinline__ float operator()(int i) const { return p[(int64_t)i * ld]; }
+};
+struct CAcc {  // centroid accessor (same address across the warp: one broadcast transaction)
+  const float* p;
+  __device__ __forceinline__ float operator()(int i) const { return __ldg(p + i); }
+};
+
+// normalizeVector, src/vectorOperations.ts:11-34, `times` times in place (queries: twice,
+// src/binaryQuantizationFormat.ts:337 and :279).  One thread per vector, sequential f64 sum.
+__global__ void k_normalize_T(float* __restrict__ T, int64_t ld, int64_t nrows, int dim, int times) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nrows) return;
+  float* col = T + t;
+  for (int rep = 0; rep < times; rep++) {
+    TAcc v{col, ld};
+    const double n = bbqn::l2norm_seq(v, dim);
+    if (n == 0) {
+      for (int i = 0; i < dim; i++) col[(int64_t)i * ld] = 0.0f;
+    } else {
+      for (int i = 0; i < dim; i++) col[(int64_t)i * ld] = (float)((double)col[(int64_t)i * ld] / n);
+    }
+  }
+}
+
+// computeCentroid, src/vectorOperations.ts:126-163: centroid = copy(V[0]); for j>=1: c_i = f32(c_i + V[j]_i)
+// strictly in row order.  One thread per component walks the chunk's rows sequentially.
+__global__ void k_centroid_accum(const float* __restrict__ T, int64_t ld, int64_t nrows, int dim,
+                                 float* __restrict__ acc, int first_chunk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dim) return;
+  const float* row = T + (int64_t)i * ld;
+  int64_t t = 0;
+  float c;
+  if (first_chunk) {
+    c = row[0];
+    t = 1;
+  } else {
+    c = acc[i];
+  }
+  for (; t < nrows; t++) c = (float)((double)c + (double)row[t]);
+  acc[i] = c;
+}
+__global__ void k_centroid_finish(float* __restrict__ acc, int dim, double n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < dim) acc[i] = (float)((double)acc[i] / n);
+}
+// getCentroidDP(undefined) = centroid . centroid, src/binaryQuantizationFormat.ts:113-121 (f64, sequential)
+__global__ void k_centroid_dp(const float* __restrict__ c, int dim, double* __restrict__ out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < dim; i++) s += (double)c[i] * (double)c[i];
+    *out = s;
+  }
+}
+
+// K5: scalarQuantize(indexBits = 1) + packAsBinary, src/optimizedScalarQuantizer.ts:108-227,420-446,
+// driven as src/binaryQuantizationFormat.ts:221-249 does.  One thread per vector; the packed row is
+// written MSB-first (dim 8j+t -> bit 7-t of byte j), zero padded to row_bytes (a multiple of 16).
+__global__ void k_osq_index(const float* __restrict__ T, int64_t ld, int64_t nrows, int dim,
+                            const float* __restrict__ centroid, int sim, double lambda, int iters,
+                            uint8_t* __restrict__ codes, int row_bytes, int64_t row0,
+                            double* __restrict__ lower, double* __restrict__ upper,
+                            double* __restrict__ addc, uint32_t* __restrict__ compsum) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nrows) return;
+  TAcc v{T + t, ld};
+  CAcc c{centroid};
+  const bbqn::OsqResult r = bbqn::osq_interval(v, c, dim, 1, sim, lambda, iters);
+  uint4* out = reinterpret_cast<uint4*>(codes + (row0 + t) * (int64_t)row_bytes);
+  uint32_t w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u, cur = 0u;
+  int nout = 0;
+  const double qsum = bbqn::osq_codes(v, c, dim, 1, r.lower, r.upper, [&](int i, uint8_t q) {
+    cur |= (uint32_t)q << (8 * ((i >> 3) & 3) + 7 - (i & 7));  // little-endian word of MSB-first bytes
+    if ((i & 31) == 31) {
+      const int s = (i >> 5) & 3;
+      if (s == 0) w0 = cur;
+      else if (s == 1) w1 = cur;
+      else if (s == 2) w2 = cur;
+      else {
+        out[nout++] = make_uint4(w0, w1, w2, cur);
+        w0 = w1 = w2 = 0u;
+      }
+      cur = 0u;
+    }
+  });
+  if (dim & 31) {  // partial last word
+    const int s = (dim >> 5) & 3;
+    if (s == 0) w0 = cur;
+    else if (s == 1) w1 = cur;
+    else if (s == 2) w2 = cur;
+    else w3 = cur;
+  }
+  if (dim & 127) out[nout++] = make_uint4(w0, w1, w2, w3);
+  for (; nout < row_bytes / 16; nout++) out[nout] = make_uint4(0u, 0u, 0u, 0u);
+  lower[row0 + t] = r.lower;
+  upper[row0 + t] = r.upper;
+  addc[row0 + t] = r.additional;
+  compsum[row0 + t] = (uint32_t)qsum;
+}
+
+// K4: quantizeQueryVector, src/binaryQuantizationFormat.ts:271-299 (normalisation done by k_normalize_T).
+// qcodes: [nq][code_ld] unpacked u8; qcorr: [nq][4] = lower, upper, additional, componentSum.
+__global__ void k_osq_query(const float* __restrict__ T, int64_t ld, int nq, int dim,
+                            const float* __restrict__ centroid, int sim, int bits, double lambda, int iters,
+                            uint8_t* __restrict__ qcodes, int code_ld, double* __restrict__ qcorr) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nq) return;
+  TAcc v{T + t, ld};
+  CAcc c{centroid};
+  const bbqn::OsqResult r = bbqn::osq_interval(v, c, dim, bits, sim, lambda, iters);
+  uint8_t* out = qcodes + (int64_t)t * code_ld;
+  const double qsum = bbqn::osq_codes(v, c, dim, bits, r.lower, r.upper, [&](int i, uint8_t q) { out[i] = q; });
+  for (int i = dim; i < code_ld; i++) out[i] = 0;
+  qcorr[4 * t + 0] = r.lower;
+  qcorr[4 * t + 1] = r.upper;
+  qcorr[4 * t + 2] = r.additional;
+  qcorr[4 * t + 3] = qsum;
+}
+
+// Query bit-planes in the index's bit order: plane b, word w holds bit b of codes[32w .. 32w+31],
+// dim 8j+t at bit 7-t of byte j (so `plane & row` pairs equal dims).  Layout [nq][nb][words].
+// Also hoists the per-query score terms (src/batchDotProduct.ts:497-502,573-578).
+__global__ void k_query_planes(const uint8_t* __restrict__ qcodes, int code_ld, const double* __restrict__ qcorr,
+                               int nq, int nb, int words, uint32_t* __restrict__ planes,
+                               bbqn::QueryTerms* __restrict__ qterms) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)nq * nb * words;
+  if (g < total) {
+    const int w = (int)(g % words);
+    const int b = (int)((g / words) % nb);
+    const int q = (int)(g / ((int64_t)words * nb));
+    const uint8_t* cd = qcodes + (int64_t)q * code_ld + 32 * w;
+    uint32_t word = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int t = 0; t < 8; t++) word |= (uint32_t)((cd[8 * j + t] >> b) & 1) << (8 * j + 7 - t);
+    planes[g] = word;
+  }
+  if (g < nq) {
+    const double* c = qcorr + 4 * g;
+    qterms[g] = bbqn::make_query_terms(c[0], c[1], c[2], c[3], nb);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: the scan.  Replaces createDirectPackedBuffer + computeBatchFourBitDotProductDirectPacked +
+// computeBatchFourBitSimilarityScores (+ the 1-bit pair) — src/batchDotProduct.ts:420-436,22-49,478-617,
+// src/utils/computeBatchFourBitDotProductDirectPacked.ts:10-53 — and the admission test of the heap
+// loop, src/binaryQuantizationFormat.ts:383-400.
+//
+// One CTA = one tile of 128 index rows x one block of queries.  Rows are staged once into shared
+// memory with 128-bit coalesced loads (padded stride: conflict-free LDS.128 per thread-row); query
+// bit-planes sit in shared memory and are read as warp broadcasts.  dot = sum_b 2^b popc(plane_b & row)
+// is the reference's integer exactly; the epilogue replays the f64 formula and rounds to f32.
+// ------------------------------------------------------------------------------------------------
+enum { SCAN_DUMP = 0, SCAN_FILTER = 1 };
+
+struct ScanParams {
+  const uint8_t* codes;   // [n][row_bytes]
+  const double* lower;
+  const double* upper;
+  const double* addc;
+  const uint32_t* compsum;
+  int64_t n;
+  int row_bytes;          // multiple of 16
+  const uint32_t* planes; // [nq][nb][row_bytes/4]
+  const bbqn::QueryTerms* qterms;
+  int nq;
+  int q_block;            // queries per CTA (blockIdx.y)
+  double dim;
+  double cdp;
+  int sim;
+  int one_bit_query;
+  uint32_t base;          // global id of row 0
+  // tile mapping: CTA x handles tile (tile_first + blockIdx.x * tile_stride)
+  int64_t tile_first;
+  int64_t tile_stride;
+  // SCAN_DUMP: scores[q * dump_ld + blockIdx.x*128 + tid]; optional dots for query 0
+  float* dump;
+  int64_t dump_ld;
+  int32_t* dots;
+  // SCAN_FILTER
+  const float* tau;       // [nq]
+  uint64_t* cand;         // [nq][cap]
+  uint32_t* cand_cnt;     // [nq]
+  uint32_t cap;
+  uint32_t* overflow;
+};
+
+template <int NB, int MODE>
+__global__ void __launch_bounds__(TILE_ROWS) k_scan(const ScanParams p) {
+  extern __shared__ uint4 smem4[];
+  const int w4 = p.row_bytes >> 4;   // 16-byte chunks per row
+  const int s4 = w4 | 1;             // padded row stride (odd => conflict-free LDS.128)
+  uint4* rows_s = smem4;                                   // [128][s4]
+  uint4* planes_s = rows_s + TILE_ROWS * s4;               // [q_block][NB][w4]
+  bbqn::QueryTerms* qt_s = reinterpret_cast<bbqn::QueryTerms*>(planes_s + (size_t)p.q_block * NB * w4);
+  float* tau_s = reinterpret_cast<float*>(qt_s + p.q_block);
+
+  const int tid = threadIdx.x;
+  const int64_t tile = p.tile_first + (int64_t)blockIdx.x * p.tile_stride;
+  const int64_t row0 = tile * TILE_ROWS;
+  const int q0 = blockIdx.y * p.q_block;
+  const int nql = min(p.q_block, p.nq - q0);
+
+  // stage the tile's rows (contiguous in HBM): 128-bit coalesced loads
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.codes + row0 * (int64_t)p.row_bytes);
+    const int64_t rows_here = min((int64_t)TILE_ROWS, p.n - row0);
+    const int total = TILE_ROWS * w4;
+    for (int c = tid; c < total; c += TILE_ROWS) {
+      const int r = c / w4, j = c - r * w4;
+      rows_s[r * s4 + j] = (r < rows_here) ? __ldg(src + c) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    const uint4* psrc = reinterpret_cast<const uint4*>(p.planes) + (size_t)q0 * NB * w4;
+    const int ptotal = nql * NB * w4;
+    for (int c = tid; c < ptotal; c += TILE_ROWS) planes_s[c] = __ldg(psrc + c);
+    for (int c = tid; c < nql; c += TILE_ROWS) {
+      qt_s[c] = p.qterms[q0 + c];
+      if (MODE == SCAN_FILTER) tau_s[c] = p.tau[q0 + c];
+    }
+  }
+  const int64_t row = row0 + tid;
+  const bool valid = row < p.n;
+  double ax = 0, lx = 0, addx = 0, x1 = 0;
+  if (valid) {
+    ax = p.lower[row];
+    lx = p.upper[row] - ax;  // `indexCorrections.upperInterval - ax`, src/batchDotProduct.ts:499,575
+    addx = p.addc[row];
+    x1 = (double)p.compsum[row];
+  }
+  __syncthreads();
+
+  const uint4* myrow = rows_s + tid * s4;
+  const uint32_t id = p.base + (uint32_t)row;
+  for (int ql = 0; ql < nql; ql++) {
+    int acc[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) acc[b] = 0;
+    const uint4* pl = planes_s + (size_t)ql * NB * w4;
+    for (int j = 0; j < w4; j++) {
+      const uint4 x = myrow[j];
+#pragma unroll
+      for (int b = 0; b < NB; b++) {
+        const uint4 q = pl[b * w4 + j];
+        acc[b] += __popc(x.x & q.x) + __popc(x.y & q.y) + __popc(x.z & q.z) + __popc(x.w & q.w);
+      }
+    }
+    int dot = 0;
+#pragma unroll
+    for (int b = 0; b < NB; b++) dot += acc[b] << b;
+    const float score = bbqn::score_f32((double)dot, ax, lx, addx, x1, qt_s[ql], p.dim, p.cdp, p.sim,
+                                        p.one_bit_query != 0);
+    const int q = q0 + ql;
+    if (MODE == SCAN_DUMP) {
+      if (valid) {
+        p.dump[(int64_t)q * p.dump_ld + (int64_t)blockIdx.x * TILE_ROWS + tid] = score;
+        if (p.dots != nullptr && q == 0) p.dots[row] = dot;
+      }
+    } else {
+      if (valid && score >= tau_s[ql]) {
+        const uint32_t pos = atomicAdd(p.cand_cnt + q, 1u);
+        if (pos < p.cap) p.cand[(size_t)q * p.cap + pos] = bbqn::topk_key(score, id);
+        else *p.overflow = 1u;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: deterministic selection.  One CTA per query sorts up to SELECT_MAX 64-bit keys
+// (ordered f32 score << 32 | ~row id) in shared memory (bitonic, descending) and emits the k best —
+// the canonical form of the MinHeap loop, src/binaryQuantizationFormat.ts:383-411 / src/minHeap.ts.
+// ------------------------------------------------------------------------------------------------
+enum { SEL_DENSE = 0, SEL_KEYS = 1, SEL_PAIRS = 2 };
+
+struct SelectParams {
+  int nq;
+  uint32_t k;
+  // SEL_DENSE: scores[q*ld + i], i < m; id = base + (tile_first + (i/128)*tile_stride)*128 + i%128
+  const float* scores;
+  int64_t ld;
+  uint32_t m;
+  int64_t tile_first;
+  int64_t tile_stride;
+  uint32_t base;
+  // SEL_KEYS: keys[q*cap + i], i < min(cnt[q], cap)
+  const uint64_t* keys;
+  const uint32_t* cnt;
+  uint32_t cap;
+  // SEL_PAIRS: lists x [nq][k_in] idx/score; idx < 0 = empty slot
+  const int32_t* in_idx;
+  const float* in_score;
+  uint32_t lists;
+  uint32_t k_in;
+  // outputs (any may be null)
+  float* tau_out;     // [nq]: score of the k-th best, -inf if fewer than k keys
+  int32_t* out_idx;   // [nq][k]
+  float* out_score;   // [nq][k]
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectParams p, uint32_t m2_max) {
+  extern __shared__ uint64_t keys_s[];
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x;
+  uint32_t m;
+  if (MODE == SEL_DENSE) m = p.m;
+  else if (MODE == SEL_KEYS) m = min(p.cnt[q], p.cap);
+  else m = p.lists * p.k_in;
+  // sort size: smallest power of two covering the keys and the k outputs (block-uniform)
+  uint32_t m2 = 2;
+  while (m2 < m || m2 < p.k) m2 <<= 1;
+  m2 = min(m2, m2_max);
+  for (uint32_t i = tid; i < m2; i += SELECT_THREADS) {
+    uint64_t key = 0ull;
+    if (i < m) {
+      if (MODE == SEL_DENSE) {
+        const uint32_t id = p.base + (uint32_t)((p.tile_first + (int64_t)(i / TILE_ROWS) * p.tile_stride) * TILE_ROWS + (i % TILE_ROWS));
+        key = bbqn::topk_key(p.scores[(int64_t)q * p.ld + i], id);
+      } else if (MODE == SEL_KEYS) {
+        key = p.keys[(size_t)q * p.cap + i];
+      } else {
+        const uint32_t l = i / p.k_in, j = i - l * p.k_in;
+        const size_t off = ((size_t)l * p.nq + q) * p.k_in + j;
+        const int32_t idx = p.in_idx[off];
+        key = idx < 0 ? 0ull : bbqn::topk_key(p.in_score[off], (uint32_t)idx);
+      }
+    }
+    keys_s[i] = key;
+  }
+  for (uint32_t size = 2; size <= m2; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (uint32_t t = tid; t < (m2 >> 1); t += SELECT_THREADS) {
+        const uint32_t i = 2 * t - (t & (stride - 1));
+        const uint32_t j = i + stride;
+        const uint64_t a = keys_s[i], b = keys_s[j];
+        const bool desc = (i & size) == 0;
+        if (desc ? (a < b) : (a > b)) {
+          keys_s[i] = b;
+          keys_s[j] = a;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (p.tau_out != nullptr && tid == 0) {
+    float t = -INFINITY;
+    if (p.k >= 1 && p.k <= m2) {
+      const uint64_t key = keys_s[p.k - 1];
+      if (key != 0ull) {
+        const float s = bbqn::topk_key_score(key);
+        if (s == s) t = s;
+      }
+    }
+    p.tau_out[q] = t;
+  }
+  if (p.out_idx != nullptr) {
+    for (uint32_t j = tid; j < p.k; j += SELECT_THREADS) {
+      const uint64_t key = j < m2 ? keys_s[j] : 0ull;
+      const size_t off = (size_t)q * p.k + j;
+      if (key == 0ull) {
+        p.out_idx[off] = -1;
+        p.out_score[off] = -INFINITY;
+      } else {
+        p.out_idx[off] = (int32_t)bbqn::topk_key_id(key);
+        p.out_score[off] = bbqn::topk_key_score(key);
+      }
+    }
+  }
+}
+
+// Input screening for the host build path (reference: binaryQuantizationFormat.ts:196-211) is done on
+// the host before upload; device-resident builds are the caller's responsibility.
+
+}  // namespace bbqk

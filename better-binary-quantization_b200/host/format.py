@@ -1,0 +1,300 @@
+"""Host-side mirror of the reference's operator interface for the search path (Python stand-in for the
+TypeScript layer, which cannot run here: no Node in the image — see INTEGRATION.md for the real TS/N-API
+binding).  Same names, argument meaning and error behaviour as the reference:
+
+  BinaryQuantizationFormat            src/binaryQuantizationFormat.ts:132-412
+    .quantizeVectors(vectors)         :165-263  -> {quantizedVectors, queryQuantizer}
+    .quantizeQueryVector(q, centroid) :271-299
+    .searchNearestNeighbors(q, t, k)  :308-412  -> [{index, score}] descending
+  BinarizedByteVectorValues           src/types.ts:32-49 (an opaque device handle here)
+  VectorSimilarityFunction            src/types.ts:9-13
+
+Everything numeric happens in libbbq_b200.so on the GPU; this file only marshals and maps errors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .. import _native
+
+QUERY_BITS = 4   # src/constants.ts:9
+INDEX_BITS = 1   # src/constants.ts:14
+
+
+class VectorSimilarityFunction:
+    EUCLIDEAN = "EUCLIDEAN"
+    COSINE = "COSINE"
+    MAXIMUM_INNER_PRODUCT = "MAXIMUM_INNER_PRODUCT"
+
+
+_SIM_CODE = {"EUCLIDEAN": 0, "COSINE": 1, "MAXIMUM_INNER_PRODUCT": 2}
+
+# status -> the reference's message (file:line in include/bbq_b200.h)
+def _message(status: int, vec: int, pos: int, what: str) -> str:
+    return {
+        1: "queryBits必须在1-8之间",
+        2: "indexBits必须在1-8之间",
+        3: "向量集合不能为空",
+        7: "k值不能为负数",
+    }.get(status) or {
+        ("build", 5): f"向量 {vec} 位置 {pos} 包含NaN值",
+        ("build", 6): f"向量 {vec} 位置 {pos} 包含Infinity值",
+        ("search", 5): f"向量位置 {pos} 包含NaN值",
+        ("search", 6): f"向量位置 {pos} 包含Infinity值",
+        ("search", 4): "查询向量维度与目标向量维度不匹配",
+    }.get((what, status)) or _native.load().bbq_last_error().decode()
+
+
+class BbqError(Exception):
+    """`throw new Error(msg)` of the reference; .status is the C-ABI status code."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(message)
+        self.status = status
+
+
+def _check(status: int, what: str = ""):
+    if status != 0:
+        v, p = C.c_int64(-1), C.c_int64(-1)
+        _native.load().bbq_last_error_pos(C.byref(v), C.byref(p))
+        raise BbqError(status, _message(status, v.value, p.value, what))
+
+
+def _as_matrix(vectors) -> np.ndarray:
+    """Float32Array[] -> contiguous [n, dim] f32; ragged input raises the reference's message (:190-192)."""
+    if isinstance(vectors, np.ndarray) and vectors.ndim == 2:
+        return np.ascontiguousarray(vectors, dtype=np.float32)
+    rows = [np.asarray(v, dtype=np.float32).ravel() for v in vectors]
+    if not rows:
+        return np.empty((0, 0), np.float32)
+    d = rows[0].size
+    for i, r in enumerate(rows[1:], 1):
+        if r.size != d:
+            raise BbqError(4, f"向量 {i} 维度 {r.size} 与第一个向量维度 {d} 不匹配")
+    return np.ascontiguousarray(np.stack(rows), dtype=np.float32)
+
+
+class BinarizedByteVectorValues:
+    """Device-resident index shard.  size()/dimension()/getCentroid() answer from cached host metadata;
+    vectorValue()/getCorrectiveTerms() do a lazy device->host copy (cold path)."""
+
+    def __init__(self, fmt: "BinaryQuantizationFormat", handle):
+        self._fmt = fmt
+        self._h = handle
+        L = _native.load()
+        self._n = int(L.bbq_index_size(handle))
+        self._dim = int(L.bbq_index_dim(handle))
+        c = np.empty(self._dim, np.float32)
+        cdp = C.c_double()
+        _check(L.bbq_index_centroid(handle, c.ctypes.data, C.byref(cdp)))
+        self._centroid, self._cdp = c, cdp.value
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                _native.load().bbq_index_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def dimension(self) -> int:
+        return self._dim
+
+    def size(self) -> int:
+        return self._n
+
+    def getCentroid(self) -> np.ndarray:
+        return self._centroid
+
+    def getCentroidDP(self, queryVector=None) -> float:
+        if queryVector is not None:  # src/binaryQuantizationFormat.ts:113-117 (not used by search)
+            q = np.asarray(queryVector, np.float32).astype(np.float64)
+            s = 0.0
+            for a, b in zip(q, self._centroid.astype(np.float64)):
+                s += a * b
+            return s
+        return self._cdp
+
+    def _export(self, ord_: int, count: int = 1):
+        if ord_ < 0 or ord_ + count > self._n:
+            raise BbqError(10, f"向量索引 {ord_} 不存在")
+        p = (self._dim + 7) // 8
+        packed = np.empty((count, p), np.uint8)
+        corr = np.empty((count, 4), np.float64)
+        _check(_native.load().bbq_index_export(self._h, ord_, count, packed.ctypes.data, corr.ctypes.data))
+        return packed, corr
+
+    def vectorValue(self, ord_: int) -> np.ndarray:
+        return self._export(ord_)[0][0]
+
+    def getUnpackedVector(self, ord_: int) -> np.ndarray:
+        return np.unpackbits(self.vectorValue(ord_))[: self._dim]
+
+    def getCorrectiveTerms(self, ord_: int) -> dict:
+        c = self._export(ord_)[1][0]
+        return {"lowerInterval": c[0], "upperInterval": c[1], "additionalCorrection": c[2],
+                "quantizedComponentSum": c[3]}
+
+    def exportAll(self):
+        """(packed u8[n, ceil(dim/8)], corr f64[n,4]) — test/diagnostic convenience."""
+        return self._export(0, self._n)
+
+
+class BinaryQuantizationFormat:
+    def __init__(self, config: dict, device: int = -1):
+        q = config.get("quantizer") or {}
+        self.config = {"queryBits": QUERY_BITS, "indexBits": INDEX_BITS, **config}
+        cfg = _native.BbqConfig()
+        cfg.query_bits = int(self.config["queryBits"]) if 0 <= self.config["queryBits"] < 2**31 else 0
+        cfg.index_bits = int(self.config["indexBits"]) if 0 <= self.config["indexBits"] < 2**31 else 0
+        # src/optimizedScalarQuantizer.ts:48-50 defaults
+        self._sim = q.get("similarityFunction", VectorSimilarityFunction.EUCLIDEAN)
+        cfg.similarity = _SIM_CODE[self._sim]
+        cfg.lambda_ = float(q.get("lambda", 0.1))
+        cfg.iters = int(q.get("iters", 5))
+        cfg.device = device
+        self._ctx = C.c_void_p()
+        _check(_native.load().bbq_create(C.byref(cfg), C.byref(self._ctx)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ctx", None):
+                _native.load().bbq_destroy(self._ctx)
+                self._ctx = None
+        except Exception:
+            pass
+
+    def getConfig(self) -> dict:
+        return dict(self.config)
+
+    # -- index build ----------------------------------------------------------------------------------
+    def quantizeVectors(self, vectors, centroid: Optional[np.ndarray] = None) -> dict:
+        if vectors is None or len(vectors) == 0:
+            raise BbqError(3, "向量集合不能为空")
+        m = _as_matrix(vectors)
+        h = C.c_void_p()
+        cen = np.ascontiguousarray(centroid, np.float32) if centroid is not None else None
+        _check(_native.load().bbq_index_build(self._ctx, m.ctypes.data, m.shape[0], m.shape[1],
+                                              cen.ctypes.data if cen is not None else None, C.byref(h)), "build")
+        return {"quantizedVectors": BinarizedByteVectorValues(self, h), "queryQuantizer": self}
+
+    def quantizeVectorsDevice(self, d_rows_ptr: int, n: int, dim: int, centroid: Optional[np.ndarray] = None):
+        """Rows already in device memory (e.g. a torch tensor's data_ptr())."""
+        h = C.c_void_p()
+        cen = np.ascontiguousarray(centroid, np.float32) if centroid is not None else None
+        _check(_native.load().bbq_index_build_device(self._ctx, d_rows_ptr, n, dim,
+                                                     cen.ctypes.data if cen is not None else None, C.byref(h)), "build")
+        return {"quantizedVectors": BinarizedByteVectorValues(self, h), "queryQuantizer": self}
+
+    def reserveIndex(self, capacity: int, dim: int, centroid) -> BinarizedByteVectorValues:
+        """Streaming build (bbq_index_reserve): explicit centroid, rows appended chunk by chunk."""
+        cen = np.ascontiguousarray(centroid, np.float32)
+        h = C.c_void_p()
+        _check(_native.load().bbq_index_reserve(self._ctx, capacity, dim, cen.ctypes.data, C.byref(h)), "build")
+        return BinarizedByteVectorValues(self, h)
+
+    def appendRows(self, targetVectors: BinarizedByteVectorValues, rows=None, d_rows_ptr: int = 0, n: int = 0):
+        L = _native.load()
+        if rows is not None:
+            m = _as_matrix(rows)
+            _check(L.bbq_index_append(targetVectors._h, m.ctypes.data, m.shape[0]), "build")
+        else:
+            _check(L.bbq_index_append_device(targetVectors._h, d_rows_ptr, n), "build")
+        targetVectors._n = int(L.bbq_index_size(targetVectors._h))
+
+    def adoptQuantized(self, packed, corr4, centroid) -> BinarizedByteVectorValues:
+        """Index quantised elsewhere (e.g. by the reference): bbq_index_from_quantized."""
+        packed = np.ascontiguousarray(packed, np.uint8)
+        corr4 = np.ascontiguousarray(corr4, np.float64)
+        centroid = np.ascontiguousarray(centroid, np.float32)
+        h = C.c_void_p()
+        _check(_native.load().bbq_index_from_quantized(self._ctx, packed.ctypes.data, corr4.ctypes.data,
+                                                       centroid.ctypes.data, packed.shape[0], centroid.size,
+                                                       C.byref(h)), "build")
+        return BinarizedByteVectorValues(self, h)
+
+    # -- query side -------------------------------------------------------------------------------------
+    def quantizeQueryVector(self, queryVector, targetVectors: BinarizedByteVectorValues) -> dict:
+        """The reference signature takes the centroid; here the centroid lives with the device index, so the
+        index handle is passed instead.  NOTE: as in searchNearestNeighbors (:337 + :279) a COSINE query is
+        normalised twice."""
+        q = np.ascontiguousarray(queryVector, np.float32)
+        codes = np.empty(q.size, np.uint8)
+        corr = np.empty(4, np.float64)
+        _check(_native.load().bbq_debug_quantize_query(targetVectors._h, q.ctypes.data, codes.ctypes.data,
+                                                       corr.ctypes.data), "search")
+        return {"quantizedQuery": codes,
+                "queryCorrections": {"lowerInterval": corr[0], "upperInterval": corr[1],
+                                     "additionalCorrection": corr[2], "quantizedComponentSum": corr[3]}}
+
+    # -- search -----------------------------------------------------------------------------------------
+    def searchNearestNeighbors(self, queryVector, targetVectors: BinarizedByteVectorValues, k: int) -> List[dict]:
+        if queryVector is None:
+            raise BbqError(8, "查询向量不能为空")
+        if targetVectors is None:
+            raise BbqError(8, "目标向量集合不能为空")
+        if k < 0:
+            raise BbqError(7, "k值不能为负数")
+        q = np.ascontiguousarray(queryVector, np.float32).ravel()
+        if q.size != targetVectors.dimension():
+            raise BbqError(4, "查询向量维度与目标向量维度不匹配")
+        idx, sc = self.searchBatch(q[None, :], targetVectors, k)
+        return [{"index": int(i), "score": float(s)} for i, s in zip(idx[0], sc[0])]
+
+    def searchBatch(self, queries, targetVectors: BinarizedByteVectorValues, k: int):
+        """Additive batched entry: row i == searchNearestNeighbors(queries[i]).
+        -> (idx i32[nq, min(k,n)], score f32[nq, min(k,n)])"""
+        if k < 0:
+            raise BbqError(7, "k值不能为负数")
+        qs = np.ascontiguousarray(queries, np.float32)
+        if qs.ndim != 2 or qs.shape[1] != targetVectors.dimension():
+            raise BbqError(4, "查询向量维度与目标向量维度不匹配")
+        nq = qs.shape[0]
+        kk = min(k, targetVectors.size())
+        idx = np.empty((nq, max(k, 1)), np.int32)
+        sc = np.empty((nq, max(k, 1)), np.float32)
+        cnt = C.c_uint32(0)
+        _check(_native.load().bbq_search(targetVectors._h, qs.ctypes.data, nq, k, idx.ctypes.data, sc.ctypes.data,
+                                         C.byref(cnt)), "search")
+        assert cnt.value == (kk if nq else 0) or k == 0
+        return idx[:, :cnt.value].copy(), sc[:, :cnt.value].copy()
+
+    # -- parity taps (tests) ------------------------------------------------------------------------------
+    def debugQcDist(self, queryVector, targetVectors: BinarizedByteVectorValues) -> np.ndarray:
+        q = np.ascontiguousarray(queryVector, np.float32)
+        out = np.empty(targetVectors.size(), np.int32)
+        _check(_native.load().bbq_debug_qcdist(targetVectors._h, q.ctypes.data, out.ctypes.data), "search")
+        return out
+
+    def debugScores(self, queryVector, targetVectors: BinarizedByteVectorValues) -> np.ndarray:
+        q = np.ascontiguousarray(queryVector, np.float32)
+        out = np.empty(targetVectors.size(), np.float32)
+        _check(_native.load().bbq_debug_scores(targetVectors._h, q.ctypes.data, out.ctypes.data), "search")
+        return out
+
+    def stats(self) -> dict:
+        s = _native.BbqStats()
+        _check(_native.load().bbq_get_stats(self._ctx, C.byref(s)))
+        return {"kernel_launches": s.kernel_launches, "last_candidates": s.last_candidates,
+                "last_path": s.last_path, "last_overflow": s.last_overflow, "scan_launches": s.scan_launches,
+                "scan_ms": s.scan_ms, "quantize_ms": s.quantize_ms, "select_ms": s.select_ms}
+
+    def setProfiling(self, enabled: bool):
+        _check(_native.load().bbq_set_profiling(self._ctx, 1 if enabled else 0))
+
+    def resetProfiling(self):
+        _check(_native.load().bbq_reset_profiling(self._ctx))
+
+    # -- device-resident entry points (plumbing for sharded search: torch tensors' data_ptr()) ------------
+    def searchDevice(self, d_queries_ptr: int, nq: int, targetVectors: BinarizedByteVectorValues, k: int,
+                     d_out_idx_ptr: int, d_out_score_ptr: int, stream: int = 0):
+        _check(_native.load().bbq_search_device(targetVectors._h, d_queries_ptr, nq, k, d_out_idx_ptr,
+                                                d_out_score_ptr, stream or None), "search")
+
+    def mergeTopKDevice(self, d_idx_ptr: int, d_score_ptr: int, lists: int, nq: int, k: int, d_out_idx_ptr: int,
+                        d_out_score_ptr: int, stream: int = 0):
+        _check(_native.load().bbq_merge_topk_device(self._ctx, d_idx_ptr, d_score_ptr, lists, nq, k,
+                                                    d_out_idx_ptr, d_out_score_ptr, stream or None), "search")

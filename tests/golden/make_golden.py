@@ -1,0 +1,61 @@
+"""Generates tests/golden/*.npz from the CPU oracle (run here, committed with its outputs).
+
+The reference itself cannot be executed in this environment (TypeScript; no node/tsc/vitest, no cargo,
+no wasm runtime), so these are ORACLE outputs on seeded inputs, not reference outputs — "parity unpinned"
+for exact values (see oracle/bbq_oracle.cpp).  They pin (a) the oracle against drift between compilers /
+boxes and (b) the CUDA path on the GPU box, where /root/reference does not exist.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+from tests.fixtures import gaussian, sincos_dataset  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CASES = {
+    # name: (n, dim, sim, query_bits, k, nq, lam, iters, data)
+    "c1_cosine_1000x128": (1000, 128, "COSINE", 4, 10, 4, 0.1, 5, "gauss"),          # BASELINE configs[0]
+    "mip_3000x96_k100": (3000, 96, "MAXIMUM_INNER_PRODUCT", 4, 100, 3, 0.1, 5, "gauss"),
+    "euclid_2000x100": (2000, 100, "EUCLIDEAN", 4, 10, 3, 0.1, 5, "gauss"),           # dim % 8 != 0
+    "cosine_1bit_query_500x64": (500, 64, "COSINE", 1, 10, 3, 0.1, 5, "gauss"),
+    "sincos_recall_100x128": (100, 128, "COSINE", 4, 10, 10, 0.001, 20, "sincos"),    # tests/recall.test.ts fixture
+}
+
+
+def make(name):
+    n, dim, sim, qb, k, nq, lam, iters, data = CASES[name]
+    if data == "gauss":
+        seed = 20260101 + sum(map(ord, name))
+        base, queries = gaussian(n, dim, seed), gaussian(nq, dim, seed + 100)
+        gen = {"seed": seed}
+    else:
+        base, queries = sincos_dataset(dim, n, nq)
+        gen = {"seed": -1}
+    idx = O.quantize_vectors(base, sim=sim, index_bits=1, lam=lam, iters=iters)
+    out = {"n": n, "dim": dim, "sim": sim, "query_bits": qb, "k": k, "lam": lam, "iters": iters, **gen,
+           "centroid": idx.centroid, "packed_head": idx.packed[:16], "corr_head": idx.corr[:16],
+           "packed_crc": np.frombuffer(idx.packed.tobytes(), np.uint8).astype(np.uint64).sum(),
+           "corr_bits_xor": np.bitwise_xor.reduce(idx.corr.view(np.uint64).ravel())}
+    top_idx, top_sc, qcodes, qcorr, dots_head, score_xor = [], [], [], [], [], []
+    for q in queries:
+        i, s, alls, alld = O.search_nearest_neighbors(q, idx, k, query_bits=qb, lam=lam, iters=iters,
+                                                      mode="canonical", want_all=True)
+        c, r = O.quantize_query_vector(q, idx.centroid, sim=sim, query_bits=qb, lam=lam, iters=iters)
+        top_idx.append(i); top_sc.append(s); qcodes.append(c); qcorr.append(r)
+        dots_head.append(alld[:32]); score_xor.append(np.bitwise_xor.reduce(alls.view(np.uint32)))
+    out.update(top_idx=np.stack(top_idx), top_score=np.stack(top_sc), qcodes=np.stack(qcodes),
+               qcorr=np.stack(qcorr), dots_head=np.stack(dots_head), score_xor=np.array(score_xor, np.uint32))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "ok", out["top_idx"][0][:5])
+
+
+if __name__ == "__main__":
+    for nm in CASES:
+        make(nm)

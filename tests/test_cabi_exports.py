@@ -1,0 +1,64 @@
+"""The C-ABI library builds for sm_100a, loads, and exports every symbol include/bbq_b200.h declares.
+No compute calls (no GPU here); on a box without a GPU bbq_create must fail loudly, never fall back."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import bbq_b200
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "bbq_b200.h"), encoding="utf-8").read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(bbq_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = bbq_b200.build_library()
+    assert os.path.exists(path)
+    names = _declared()
+    assert len(names) >= 20
+    L = C.CDLL(path)
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/bbq_b200.h but not exported"
+    # and the Python binding table covers exactly the header
+    assert sorted(bbq_b200._native.SYMBOLS) == names
+    assert bbq_b200._native.load().bbq_abi_version() == 1
+
+
+def test_library_holds_sm100a_code():
+    out = subprocess.run(["cuobjdump", "-lelf", bbq_b200._native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_config_validation_precedes_device_probe():
+    # src/binaryQuantizationFormat.ts:143-148
+    with pytest.raises(bbq_b200.BbqError) as e:
+        bbq_b200.createBinaryQuantizationFormat({"queryBits": 9, "quantizer": {"similarityFunction": "COSINE"}})
+    assert e.value.status == 1 and str(e.value) == "queryBits必须在1-8之间"
+    with pytest.raises(bbq_b200.BbqError) as e:
+        bbq_b200.createBinaryQuantizationFormat({"indexBits": 0, "quantizer": {"similarityFunction": "COSINE"}})
+    assert e.value.status == 2 and str(e.value) == "indexBits必须在1-8之间"
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(bbq_b200.BbqError) as e:
+        bbq_b200.createBinaryQuantizationFormat()
+    assert e.value.status == 100
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "better-binary-quantization_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cc", ".ts")):
+                src = open(os.path.join(dp, f), encoding="utf-8").read()
+                assert "oracle" not in src.lower() or f in ("bbq_numerics.cuh",), f"{f} mentions the oracle"

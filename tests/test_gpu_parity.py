@@ -1,0 +1,321 @@
+"""GPU parity: the CUDA path, called through the C ABI (libbbq_b200.so) behind the reference-shaped host
+interface, against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): integer bit dot products BIT-EXACT; returned top-k index lists identical
+(ties broken by lower index); corrected f32 scores within 1e-5 relative — in fact asserted BIT-EXACT here,
+because the epilogue replays the reference's f64 operation order (the 1e-5 tolerance is also written out).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.fixtures import gaussian, sincos_dataset, true_topk_cosine
+from tests.golden_util import golden_cases, load_golden
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5  # north_star tolerance for corrected float scores
+SIMS = ["EUCLIDEAN", "COSINE", "MAXIMUM_INNER_PRODUCT"]
+
+
+@pytest.fixture(scope="module")
+def bbq():
+    import bbq_b200
+    bbq_b200.build_library()
+    return bbq_b200
+
+
+def make_format(bbq, sim, qb=4, lam=0.1, iters=5, force_path=None):
+    old = os.environ.pop("BBQ_FORCE_PATH", None)
+    if force_path is not None:
+        os.environ["BBQ_FORCE_PATH"] = str(force_path)
+    try:
+        return bbq.createBinaryQuantizationFormat(
+            {"queryBits": qb, "indexBits": 1, "quantizer": {"similarityFunction": sim, "lambda": lam, "iters": iters}})
+    finally:
+        os.environ.pop("BBQ_FORCE_PATH", None)
+        if old is not None:
+            os.environ["BBQ_FORCE_PATH"] = old
+
+
+def bits_equal(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    assert a.dtype == b.dtype and a.shape == b.shape, (a.dtype, b.dtype, a.shape, b.shape)
+    u = {4: np.uint32, 8: np.uint64, 1: np.uint8}[a.dtype.itemsize]
+    return np.array_equal(a.view(u), b.view(u))
+
+
+def assert_scores_close(got, want):
+    ok = np.isclose(got.astype(np.float64), want.astype(np.float64), rtol=REL_TOL, atol=0) | (got == want) | \
+        (np.isnan(got) & np.isnan(want))
+    assert ok.all(), f"score rel err > {REL_TOL}"
+    assert bits_equal(got, want), "scores are within tolerance but not bit-identical to the f64-replayed reference"
+
+
+# ---- K5: index build --------------------------------------------------------------------------------
+@pytest.mark.parametrize("sim", SIMS)
+@pytest.mark.parametrize("n,dim", [(1000, 128), (257, 100), (3, 8), (5000, 768), (40000, 64)])
+def test_index_build_bit_exact(bbq, sim, n, dim):
+    rows = gaussian(n, dim, 11 + n + dim)
+    want = O.quantize_vectors(rows, sim=sim, want_unpacked=False)
+    fmt = make_format(bbq, sim)
+    qv = fmt.quantizeVectors(rows)["quantizedVectors"]
+    assert qv.size() == n and qv.dimension() == dim
+    assert bits_equal(qv.getCentroid(), want.centroid)
+    assert qv.getCentroidDP() == O.centroid_dp(want.centroid)
+    packed, corr = qv.exportAll()
+    assert np.array_equal(packed, want.packed)
+    assert bits_equal(corr, want.corr)
+    # accessor forms of the reference interface (src/types.ts:32-49)
+    assert np.array_equal(qv.vectorValue(n - 1), want.packed[n - 1])
+    assert qv.getCorrectiveTerms(0)["lowerInterval"] == want.corr[0, 0]
+    assert np.array_equal(qv.getUnpackedVector(0), np.unpackbits(want.packed[0])[:dim])
+
+
+def test_index_build_explicit_centroid_and_list_input(bbq):
+    rows = gaussian(300, 64, 5)
+    cen = np.zeros(64, np.float32)
+    want = O.quantize_vectors(rows, sim="EUCLIDEAN", centroid=cen, want_unpacked=False)
+    fmt = make_format(bbq, "EUCLIDEAN")
+    qv = fmt.quantizeVectors([r for r in rows], centroid=cen)["quantizedVectors"]   # Float32Array[] form
+    packed, corr = qv.exportAll()
+    assert np.array_equal(packed, want.packed) and bits_equal(corr, want.corr)
+
+
+def test_index_build_degenerate_rows(bbq):
+    # single vector == centroid -> constant centred vector -> NaN interval in the reference; zero vectors under COSINE
+    for sim in SIMS:
+        rows = gaussian(1, 32, 1)
+        want = O.quantize_vectors(rows, sim=sim, want_unpacked=False)
+        qv = make_format(bbq, sim).quantizeVectors(rows)["quantizedVectors"]
+        packed, corr = qv.exportAll()
+        assert np.array_equal(packed, want.packed) and bits_equal(corr, want.corr)
+    rows = gaussian(50, 40, 2)
+    rows[7] = 0
+    rows[9] = rows[8]
+    want = O.quantize_vectors(rows, sim="COSINE", want_unpacked=False)
+    qv = make_format(bbq, "COSINE").quantizeVectors(rows)["quantizedVectors"]
+    packed, corr = qv.exportAll()
+    assert np.array_equal(packed, want.packed) and bits_equal(corr, want.corr)
+
+
+# ---- K4: query quantisation ----------------------------------------------------------------------------
+@pytest.mark.parametrize("sim", SIMS)
+@pytest.mark.parametrize("qb", [1, 2, 4, 7, 8])
+def test_query_quantize_bit_exact(bbq, sim, qb):
+    rows, qs = gaussian(400, 200, 21), gaussian(5, 200, 22)
+    fmt = make_format(bbq, sim, qb=qb)
+    qv = fmt.quantizeVectors(rows)["quantizedVectors"]
+    for q in qs:
+        codes, corr = O.quantize_query_vector(q, qv.getCentroid(), sim=sim, query_bits=qb)
+        got = fmt.quantizeQueryVector(q, qv)
+        assert np.array_equal(got["quantizedQuery"], codes)
+        gc = got["queryCorrections"]
+        assert bits_equal(np.array([gc["lowerInterval"], gc["upperInterval"], gc["additionalCorrection"],
+                                    gc["quantizedComponentSum"]]), corr)
+
+
+# ---- K1: integer dots and corrected scores over the whole index ------------------------------------------
+@pytest.mark.parametrize("sim", SIMS)
+@pytest.mark.parametrize("qb", [1, 4, 8])
+@pytest.mark.parametrize("n,dim", [(3000, 128), (1500, 100), (2000, 768), (700, 1536)])
+def test_qcdist_and_scores_bit_exact(bbq, sim, qb, n, dim):
+    rows, qs = gaussian(n, dim, 31 + dim), gaussian(2, dim, 32 + dim)
+    idx = O.quantize_vectors(rows, sim=sim, want_unpacked=False)
+    fmt = make_format(bbq, sim, qb=qb)
+    qv = fmt.adoptQuantized(idx.packed, idx.corr, idx.centroid)
+    for q in qs:
+        _, _, alls, alld = O.search_nearest_neighbors(q, idx, 5, query_bits=qb, want_all=True)
+        assert np.array_equal(fmt.debugQcDist(q, qv), alld)          # integers: bit-exact
+        assert_scores_close(fmt.debugScores(q, qv), alls)
+
+
+# ---- K1+K3: top-k ------------------------------------------------------------------------------------------
+def _check_search(fmt, qv, idx, queries, k, qb, lam=0.1, iters=5):
+    gi, gs = fmt.searchBatch(queries, qv, k)
+    for qi, q in enumerate(queries):
+        wi, ws, alls, _ = O.search_nearest_neighbors(q, idx, k, query_bits=qb, lam=lam, iters=iters,
+                                                     mode="canonical", want_all=True)
+        assert gi[qi].tolist() == wi.tolist(), f"query {qi}: top-{k} index list differs"
+        assert_scores_close(gs[qi], ws)
+        hi, _ = O.topk(alls, k, "heap")
+        ties = len(np.unique(alls[wi])) < len(wi) or (len(wi) < len(alls) and np.sort(alls)[::-1][len(wi)] == ws[-1])
+        if not ties:  # reference heap == canonical unless an exact f32 tie straddles the k-th place
+            assert set(hi.tolist()) == set(wi.tolist())
+        # single-query form returns the same row
+        one = fmt.searchNearestNeighbors(q, qv, k)
+        assert [r["index"] for r in one] == wi.tolist()
+
+
+@pytest.mark.parametrize("sim", SIMS)
+@pytest.mark.parametrize("n,dim,k,force", [
+    (1000, 128, 10, None),       # BASELINE configs[0] shape (direct path)
+    (20000, 256, 10, None),      # sampled threshold + filtered scan
+    (20000, 256, 100, None),
+    (20000, 256, 10, 2),         # exact chunked path forced
+    (9000, 96, 100, 1),          # filtered path forced on a small index
+    (33000, 100, 10, None),      # dim % 8 != 0, ragged last tile
+])
+def test_search_topk_identical(bbq, sim, n, dim, k, force):
+    rows, qs = gaussian(n, dim, 41 + n), gaussian(6, dim, 42 + n)
+    idx = O.quantize_vectors(rows, sim=sim, want_unpacked=False)
+    fmt = make_format(bbq, sim, force_path=force)
+    qv = fmt.quantizeVectors(rows)["quantizedVectors"]
+    _check_search(fmt, qv, idx, qs, k, 4)
+    if force is not None:
+        assert fmt.stats()["last_path"] == force
+
+
+@pytest.mark.parametrize("qb", [1, 8])
+def test_search_other_query_bits(bbq, qb):
+    rows, qs = gaussian(18000, 128, 51), gaussian(4, 128, 52)
+    for sim in SIMS:
+        idx = O.quantize_vectors(rows, sim=sim, want_unpacked=False)
+        fmt = make_format(bbq, sim, qb=qb)
+        qv = fmt.quantizeVectors(rows)["quantizedVectors"]
+        _check_search(fmt, qv, idx, qs, 10, qb)
+
+
+def test_search_ties_lower_index_first(bbq):
+    """Duplicate rows give exact f32 ties; the contract is (score desc, index asc)."""
+    rows = gaussian(40, 64, 61)
+    rows = np.concatenate([rows] * 500)           # 20000 rows, every score repeated 500 times
+    for sim in SIMS:
+        idx = O.quantize_vectors(rows[:40], sim=sim, want_unpacked=False, centroid=np.zeros(64, np.float32))
+        packed, corr = np.concatenate([idx.packed] * 500), np.concatenate([idx.corr] * 500)
+        big = O.OracleIndex(idx.centroid, packed, None, corr, 64, sim, 1)
+        for force in (None, 2):
+            fmt = make_format(bbq, sim, force_path=force)
+            qv = fmt.adoptQuantized(packed, corr, idx.centroid)
+            for q in gaussian(3, 64, 62):
+                wi, ws = O.search_nearest_neighbors(q, big, 25, mode="canonical")
+                gi, gs = fmt.searchBatch(q[None], qv, 25)
+                assert gi[0].tolist() == wi.tolist() and bits_equal(gs[0], ws)
+                assert np.all(np.diff(gi[0][:20]) == 40)   # the best row's duplicates, ascending ids
+
+
+def test_search_edge_cases(bbq):
+    rows = gaussian(7, 32, 71)
+    fmt = make_format(bbq, "COSINE")
+    qv = fmt.quantizeVectors(rows)["quantizedVectors"]
+    q = gaussian(1, 32, 72)[0]
+    assert fmt.searchNearestNeighbors(q, qv, 0) == []                     # k == 0 -> []
+    res = fmt.searchNearestNeighbors(q, qv, 10)                           # k > N -> N results
+    idx = O.quantize_vectors(rows, sim="COSINE")
+    wi, ws = O.search_nearest_neighbors(q, idx, 10, mode="canonical")
+    assert [r["index"] for r in res] == wi.tolist() and len(res) == 7
+    assert [np.float32(r["score"]) for r in res] == ws.tolist()
+    with pytest.raises(bbq.BbqError, match="k值不能为负数"):
+        fmt.searchNearestNeighbors(q, qv, -1)
+    with pytest.raises(bbq.BbqError, match="查询向量维度与目标向量维度不匹配"):
+        fmt.searchNearestNeighbors(q[:16], qv, 3)
+    with pytest.raises(bbq.BbqError, match="查询向量不能为空"):
+        fmt.searchNearestNeighbors(None, qv, 3)
+    with pytest.raises(bbq.BbqError, match="向量集合不能为空"):
+        fmt.quantizeVectors([])
+    with pytest.raises(bbq.BbqError, match="维度"):
+        fmt.quantizeVectors([np.zeros(4, np.float32), np.zeros(5, np.float32)])
+    bad = rows.copy()
+    bad[3, 5] = np.nan
+    with pytest.raises(bbq.BbqError, match="包含NaN值"):
+        fmt.quantizeVectors(bad)
+    bad = rows.copy()
+    bad[2, 1] = np.inf
+    with pytest.raises(bbq.BbqError, match="向量 2 位置 1 包含Infinity值"):
+        make_format(bbq, "EUCLIDEAN").quantizeVectors(bad)
+    qn = q.copy()
+    qn[0] = np.nan
+    with pytest.raises(bbq.BbqError, match="包含NaN值"):
+        fmt.searchNearestNeighbors(qn, qv, 3)
+    # single-row index
+    one = make_format(bbq, "EUCLIDEAN").quantizeVectors(rows[:1])["quantizedVectors"]
+    assert one.size() == 1
+
+
+def test_quick_search_and_recall_fixture(bbq):
+    """tests/recall.test.ts: 128-d sin/cos fixture, lambda=0.001, iters=20, COSINE: recall@10 >= 0.60 (4b x 1b)
+    and >= 0.70 (1b x 1b); quickSearch == oracle quick_search."""
+    base, queries = sincos_dataset(128, 100, 10)
+    for qb, thr in ((4, 0.60), (1, 0.70)):
+        fmt = make_format(bbq, "COSINE", qb=qb, lam=0.001, iters=20)
+        qv = fmt.quantizeVectors(base)["quantizedVectors"]
+        tot = 0.0
+        for q in queries:
+            got = [r["index"] for r in fmt.searchNearestNeighbors(q, qv, 10)]
+            assert len(got) == 10
+            tot += len(set(got) & set(true_topk_cosine(q, base, 10).tolist())) / 10
+        assert tot / len(queries) >= thr
+    res = bbq.quickSearch(queries[0], base, 10, bbq.VectorSimilarityFunction.COSINE)
+    wi, ws = O.quick_search(queries[0], base, 10, "COSINE")
+    assert [r["index"] for r in res] == wi.tolist()
+    scores = [r["score"] for r in res]
+    assert scores == sorted(scores, reverse=True)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_against_golden_fixtures(bbq, name):
+    g = load_golden(name)
+    fmt = make_format(bbq, g["sim"], qb=g["query_bits"], lam=g["lam"], iters=g["iters"])
+    qv = fmt.quantizeVectors(g["base"])["quantizedVectors"]
+    assert bits_equal(qv.getCentroid(), g["centroid"])
+    packed, corr = qv.exportAll()
+    assert np.array_equal(packed[:16], g["packed_head"]) and bits_equal(corr[:16], g["corr_head"])
+    assert np.frombuffer(packed.tobytes(), np.uint8).astype(np.uint64).sum() == g["packed_crc"]
+    assert np.bitwise_xor.reduce(corr.view(np.uint64).ravel()) == g["corr_bits_xor"]
+    gi, gs = fmt.searchBatch(g["queries"], qv, g["k"])
+    assert np.array_equal(gi, g["top_idx"]) and bits_equal(gs, g["top_score"])
+    for qi, q in enumerate(g["queries"]):
+        assert np.array_equal(fmt.debugQcDist(q, qv)[:32], g["dots_head"][qi])
+        assert np.bitwise_xor.reduce(fmt.debugScores(q, qv).view(np.uint32)) == g["score_xor"][qi]
+        got = fmt.quantizeQueryVector(q, qv)
+        assert np.array_equal(got["quantizedQuery"], g["qcodes"][qi])
+
+
+def test_batch_equals_single_and_is_deterministic(bbq):
+    rows, qs = gaussian(30000, 128, 81), gaussian(70, 128, 82)
+    fmt = make_format(bbq, "EUCLIDEAN")
+    qv = fmt.quantizeVectors(rows)["quantizedVectors"]
+    gi, gs = fmt.searchBatch(qs, qv, 10)
+    gi2, gs2 = fmt.searchBatch(qs, qv, 10)
+    assert np.array_equal(gi, gi2) and bits_equal(gs, gs2)
+    for qi in (0, 33, 69):
+        one = fmt.searchNearestNeighbors(qs[qi], qv, 10)
+        assert [r["index"] for r in one] == gi[qi].tolist()
+
+
+# ---- sharding: G shards + deterministic merge == one index --------------------------------------
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_sharded_merge_equals_single(bbq, shards):
+    import ctypes as C
+    import torch
+    n, dim, k, nq = 48000, 128, 10, 9   # 2 shards -> filtered path, 3/8 shards -> direct path
+    rows, qs = gaussian(n, dim, 91), gaussian(nq, dim, 92)
+    sim = "COSINE"
+    idx = O.quantize_vectors(rows, sim=sim, want_unpacked=False)
+    fmt = make_format(bbq, sim)
+    L = bbq._native.load()
+    bounds = np.linspace(0, n, shards + 1).astype(int)
+    dq = torch.from_numpy(qs).cuda()
+    all_idx = torch.empty((shards, nq, k), dtype=torch.int32, device="cuda")
+    all_sc = torch.empty((shards, nq, k), dtype=torch.float32, device="cuda")
+    keep = []
+    for s in range(shards):
+        a, b = bounds[s], bounds[s + 1]
+        qv = fmt.adoptQuantized(idx.packed[a:b], idx.corr[a:b], idx.centroid)   # same centroid on every shard
+        assert L.bbq_index_set_base(qv._h, int(a)) == 0
+        st = L.bbq_search_device(qv._h, dq.data_ptr(), nq, k, all_idx[s].data_ptr(), all_sc[s].data_ptr(), None)
+        assert st == 0, L.bbq_last_error()
+        keep.append(qv)
+    torch.cuda.synchronize()
+    out_idx = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+    out_sc = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    st = L.bbq_merge_topk_device(fmt._ctx, all_idx.data_ptr(), all_sc.data_ptr(), shards, nq, k, out_idx.data_ptr(),
+                                 out_sc.data_ptr(), None)
+    assert st == 0, L.bbq_last_error()
+    torch.cuda.synchronize()
+    gi, gs = out_idx.cpu().numpy(), out_sc.cpu().numpy()
+    for qi, q in enumerate(qs):
+        wi, ws = O.search_nearest_neighbors(q, idx, k, mode="canonical")
+        assert gi[qi].tolist() == wi.tolist() and bits_equal(gs[qi], ws)
