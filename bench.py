@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — QPS & effective index GB/s of the 4b x 1b BBQ score+top-k path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic queries: quantise the query batch (K4),
+scan + score + top-k over this rank's row shard (K1/K3), and for N > 1 one NCCL all_gather of the per-shard
+top-k lists + the deterministic merge.  The corpus (BASELINE configs[2] by default: 1M x 1024, EUCLIDEAN,
+k=10, batch of 1024 queries) is FIXED and sharded row-wise over the N GPUs => "scaling": "strong".
+
+value      device-timed whole-job QPS, index resident in HBM, queries already on device
+e2e        the same through the host API: pinned host queries -> H2D, search, D2H of the results, every step
+roofline   the dominant kernel (the scan) against the measured HBM peak in MEASURED_PEAKS.json
+cpu_baseline   the CPU oracle (restatement of the reference's TypeScript path; "port") on a bounded sample,
+               same index bytes, 1 thread (the reference is single-threaded Node)
+--impl reference   times that CPU path as the main line (the TypeScript reference itself cannot run here:
+                   no node / tsc / cargo in the image)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1..3]
+    "c2": dict(n=100_000, dim=768, sim="MAXIMUM_INNER_PRODUCT", k=100, nq=1,
+               name="100k x 768 MAXIMUM_INNER_PRODUCT k=100 single query (BASELINE configs[1])"),
+    "c3": dict(n=1_000_000, dim=1024, sim="EUCLIDEAN", k=10, nq=1024,
+               name="1M x 1024 EUCLIDEAN k=10 batch of 1024 queries (BASELINE configs[2])"),
+    "c4": dict(n=100_000_000, dim=1024, sim="COSINE", k=10, nq=4096,
+               name="100M x 1024 COSINE k=10 batch of 4096 queries, row-sharded (BASELINE configs[3])"),
+}
+CHUNK = 65536            # corpus generation granularity: chunk c is seeded by (SEED + c) whatever N is
+SEED_CORPUS, SEED_QUERY = 20260101, 20260201
+METRIC, UNIT = "QPS (4b x 1b BBQ score+top-k)", "queries/s"
+
+
+def gen_chunk_host(c, dim, rows):
+    return np.random.default_rng(SEED_CORPUS + c).standard_normal((rows, dim), dtype=np.float32)
+
+
+def gen_queries(nq, dim):
+    return np.random.default_rng(SEED_QUERY).standard_normal((nq, dim), dtype=np.float32)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.lines, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # median over the busier half of the samples (the sampler also sees the gaps between steps)
+        sm_sorted = sorted(sm)
+        return {"sm_mhz": (sm_sorted[len(sm_sorted) // 2] if sm else None), "sm_max_mhz": (max(mx) if mx else None),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU leg: the oracle on host cores (bench.py's cpu_baseline and --impl reference are the only legs that may run it)
+# ---------------------------------------------------------------------------------------------------------------
+def oracle_index_from_arrays(packed, corr, centroid, dim, sim):
+    from oracle import oracle as O
+    return O.OracleIndex(np.ascontiguousarray(centroid, np.float32), np.ascontiguousarray(packed),
+                         None, np.ascontiguousarray(corr), dim, sim, 1)
+
+
+def cpu_time_queries(oidx, queries, k, budget_s, max_q):
+    """Runs the oracle's searchNearestNeighbors (reference heap selection) query by query, 1 thread."""
+    from oracle import oracle as O
+    done, t0, res = 0, time.perf_counter(), []
+    for q in queries[:max_q]:
+        res.append(O.search_nearest_neighbors(q, oidx, k, query_bits=4, mode="heap"))
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return done, time.perf_counter() - t0, res
+
+
+def build_oracle_index_threaded(w, n_rows):
+    """Index build for the reference arm (untimed): the oracle's quantizeVectors over row chunks on all host
+    threads (ctypes releases the GIL); explicit zero centroid as in the GPU arm."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    dim, sim = w["dim"], w["sim"]
+    cen = np.zeros(dim, np.float32)
+    nchunks = -(-n_rows // CHUNK)
+
+    def one(c):
+        rows = min(CHUNK, n_rows - c * CHUNK)
+        ix = O.quantize_vectors(gen_chunk_host(c, dim, rows), sim=sim, centroid=cen, want_unpacked=False)
+        return ix.packed, ix.corr
+
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+        parts = list(ex.map(one, range(nchunks)))
+    return oracle_index_from_arrays(np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]),
+                                    cen, dim, sim)
+
+
+def run_reference(args, w, rank):
+    """--impl reference: the reference algorithm's CPU path (oracle port) on the box's host cores."""
+    if rank != 0:
+        return
+    n = w["n"]
+    sample_rows = min(n, args.ref_rows)
+    t0 = time.perf_counter()
+    oidx = build_oracle_index_threaded(w, sample_rows)
+    build_s = time.perf_counter() - t0
+    queries = gen_queries(max(w["nq"], 1), w["dim"])
+    qps_steps = []
+    qi = 0
+    per_step = max(1, args.ref_queries_per_step)
+    for step in range(args.warmup + args.steps):
+        qs = [queries[(qi + j) % len(queries)] for j in range(per_step)]
+        qi += per_step
+        done, dt, _ = cpu_time_queries(oidx, qs, w["k"], 1e9, per_step)
+        if step >= args.warmup:
+            qps_steps.append(dt)
+    total = sum(qps_steps)
+    # per-query cost is linear in the rows scanned: scale the sample to the full corpus (marked as such)
+    scale = n / sample_rows
+    qps = per_step * args.steps / (total * scale)
+    sample = (f"{per_step} queries/step over {sample_rows} of {n} rows"
+              + (f", per-query time scaled x{scale:.0f} to the full corpus (extrapolated)" if scale != 1 else "")
+              + f"; oracle index build {build_s:.1f}s on {os.cpu_count()} threads (untimed); search 1 thread")
+    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int32 dot + f64 epilogue", "data": "synthetic",
+            "config": {"workload": w["name"], "note": "CPU restatement of the reference TypeScript path (oracle port); "
+                       "the TypeScript reference cannot run here (no node/tsc)"},
+            "cpu_baseline": {"value": qps, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_gpu(args, w, rank, world, local_rank):
+    import torch
+    import bbq_b200
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    bbq_b200.build_library()
+    n, dim, sim, k, nq = w["n"], w["dim"], w["sim"], w["k"], w["nq"]
+    r0, r1 = bbq_b200.shard_bounds(n, world, rank)
+    fmt = bbq_b200.createBinaryQuantizationFormat(
+        {"queryBits": 4, "indexBits": 1, "quantizer": {"similarityFunction": sim, "lambda": 0.1, "iters": 5}},
+        device=local_rank)
+    # --- corpus: N(0,1) f32, generated per 64Ki-row chunk (independent of N), quantised on device (K5) ---
+    t_build = time.perf_counter()
+    cen = np.zeros(dim, np.float32)  # analytic centroid of the synthetic corpus, supplied explicitly
+    shard = fmt.reserveIndex(max(r1 - r0, 1), dim, cen)
+    device_gen = args.datagen == "device" or (args.datagen == "auto" and n > 4_000_000)
+    c = r0 // CHUNK
+    pos = r0
+    while pos < r1:
+        c0 = c * CHUNK
+        lo, hi = max(pos, c0), min(r1, c0 + CHUNK)
+        if device_gen:
+            g = torch.Generator(device="cuda")
+            g.manual_seed(SEED_CORPUS + c)
+            rows = torch.randn((min(CHUNK, n - c0), dim), generator=g, device="cuda", dtype=torch.float32)
+            part = rows[lo - c0:hi - c0].contiguous()
+            fmt.appendRows(shard, d_rows_ptr=part.data_ptr(), n=hi - lo)
+            del rows, part
+        else:
+            rows = gen_chunk_host(c, dim, min(CHUNK, n - c0))
+            fmt.appendRows(shard, rows=rows[lo - c0:hi - c0])
+        pos = hi
+        c += 1
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t_build
+    searcher = bbq_b200.ShardedSearcher(fmt, shard, r0, rank, world)
+    hq = torch.from_numpy(gen_queries(nq, dim)).pin_memory()
+    dq = hq.cuda()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if sampler:
+            sampler.start()
+        tot = 0.0
+        for _ in range(steps):
+            flush.zero_()                      # L2 flush between timed iterations, outside the timed pair
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(searcher.stream)
+            fn()
+            e1.record(searcher.stream)
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        t = torch.tensor([tot], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)   # max over ranks
+        return float(t.item()), clocks
+
+    # --- value: device-resident timing, with the library's per-kernel event taps on --------------------------
+    fmt.setProfiling(True)
+    for _ in range(args.warmup):
+        searcher.search_device(dq, k)
+    torch.cuda.synchronize()
+    fmt.resetProfiling()
+    l0 = fmt.stats()["kernel_launches"]
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total, clocks = timed(lambda: searcher.search_device(dq, k), args.steps, 0, sampler)
+    st = fmt.stats()
+    launches = st["kernel_launches"] - l0
+    fmt.setProfiling(False)
+    ms_step = ms_total / args.steps
+    qps = nq / (ms_step * 1e-3)
+
+    # --- e2e: pinned host queries -> H2D -> search (+ all_gather + merge) -> D2H, every step ------------------
+    e2e_ms, _ = timed(lambda: searcher.search(hq, k), args.steps, args.warmup)
+    e2e_qps = nq / (e2e_ms / args.steps * 1e-3)
+    h2d = nq * dim * 4 * world
+    d2h = nq * k * 8 * world
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # --- roofline of the dominant kernel (the scan; CUDA events on its own stream inside the library) --------
+    peak, peak_src = load_peaks()
+    rows_local = r1 - r0
+    bvec = (dim + 7) // 8 + 16                  # algorithmic bytes / scanned vector
+    scan_ms = st["scan_ms"] / max(st["scan_launches"], 1)
+    # the filtered scan is the launch that carries the step; its sample pre-pass is a second, small launch
+    scan_ms_step = st["scan_ms"] / args.steps
+    algo_bytes = rows_local * bvec
+    achieved = algo_bytes / (scan_ms_step * 1e-3) / 1e9 if scan_ms_step > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "bbqk::k_scan",
+                "algorithmic_bytes_per_step": algo_bytes, "scan_ms_per_step": scan_ms_step,
+                "scan_launches_per_step": st["scan_launches"] / args.steps, "avg_scan_launch_ms": scan_ms,
+                "query_effective_GBps": nq * algo_bytes / (scan_ms_step * 1e-3) / 1e9 if scan_ms_step > 0 else 0.0,
+                "quantize_ms_per_step": st["quantize_ms"] / args.steps, "select_ms_per_step": st["select_ms"] / args.steps}
+
+    # --- CPU baseline beside it (rank 0, N=1 only): the oracle over THIS index's bytes, bounded sample --------
+    cpu = None
+    parity = None
+    if world == 1 and not args.no_cpu:
+        packed, corr = shard.exportAll()
+        oidx = oracle_index_from_arrays(packed, corr, shard.getCentroid(), dim, sim)
+        qs = gen_queries(nq, dim)
+        done, dt, res = cpu_time_queries(oidx, qs, k, args.cpu_budget, args.cpu_max_queries)
+        cpu = {"value": done / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{done} of {nq} queries over the full {n}-row index, 1 thread, {dt:.1f}s "
+                         "(oracle = C++ restatement of the reference TypeScript path, not V8)"}
+        oi, os_ = searcher.search(hq, k)
+        oi = oi.numpy()
+        ok = all(oi[i].tolist() == res[i][0].tolist() for i in range(done))
+        parity = {"queries_checked": done, "topk_index_lists_identical": bool(ok)}
+
+    line = {"metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32 popcount dot + f64 epilogue -> f32 score", "data": "synthetic",
+            "config": {"workload": w["name"], "rows_total": n, "rows_per_gpu": rows_local, "dim": dim, "k": k,
+                       "queries_per_step": nq, "similarity": sim, "query_bits": 4, "index_bits": 1,
+                       "sharding": f"row-wise x{world}, NCCL all_gather top-k merge" if world > 1 else "single shard",
+                       "l2": "256 MB flush buffer written between timed iterations",
+                       "corpus": f"N(0,1) f32, {'device' if device_gen else 'host'}-generated per 65536-row chunk, "
+                                 f"explicit zero centroid; index build {build_s:.1f}s (untimed)",
+                       "path": {0: "direct", 1: "sampled threshold + filtered scan", 2: "exact chunked"}[st["last_path"]]},
+            "index_GBps": achieved, "index_frac_of_hbm_peak": achieved / peak,
+            "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}
+    if cpu:
+        line["cpu_baseline"] = cpu
+        line["parity"] = parity
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--datagen", default="auto", choices=["auto", "host", "device"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--cpu-max-queries", type=int, default=16)
+    ap.add_argument("--ref-rows", type=int, default=1_000_000, help="--impl reference: rows of the corpus sampled")
+    ap.add_argument("--ref-queries-per-step", type=int, default=1)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, w, rank)
+        return
+    if world != args.gpus:
+        if args.gpus != 1 and world == 1:
+            # launched without torchrun: re-exec under it
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+            os.execv(sys.executable, cmd)
+    run_gpu(args, w, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
