@@ -16,7 +16,7 @@ HEADER = os.path.join(_HERE, "..", "include", "bbq_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 SOURCES = ["bbq_api.cu"]
-DEPS = ["bbq_api.cu", "bbq_kernels.cuh", "bbq_numerics.cuh"]
+DEPS = ["bbq_api.cu", "bbq_kernels.cuh", "bbq_mma.cuh", "bbq_numerics.cuh"]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
@@ -39,7 +39,8 @@ class BbqConfig(C.Structure):
 
 class BbqStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("last_candidates", C.c_uint64), ("last_path", C.c_uint32),
-                ("last_overflow", C.c_uint32), ("scan_launches", C.c_uint64), ("scan_ms", C.c_double),
+                ("last_overflow", C.c_uint32), ("last_engine", C.c_uint32), ("reserved0", C.c_uint32),
+                ("scan_launches", C.c_uint64), ("scan_ms", C.c_double),
                 ("quantize_ms", C.c_double), ("select_ms", C.c_double)]
 
 

@@ -12,6 +12,7 @@
 
 #include "../../include/bbq_b200.h"
 #include "bbq_kernels.cuh"
+#include "bbq_mma.cuh"
 
 using namespace bbqk;
 
@@ -76,7 +77,8 @@ struct bbq_ctx {
   DevBuf T, stage, cacc;
   // query scratch
   DevBuf qrows, qT, qcodes, qcorr, planes, qterms, tau, dump, cand, cand_cnt, flag, lists_a, lists_b,
-      out_idx, out_score, dots;
+      out_idx, out_score, dots, images, qscreen;
+  int scan_engine = 0;  // BBQ_SCAN: 0 auto, 1 popcount kernel only, 2 tensor-core kernel whenever it can run
   uint32_t* h_flag = nullptr;  // pinned: [0..nq) candidate counts, [nq] overflow flag
   // profiling (bbq_set_profiling): event pairs per kernel group, drained by bbq_get_stats
   bool profiling = false;
@@ -126,6 +128,8 @@ struct bbq_index {
   std::vector<float> centroid_h;
   double cdp = 0.0;
   uint64_t base = 0;
+  IndexBounds* bounds = nullptr;  // device; valid for bounds_n rows (tensor-core screen margins)
+  uint64_t bounds_n = 0;
   uint64_t capacity = 0;  // rows allocated (== n except while a streaming build is in progress)
 };
 
@@ -175,6 +179,7 @@ extern "C" int bbq_create(const bbq_config* config, bbq_ctx** out_ctx) {
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaMallocHost(&c->h_flag, (QUERY_BATCH + 1) * sizeof(uint32_t)));
   if (const char* e = getenv("BBQ_FORCE_PATH")) c->force_path = atoi(e);
+  if (const char* e = getenv("BBQ_SCAN")) c->scan_engine = !strcmp(e, "popc") ? 1 : !strcmp(e, "mma") ? 2 : 0;
   *out_ctx = c;
   return BBQ_OK;
 }
@@ -185,7 +190,7 @@ extern "C" void bbq_destroy(bbq_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (DevBuf* b : {&c->T, &c->stage, &c->cacc, &c->qrows, &c->qT, &c->qcodes, &c->qcorr, &c->planes, &c->qterms,
                     &c->tau, &c->dump, &c->cand, &c->cand_cnt, &c->flag, &c->lists_a, &c->lists_b, &c->out_idx,
-                    &c->out_score, &c->dots})
+                    &c->out_score, &c->dots, &c->images, &c->qscreen})
     b->release();
   if (c->h_flag) cudaFreeHost(c->h_flag);
   for (auto& p : c->ev_pending) {
@@ -270,6 +275,7 @@ extern "C" void bbq_index_destroy(bbq_index* ix) {
   cudaFree(ix->addc);
   cudaFree(ix->compsum);
   cudaFree(ix->centroid);
+  if (ix->bounds) cudaFree(ix->bounds);
   delete ix;
 }
 
@@ -656,6 +662,112 @@ static int quantize_queries(bbq_index* ix, const float* d_queries, int nq, cudaS
   return BBQ_OK;
 }
 
+// ---- tensor-core scan (K2) -------------------------------------------------------------------------
+struct MmaPlan {
+  int n_tile = 0, passes = 0, nstage = 0, kbytes = 0;
+  size_t smem = 0;
+};
+static bool mma_plan(const bbq_index* ix, int nq, MmaPlan* out) {
+  const bbq_ctx* c = ix->ctx;
+  if (c->scan_engine == 1 || c->cfg.query_bits > 5) return false;
+  MmaPlan pl;
+  pl.kbytes = ix->row_bytes * 8;
+  const size_t budget = 227 * 1024 - 1024;
+  int n_cap = (int)(budget / ((size_t)pl.kbytes + 64)) / 16 * 16;
+  n_cap = std::min(n_cap, MMA_N_MAX);
+  if (n_cap < 16) return false;
+  if (c->scan_engine != 2 && nq < 64) return false;  // small batches: the popcount kernel is HBM/latency bound anyway
+  pl.passes = (nq + n_cap - 1) / n_cap;
+  pl.n_tile = (((nq + pl.passes - 1) / pl.passes) + 15) / 16 * 16;
+  pl.nstage = std::min(8, (512 - 2 * pl.n_tile) / 32);
+  pl.smem = (size_t)pl.n_tile * pl.kbytes + (size_t)pl.n_tile * (sizeof(QScreen) + sizeof(bbqn::QueryTerms)) + 23 * 8 + 16;
+  *out = pl;
+  return true;
+}
+
+static int ensure_bounds(bbq_index* ix, cudaStream_t st) {
+  bbq_ctx* c = ix->ctx;
+  if (ix->bounds && ix->bounds_n == ix->n) return BBQ_OK;
+  if (!ix->bounds) CU(cudaMalloc(&ix->bounds, sizeof(IndexBounds)));
+  CU(cudaMemsetAsync(ix->bounds, 0, sizeof(IndexBounds), st));
+  LAUNCH(c, k_index_bounds, 296, 256, 0, st, ix->lower, ix->upper, ix->addc, ix->compsum, (int64_t)ix->n,
+         reinterpret_cast<uint32_t*>(ix->bounds));
+  ix->bounds_n = ix->n;
+  return BBQ_OK;
+}
+
+// B images for the whole query batch (after quantize_queries)
+static int prepare_mma_operands(bbq_index* ix, int nq, const MmaPlan& pl, cudaStream_t st) {
+  bbq_ctx* c = ix->ctx;
+  const size_t bytes = (size_t)pl.passes * pl.n_tile * pl.kbytes;
+  TRY(c->images.reserve(bytes));
+  TRY(c->qscreen.reserve((size_t)pl.passes * pl.n_tile * sizeof(QScreen)));
+  ProfScope prof(c, st, PROF_QUANT);
+  const int64_t threads = (int64_t)pl.passes * pl.n_tile * (pl.kbytes / 16);
+  LAUNCH(c, k_query_tiles, (unsigned)((threads + 255) / 256), 256, 0, st, c->qcodes.as<uint8_t>(), ix->row_bytes * 8, nq,
+         pl.n_tile, pl.kbytes, c->images.as<uint8_t>());
+  return BBQ_OK;
+}
+
+template <int MODE>
+static int launch_mma_sim(bbq_ctx* c, int sim, unsigned grid, size_t smem, cudaStream_t st, const MmaParams& p) {
+#define BBQ_MMA_CASE(S)                                                                                         \
+  case S:                                                                                                       \
+    CU(cudaFuncSetAttribute(k_scan_mma<MODE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+    LAUNCH(c, (k_scan_mma<MODE, S>), grid, MMA_THREADS, smem, st, p);                                           \
+    break;
+  switch (sim) {
+    BBQ_MMA_CASE(0)
+    BBQ_MMA_CASE(1)
+    BBQ_MMA_CASE(2)
+    default:
+      return fail(BBQ_ERR_INVALID_ARG, "unknown similarity");
+  }
+#undef BBQ_MMA_CASE
+  return BBQ_OK;
+}
+
+static int launch_scan_mma(bbq_index* ix, int mode, int nq, const MmaPlan& pl, int64_t tile_first, int64_t tile_stride,
+                           int64_t ntiles, float* dump, int64_t dump_ld, uint64_t* cand, uint32_t* cand_cnt,
+                           uint32_t cap, uint32_t* overflow, cudaStream_t st) {
+  bbq_ctx* c = ix->ctx;
+  MmaParams p{};
+  p.codes = ix->codes;
+  p.lower = ix->lower;
+  p.upper = ix->upper;
+  p.addc = ix->addc;
+  p.compsum = ix->compsum;
+  p.n = (int64_t)ix->n;
+  p.row_bytes = ix->row_bytes;
+  p.kbytes = pl.kbytes;
+  p.images = c->images.as<uint8_t>();
+  p.qscreen = c->qscreen.as<QScreen>();
+  p.qterms = c->qterms.as<bbqn::QueryTerms>();
+  p.nq = nq;
+  p.n_tile = pl.n_tile;
+  p.passes = pl.passes;
+  p.nstage = pl.nstage;
+  p.dim = (double)ix->dim;
+  p.cdp = ix->cdp;
+  p.sim = (int)c->cfg.similarity;
+  p.one_bit_query = c->cfg.query_bits == 1 ? 1 : 0;
+  p.base = (uint32_t)ix->base;
+  p.tile_first = tile_first;
+  p.tile_stride = tile_stride;
+  p.ntiles = ntiles;
+  p.dump = dump;
+  p.dump_ld = dump_ld;
+  p.cand = cand;
+  p.cand_cnt = cand_cnt;
+  p.cap = cap;
+  p.overflow = overflow;
+  ProfScope prof(c, st, PROF_SCAN);
+  c->stats.scan_launches++;
+  const unsigned grid = (unsigned)std::min<int64_t>(ntiles, c->sm_count);
+  if (mode == SCAN_DUMP) return launch_mma_sim<SCAN_DUMP>(c, p.sim, grid, pl.smem, st, p);
+  return launch_mma_sim<SCAN_FILTER>(c, p.sim, grid, pl.smem, st, p);
+}
+
 static ScanParams base_scan_params(bbq_index* ix, int nq) {
   bbq_ctx* c = ix->ctx;
   ScanParams p{};
@@ -772,12 +884,23 @@ static int search_filtered(bbq_index* ix, int nq, uint32_t k, int32_t* d_out_idx
   TRY(c->tau.reserve((size_t)nq * sizeof(float)));
   TRY(c->cand.reserve((size_t)nq * CAND_CAP * sizeof(uint64_t)));
   TRY(c->cand_cnt.reserve((size_t)(nq + 1) * sizeof(uint32_t)));
+  MmaPlan pl;
+  const bool use_mma = mma_plan(ix, nq, &pl);
+  c->stats.last_engine = use_mma ? 2 : 1;
+  if (use_mma) {
+    TRY(prepare_mma_operands(ix, nq, pl, st));
+    TRY(ensure_bounds(ix, st));
+  }
   {
     ScanParams p = base_scan_params(ix, nq);
     p.tile_stride = stride;
     p.dump = c->dump.as<float>();
     p.dump_ld = SELECT_MAX;
-    TRY(launch_scan(ix, SCAN_DUMP, p, stiles, st));
+    if (use_mma)
+      TRY(launch_scan_mma(ix, SCAN_DUMP, nq, pl, 0, stride, stiles, c->dump.as<float>(), SELECT_MAX, nullptr, nullptr, 0,
+                          nullptr, st));
+    else
+      TRY(launch_scan(ix, SCAN_DUMP, p, stiles, st));
     SelectParams s{};
     s.nq = nq;
     s.k = k;
@@ -799,7 +922,18 @@ static int search_filtered(bbq_index* ix, int nq, uint32_t k, int32_t* d_out_idx
     p.cand_cnt = cnt;
     p.cap = CAND_CAP;
     p.overflow = cnt + nq;
-    TRY(launch_scan(ix, SCAN_FILTER, p, ntiles, st));
+    if (use_mma) {
+      {
+        ProfScope prof(c, st, PROF_QUANT);
+        const int nq_pad = pl.passes * pl.n_tile;
+        LAUNCH(c, k_query_screen, (nq_pad + 127) / 128, 128, 0, st, c->qterms.as<bbqn::QueryTerms>(), c->tau.as<float>(),
+               nq, nq_pad, (double)ix->dim, ix->cdp, (int)c->cfg.similarity, c->cfg.query_bits == 1 ? 1 : 0, ix->bounds,
+               c->qscreen.as<QScreen>());
+      }
+      TRY(launch_scan_mma(ix, SCAN_FILTER, nq, pl, 0, 1, ntiles, nullptr, 0, p.cand, cnt, CAND_CAP, cnt + nq, st));
+    } else {
+      TRY(launch_scan(ix, SCAN_FILTER, p, ntiles, st));
+    }
   }
   {
     SelectParams s{};

@@ -1,0 +1,496 @@
+// bbq_mma.cuh — K2: the batched scan on the 5th-generation tensor cores (tcgen05, sm_100a only).
+//
+// For a batch of queries the scan is the integer contraction  dot[v][q] = sum_d bit_d(x_v) * q_code[q][d]
+// (src/utils/computeBatchFourBitDotProductDirectPacked.ts:10-53, one call per query in the reference).
+// Here it is ONE persistent, warp-specialised kernel per query batch:
+//
+//   * B operand  = a block of <= 224 queries' codes, resident in shared memory for a whole pass over the
+//                  index shard (no-swizzle K-major core-matrix image, loaded with cp.async.bulk);
+//   * A operand  = the 1-bit index rows, expanded on the fly by 4 "expansion" warps (one thread per row,
+//                  1 SHF + 8 LOP3 per 32 dims) and written STRAIGHT INTO TENSOR MEMORY with tcgen05.st —
+//                  the packed index is the only thing streamed from HBM (128 B/row), the expanded bytes
+//                  never touch shared memory;
+//   * D          = s32 accumulators in TMEM, double buffered: tcgen05.mma.kind::i8 (M=128, N<=224, K=32)
+//                  issued by one elected thread; exact integers (<= 15*8*dim, far below 2^31);
+//   * epilogue   = 4 warps read D with tcgen05.ld (thread = index row, columns = queries), screen every
+//                  pair with a 4-FMA fp32 bound against the query's running k-th score, and replay the
+//                  reference's f64 corrective formula (src/batchDotProduct.ts:554-617) only for the pairs
+//                  the screen cannot exclude; survivors are appended to the per-query candidate lists.
+//
+// A is expanded with weights: K position 32g + 4u + j (u = 4s + b) holds  2^b * bit(4s+b of packed byte j of
+// word g)  and B holds  code[dim] * 2^(3-b), so every product is 8 * code * bit and D = 8 * dot exactly;
+// this lets one shift serve eight masks.  Requires code * 8 <= 255, i.e. queryBits <= 5.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "bbq_kernels.cuh"
+
+namespace bbqk {
+
+constexpr int MMA_THREADS = 384;      // warp 0 B loader, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4-7 expansion, 8-11 epilogue
+constexpr int MMA_N_MAX = 224;        // 2 accumulators + >= 2 A stages must fit the 512 TMEM columns
+constexpr int MMA_CHUNK_DIMS = 128;   // dims per A stage (32 TMEM columns)
+
+// per-query constants of the fp32 screen (see k_query_screen)
+struct __align__(16) QScreen {
+  float ly8;    // ly / 8          (D = 8 * dot)
+  float aq;     // A_q = ay * dim + ly * y1
+  float ay;
+  float negl;   // -(L - margin)
+  float wadj;   // EUCLIDEAN upper window (1/(2 tau) + 2 margin); +inf otherwise
+  float tau;
+  float pad0, pad1;
+};
+
+struct IndexBounds {  // maxima over the shard's correctives, for the screen's error margin
+  float lx, ax, mv, wv;
+};
+
+// ---- small PTX wrappers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc], kind::i8, cta_group::1
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// no-swizzle K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// core matrix = 8 rows x 16 B contiguous; LBO = byte step between K-adjacent core matrices,
+// SBO = byte step between row-adjacent core matrices.
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// cute::UMMA::InstrDescriptor for kind::i8: u8 x u8 -> s32, both operands K-major
+__host__ __device__ inline uint32_t make_idesc_i8(int m, int n) {
+  return (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- operand / constant preparation ------------------------------------------------------------
+// B image of pass p: element (n, kpos) at (kpos/16)*(n_tile*16) + (n/8)*128 + (n%8)*16 + kpos%16, where
+// kpos = 32g + 4u + j  <->  dim 32g + 8j + 7 - u, weight 2^(3 - u%4)  (see file header).  Queries beyond nq: 0.
+__global__ void k_query_tiles(const uint8_t* __restrict__ qcodes, int code_ld, int nq, int n_tile, int kbytes,
+                              uint8_t* __restrict__ images) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (pass, n, 16-byte k group)
+  const int k16s = kbytes / 16;
+  const int passes = (nq + n_tile - 1) / n_tile;
+  if (g >= (int64_t)passes * n_tile * k16s) return;
+  const int n = (int)(g % n_tile);
+  const int k16 = (int)((g / n_tile) % k16s);
+  const int p = (int)(g / ((int64_t)n_tile * k16s));
+  const int q = p * n_tile + n;
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  if (q < nq) {
+    const uint8_t* cd = qcodes + (int64_t)q * code_ld;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const int kpos = k16 * 16 + i;
+      const int grp = kpos >> 5, u = (kpos >> 2) & 7, j = kpos & 3;
+      const uint32_t v = (uint32_t)cd[32 * grp + 8 * j + 7 - u] << (3 - (u & 3));
+      w[i >> 2] |= (v & 0xFFu) << (8 * (i & 3));
+    }
+  }
+  uint4* dst = reinterpret_cast<uint4*>(images + (size_t)p * n_tile * kbytes + (size_t)k16 * n_tile * 16 +
+                                        (size_t)(n >> 3) * 128 + (size_t)(n & 7) * 16);
+  *dst = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// maxima of lx, |ax|, lx*x1, |addx| over the shard (finite, lx > 0 rows only)
+__global__ void k_index_bounds(const double* __restrict__ lower, const double* __restrict__ upper,
+                               const double* __restrict__ addc, const uint32_t* __restrict__ compsum, int64_t n,
+                               uint32_t* __restrict__ out4) {
+  float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ax = lower[i], lx = upper[i] - ax, ad = addc[i];
+    if (lx > 0 && bbqn::js_isfinite(lx) && bbqn::js_isfinite(ax) && bbqn::js_isfinite(ad)) {
+      m0 = fmaxf(m0, __double2float_ru(lx));
+      m1 = fmaxf(m1, __double2float_ru(fabs(ax)));
+      m2 = fmaxf(m2, __double2float_ru(lx * (double)compsum[i]));
+      m3 = fmaxf(m3, __double2float_ru(fabs(ad)));
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+    m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    m3 = fmaxf(m3, __shfl_xor_sync(0xffffffffu, m3, o));
+  }
+  if ((threadIdx.x & 31) == 0) {  // non-negative floats order like their bit patterns
+    atomicMax(out4 + 0, __float_as_uint(m0));
+    atomicMax(out4 + 1, __float_as_uint(m1));
+    atomicMax(out4 + 2, __float_as_uint(m2));
+    atomicMax(out4 + 3, __float_as_uint(m3));
+  }
+}
+
+// The screen.  With s = ax*A_q + (lx*x1)*ay + lx*ly*dot (the reference's base score, regrouped) every
+// similarity's admission test "f32(score) >= tau" is, over the reals, a window on s:
+//   EUCLIDEAN  (addq+1-1/tau)/2 <= s - addx/2 <  (addq+1)/2          (pole at 1+e = 0, clamp below it)
+//   COSINE     s + addx >= 2 tau - 1 - addq + cdp
+//   MIP        s + addx >= g(tau) - addq + cdp,  g = (tau-1)*S for tau >= 1 else (1-1/tau)*S,  S = 1/15 (1 if queryBits==1)
+// Dividing by lx > 0:  F = ly*dot + (ax/lx)*A_q + x1*ay + (c*addx)/lx - L/lx  >= 0  [and F <= W/lx].
+// F is evaluated in fp32; `margin` (in s units) bounds every rounding in that chain and the f32 rounding
+// of the score itself, so the screen only ever errs towards admitting a pair to the exact f64 replay.
+__global__ void k_query_screen(const bbqn::QueryTerms* __restrict__ qterms, const float* __restrict__ tau, int nq,
+                               int nq_pad, double dim, double cdp, int sim, int one_bit_query,
+                               const IndexBounds* __restrict__ bounds, QScreen* __restrict__ out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq_pad) return;
+  QScreen s;
+  s.ly8 = s.aq = s.ay = 0.f;
+  s.negl = INFINITY;  // admit everything
+  s.wadj = INFINITY;
+  s.tau = -INFINITY;
+  s.pad0 = s.pad1 = 0.f;
+  if (q < nq) {
+    const bbqn::QueryTerms t = qterms[q];
+    const double tq = (double)tau[q];
+    s.tau = tau[q];
+    const double aq = t.ay * dim + t.ly * t.y1;
+    double L = 0, W = INFINITY;
+    bool ok = tq > 0 && bbqn::js_isfinite(tq) && bbqn::js_isfinite(aq) && bbqn::js_isfinite(t.ay) &&
+              bbqn::js_isfinite(t.ly) && bbqn::js_isfinite(t.addq);
+    if (ok) {
+      if (sim == bbqn::SIM_EUCLIDEAN) {
+        L = (t.addq + 1.0 - 1.0 / tq) / 2;
+        W = 1.0 / (2 * tq);
+      } else if (sim == bbqn::SIM_COSINE) {
+        L = 2 * tq - 1.0 - t.addq + cdp;
+      } else {
+        const double S = one_bit_query ? 1.0 : (1.0 / 15.0);
+        L = (tq >= 1 ? (tq - 1.0) * S : (1.0 - 1.0 / tq) * S) - t.addq + cdp;
+      }
+      const IndexBounds b = *bounds;
+      const double eps = 1.0 / 16777216.0;  // 2^-24
+      const double wv = (sim == bbqn::SIM_EUCLIDEAN) ? 0.5 * b.wv : b.wv;
+      double margin = 32.0 * eps * ((double)b.lx * fabs(t.ly) * fabs(t.y1) + (double)b.ax * fabs(aq) + (double)b.mv * fabs(t.ay) +
+                                    wv + fabs(L)) +
+                      16.0 * eps * (fabs(L) + 1.0 + fabs(t.addq) + fabs(cdp) + fabs(W == INFINITY ? 0.0 : W));
+      ok = bbqn::js_isfinite(margin) && bbqn::js_isfinite(L);
+      if (ok) {
+        s.ly8 = (float)(t.ly / 8);
+        s.aq = (float)aq;
+        s.ay = (float)t.ay;
+        s.negl = __double2float_ru(-(L - margin));
+        s.wadj = (W == INFINITY) ? INFINITY : __double2float_ru(W + 2 * margin);
+      }
+    }
+  }
+  out[q] = s;
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------
+struct MmaParams {
+  const uint8_t* codes;
+  const double* lower;
+  const double* upper;
+  const double* addc;
+  const uint32_t* compsum;
+  int64_t n;
+  int row_bytes;           // packed bytes per row (multiple of 16)
+  int kbytes;              // expanded K bytes per row = row_bytes * 8
+  const uint8_t* images;   // [passes][n_tile * kbytes]
+  const QScreen* qscreen;  // [passes * n_tile]
+  const bbqn::QueryTerms* qterms;
+  int nq, n_tile, passes, nstage;
+  double dim, cdp;
+  int sim, one_bit_query;
+  uint32_t base;
+  int64_t tile_first, tile_stride, ntiles;  // tiles handled: tile_first + i*tile_stride, i < ntiles
+  // SCAN_DUMP: exact score of every pair -> dump[q*dump_ld + i*128 + row]
+  float* dump;
+  int64_t dump_ld;
+  // SCAN_FILTER
+  uint64_t* cand;
+  uint32_t* cand_cnt;
+  uint32_t cap;
+  uint32_t* overflow;
+};
+
+template <int MODE, int SIM>
+__global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const MmaParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // layout: [B image n_tile*kbytes][QScreen n_tile][QueryTerms n_tile][barriers][tmem ptr]
+  uint8_t* b_smem = smem_raw;
+  QScreen* qs_s = reinterpret_cast<QScreen*>(b_smem + (size_t)p.n_tile * p.kbytes);
+  bbqn::QueryTerms* qt_s = reinterpret_cast<bbqn::QueryTerms*>(qs_s + p.n_tile);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(qt_s + p.n_tile);
+  uint64_t* a_full = bars;            // [8]
+  uint64_t* a_empty = bars + 8;       // [8]
+  uint64_t* acc_full = bars + 16;     // [2]
+  uint64_t* acc_empty = bars + 18;    // [2]
+  uint64_t* b_full = bars + 20;
+  uint64_t* b_empty = bars + 21;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 22);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nstage = p.nstage;
+  const int nchunks = p.kbytes / MMA_CHUNK_DIMS;  // A stages per tile
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; i++) {
+      mbar_init(a_full + i, 128);
+      mbar_init(a_empty + i, 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(acc_full + i, 1);
+      mbar_init(acc_empty + i, 128);
+    }
+    mbar_init(b_full, 1);
+    mbar_init(b_empty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  const uint32_t acc_col = 0;                              // accumulators: columns [0, 2*n_tile)
+  const uint32_t a_col = 2u * (uint32_t)p.n_tile;          // A stages: 32 columns each
+
+  if (warp == 0) {
+    // ===== B loader: one resident query block per pass =====
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)p.n_tile * (uint32_t)p.kbytes;
+      for (int pass = 0; pass < p.passes; pass++) {
+        mbar_wait(b_empty, (uint32_t)((pass & 1) ^ 1));  // previous pass's MMAs have drained
+        mbar_expect_tx(b_full, bytes);
+        const uint8_t* src = p.images + (size_t)pass * bytes;
+        for (uint32_t off = 0; off < bytes; off += 32768u) {
+          const uint32_t sz = min(32768u, bytes - off);
+          bulk_g2s(b_smem + off, src + off, sz, b_full);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = make_idesc_i8(128, p.n_tile);
+    const uint32_t lbo = (uint32_t)p.n_tile * 16u;
+    const uint32_t b_addr = smem_u32(b_smem);
+    uint32_t stage = 0, sphase = 0, tcount = 0;
+    for (int pass = 0; pass < p.passes; pass++) {
+      mbar_wait(b_full, (uint32_t)(pass & 1));
+      for (int64_t i = blockIdx.x; i < p.ntiles; i += gridDim.x) {
+        const uint32_t buf = tcount & 1u, bphase = (tcount >> 1) & 1u;
+        mbar_wait(acc_empty + buf, bphase ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc_col + buf * (uint32_t)p.n_tile;
+        for (int kc = 0; kc < nchunks; kc++) {
+          mbar_wait(a_full + stage, sphase);
+          tc_fence_after();
+          if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const uint32_t a_tmem = tmem_base + a_col + stage * 32u + (uint32_t)j * 8u;
+              const uint64_t bdesc = make_kmajor_desc(b_addr + (uint32_t)((kc * 4 + j) * 2) * lbo, lbo, 128u);
+              tc_mma_i8_ts(d_tmem, a_tmem, bdesc, idesc, (kc | j) != 0 ? 1u : 0u);
+            }
+            tc_commit(a_empty + stage);  // frees the A stage once these MMAs have read it
+          }
+          __syncwarp();
+          if (++stage == (uint32_t)nstage) {
+            stage = 0;
+            sphase ^= 1u;
+          }
+        }
+        if (lane == 0) tc_commit(acc_full + buf);
+        __syncwarp();
+        tcount++;
+      }
+      if (lane == 0) tc_commit(b_empty);  // all MMAs of this pass done -> B may be replaced
+      __syncwarp();
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===== expansion: packed 1-bit row -> weighted u8 A operand, straight into TMEM =====
+    const int r = (warp - 4) * 32 + lane;  // row within the tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const int w4 = p.row_bytes >> 4;
+    uint32_t stage = 0, sphase = 0;
+    for (int pass = 0; pass < p.passes; pass++) {
+      for (int64_t i = blockIdx.x; i < p.ntiles; i += gridDim.x) {
+        const int64_t row = (p.tile_first + i * p.tile_stride) * TILE_ROWS + r;
+        const uint4* src = reinterpret_cast<const uint4*>(p.codes + row * (int64_t)p.row_bytes);
+        const bool valid = row < p.n;
+        for (int kc = 0; kc < nchunks; kc++) {
+          const uint4 x = (valid && kc < w4) ? __ldg(src + kc) : make_uint4(0u, 0u, 0u, 0u);
+          uint32_t e[32];
+          const uint32_t ws[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            const uint32_t lo = ws[g], hi = ws[g] >> 4;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+              e[8 * g + b] = lo & (0x01010101u << b);      // u = b     : bit b   of each packed byte, weight 2^b
+              e[8 * g + 4 + b] = hi & (0x01010101u << b);  // u = 4 + b : bit 4+b of each packed byte, weight 2^b
+            }
+          }
+          mbar_wait(a_empty + stage, sphase ^ 1u);
+          tc_fence_after();
+          tc_st32(lane_addr + a_col + stage * 32u, e);
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(a_full + stage);
+          if (++stage == (uint32_t)nstage) {
+            stage = 0;
+            sphase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===== epilogue: screen (fp32) + exact replay (f64) + candidate append =====
+    const int r = (warp - 8) * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const int et = threadIdx.x - 256;  // 0..127 within the epilogue group
+    uint32_t tcount = 0;
+    for (int pass = 0; pass < p.passes; pass++) {
+      // per-pass query constants -> shared memory (epilogue warps only: named barrier 1)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int q0 = pass * p.n_tile;
+      const int nv = min(p.n_tile, p.nq - q0);
+      for (int c = et; c < p.n_tile; c += 128) {
+        if (MODE == SCAN_FILTER) qs_s[c] = p.qscreen[q0 + c];
+        if (c < nv) qt_s[c] = p.qterms[q0 + c];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int64_t i = blockIdx.x; i < p.ntiles; i += gridDim.x) {
+        const int64_t row = (p.tile_first + i * p.tile_stride) * TILE_ROWS + r;
+        const bool valid = row < p.n;
+        double ax = 0, lx = 0, addx = 0, x1 = 0;
+        float rv = 0.f, x1f = 0.f, gv = INFINITY, iv = 0.f;
+        bool always = true;
+        if (valid) {
+          ax = p.lower[row];
+          lx = p.upper[row] - ax;
+          addx = p.addc[row];
+          x1 = (double)p.compsum[row];
+          if (MODE == SCAN_FILTER && lx > 0 && bbqn::js_isfinite(lx) && bbqn::js_isfinite(ax) &&
+              bbqn::js_isfinite(addx)) {
+            const double inv = 1.0 / lx;
+            rv = (float)(ax * inv);
+            x1f = (float)x1;
+            gv = (float)((SIM == bbqn::SIM_EUCLIDEAN ? -0.5 * addx : addx) * inv);
+            iv = (float)inv;
+            always = !(bbqn::js_isfinite((double)rv) && bbqn::js_isfinite((double)gv) && bbqn::js_isfinite((double)iv));
+          }
+        }
+        const uint32_t id = p.base + (uint32_t)row;
+        const uint32_t buf = tcount & 1u, bphase = (tcount >> 1) & 1u;
+        mbar_wait(acc_full + buf, bphase);
+        tc_fence_after();
+        const uint32_t d_addr = lane_addr + buf * (uint32_t)p.n_tile;
+        for (int c0 = 0; c0 < nv; c0 += 16) {
+          int acc[16];
+          tc_ld16(d_addr + (uint32_t)c0, acc);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const int c = c0 + j;
+            if (c < nv) {
+              bool pass_screen = true;
+              if (MODE == SCAN_FILTER) {
+                const float4 a = *reinterpret_cast<const float4*>(&qs_s[c]);
+                const float f = fmaf(a.x, (float)acc[j], fmaf(rv, a.y, fmaf(x1f, a.z, fmaf(a.w, iv, gv))));
+                pass_screen = f >= 0.f;
+                if (SIM == bbqn::SIM_EUCLIDEAN) pass_screen = pass_screen && !(f > qs_s[c].wadj * iv);
+                pass_screen = pass_screen || always;
+              }
+              if (pass_screen && valid) {
+                const float score = bbqn::score_f32((double)(acc[j] >> 3), ax, lx, addx, x1, qt_s[c], p.dim, p.cdp, SIM,
+                                                    p.one_bit_query != 0);
+                const int q = q0 + c;
+                if (MODE == SCAN_DUMP) {
+                  p.dump[(int64_t)q * p.dump_ld + i * TILE_ROWS + r] = score;
+                } else if (score >= qs_s[c].tau) {
+                  const uint32_t pos = atomicAdd(p.cand_cnt + q, 1u);
+                  if (pos < p.cap) p.cand[(size_t)q * p.cap + pos] = bbqn::topk_key(score, id);
+                  else *p.overflow = 1u;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(acc_empty + buf);
+        tcount++;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace bbqk

@@ -279,7 +279,8 @@ class BinaryQuantizationFormat:
         s = _native.BbqStats()
         _check(_native.load().bbq_get_stats(self._ctx, C.byref(s)))
         return {"kernel_launches": s.kernel_launches, "last_candidates": s.last_candidates,
-                "last_path": s.last_path, "last_overflow": s.last_overflow, "scan_launches": s.scan_launches,
+                "last_path": s.last_path, "last_overflow": s.last_overflow, "last_engine": s.last_engine,
+                "scan_launches": s.scan_launches,
                 "scan_ms": s.scan_ms, "quantize_ms": s.quantize_ms, "select_ms": s.select_ms}
 
     def setProfiling(self, enabled: bool):

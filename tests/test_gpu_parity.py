@@ -27,17 +27,21 @@ def bbq():
     return bbq_b200
 
 
-def make_format(bbq, sim, qb=4, lam=0.1, iters=5, force_path=None):
-    old = os.environ.pop("BBQ_FORCE_PATH", None)
+def make_format(bbq, sim, qb=4, lam=0.1, iters=5, force_path=None, scan=None):
+    """force_path / scan are test knobs read by bbq_create (BBQ_FORCE_PATH, BBQ_SCAN=popc|mma)."""
+    saved = {k: os.environ.pop(k, None) for k in ("BBQ_FORCE_PATH", "BBQ_SCAN")}
     if force_path is not None:
         os.environ["BBQ_FORCE_PATH"] = str(force_path)
+    if scan is not None:
+        os.environ["BBQ_SCAN"] = scan
     try:
         return bbq.createBinaryQuantizationFormat(
             {"queryBits": qb, "indexBits": 1, "quantizer": {"similarityFunction": sim, "lambda": lam, "iters": iters}})
     finally:
-        os.environ.pop("BBQ_FORCE_PATH", None)
-        if old is not None:
-            os.environ["BBQ_FORCE_PATH"] = old
+        for k, v in saved.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
 
 
 def bits_equal(a, b):
@@ -283,6 +287,55 @@ def test_batch_equals_single_and_is_deterministic(bbq):
     for qi in (0, 33, 69):
         one = fmt.searchNearestNeighbors(qs[qi], qv, 10)
         assert [r["index"] for r in one] == gi[qi].tolist()
+
+
+# ---- K2: the tcgen05 batched scan must give the same answers as the popcount scan and the oracle -------------
+@pytest.mark.parametrize("sim", SIMS)
+@pytest.mark.parametrize("n,dim,nq,k,qb", [
+    (20000, 256, 70, 10, 4),       # one pass, ragged query block
+    (33000, 100, 40, 10, 4),       # dim % 128 != 0, ragged last tile
+    (40000, 1024, 300, 10, 4),     # two passes of resident query blocks (BASELINE dims)
+    (20000, 768, 64, 100, 4),      # k = 100
+    (20000, 128, 96, 10, 1),       # 1-bit queries
+    (20000, 128, 96, 10, 5),       # widest query the weighted expansion supports
+])
+def test_mma_scan_matches_oracle_and_popcount(bbq, sim, n, dim, nq, k, qb):
+    rows, qs = gaussian(n, dim, 101 + n + dim), gaussian(nq, dim, 102 + n)
+    idx = O.quantize_vectors(rows, sim=sim, want_unpacked=False)
+    fm = make_format(bbq, sim, qb=qb, scan="mma")
+    fp = make_format(bbq, sim, qb=qb, scan="popc")
+    qm = fm.adoptQuantized(idx.packed, idx.corr, idx.centroid)
+    qp = fp.adoptQuantized(idx.packed, idx.corr, idx.centroid)
+    mi, ms = fm.searchBatch(qs, qm, k)
+    pi, ps = fp.searchBatch(qs, qp, k)
+    assert fm.stats()["last_engine"] == 2 and fm.stats()["last_path"] == 1 and fm.stats()["last_overflow"] == 0
+    assert fp.stats()["last_engine"] == 1
+    assert np.array_equal(mi, pi) and bits_equal(ms, ps)
+    for qi in range(0, nq, max(1, nq // 6)):
+        wi, ws = O.search_nearest_neighbors(qs[qi], idx, k, query_bits=qb, mode="canonical")
+        assert mi[qi].tolist() == wi.tolist() and bits_equal(ms[qi], ws)
+
+
+def test_mma_scan_ties_and_degenerate_rows(bbq):
+    """Exact f32 ties (duplicate rows) and rows whose interval is degenerate (always sent to the exact replay)."""
+    rows = gaussian(50, 128, 111)
+    rows[7] = 0
+    rows = np.concatenate([rows] * 400)     # 20000 rows, every score 400 times
+    for sim in SIMS:
+        idx = O.quantize_vectors(rows[:50], sim=sim, want_unpacked=False, centroid=np.zeros(128, np.float32))
+        corr = idx.corr.copy()
+        corr[11, 1] = corr[11, 0]           # lx == 0
+        corr[12, 1] = np.nan                # non-finite interval
+        packed, corr = np.concatenate([idx.packed] * 400), np.concatenate([corr] * 400)
+        big = O.OracleIndex(idx.centroid, packed, None, corr, 128, sim, 1)
+        fm = make_format(bbq, sim, scan="mma")
+        qm = fm.adoptQuantized(packed, corr, idx.centroid)
+        qs = gaussian(64, 128, 112)
+        mi, ms = fm.searchBatch(qs, qm, 30)
+        assert fm.stats()["last_engine"] == 2
+        for qi in (0, 13, 63):
+            wi, ws = O.search_nearest_neighbors(qs[qi], big, 30, mode="canonical")
+            assert mi[qi].tolist() == wi.tolist() and bits_equal(ms[qi], ws)
 
 
 # ---- sharding: G shards + deterministic merge == one index (SURVEY §8e) --------------------------------------
