@@ -27,7 +27,8 @@
 
 namespace bbqk {
 
-constexpr int MMA_THREADS = 384;      // warp 0 B loader, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4-7 expansion, 8-11 epilogue
+constexpr int MMA_EPI_WARPS = 8;      // epilogue warps: two per TMEM lane quarter, alternating 16-column chunks
+constexpr int MMA_THREADS = (8 + MMA_EPI_WARPS) * 32;  // warp 0 B loader, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4-7 expansion, 8.. epilogue
 constexpr int MMA_N_MAX = 224;        // 2 accumulators + >= 2 A stages must fit the 512 TMEM columns
 constexpr int MMA_CHUNK_DIMS = 128;   // dims per A stage (32 TMEM columns)
 
@@ -202,9 +203,9 @@ __global__ void k_query_screen(const bbqn::QueryTerms* __restrict__ qterms, cons
   if (q >= nq_pad) return;
   QScreen s;
   s.ly8 = s.aq = s.ay = 0.f;
-  s.negl = INFINITY;  // admit everything
+  s.negl = (q < nq) ? INFINITY : -INFINITY;  // real query: admit everything unless bounded below; padding: admit nothing
   s.wadj = INFINITY;
-  s.tau = -INFINITY;
+  s.tau = (q < nq) ? -INFINITY : INFINITY;
   s.pad0 = s.pad1 = 0.f;
   if (q < nq) {
     const bbqn::QueryTerms t = qterms[q];
@@ -271,6 +272,19 @@ struct MmaParams {
   uint32_t* overflow;
 };
 
+// The exact replay of one (row, query) pair the screen could not exclude — deliberately out of line: it runs
+// for ~0.1% of the pairs and must not bloat (or serialise) the branch-free screen loop.
+template <int SIM>
+__device__ __noinline__ void mma_exact_pair(const MmaParams& p, int acc, int q, float tau, const bbqn::QueryTerms* qt,
+                                            double ax, double lx, double addx, double x1, uint32_t id) {
+  const float score = bbqn::score_f32((double)(acc >> 3), ax, lx, addx, x1, *qt, p.dim, p.cdp, SIM, p.one_bit_query != 0);
+  if (q < p.nq && score >= tau) {
+    const uint32_t pos = atomicAdd(p.cand_cnt + q, 1u);
+    if (pos < p.cap) p.cand[(size_t)q * p.cap + pos] = bbqn::topk_key(score, id);
+    else *p.overflow = 1u;
+  }
+}
+
 template <int MODE, int SIM>
 __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const MmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -298,7 +312,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const MmaParams p) 
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(acc_full + i, 1);
-      mbar_init(acc_empty + i, 128);
+      mbar_init(acc_empty + i, MMA_EPI_WARPS * 32);
     }
     mbar_init(b_full, 1);
     mbar_init(b_empty, 1);
@@ -371,68 +385,90 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const MmaParams p) 
     }
   } else if (warp >= 4 && warp < 8) {
     // ===== expansion: packed 1-bit row -> weighted u8 A operand, straight into TMEM =====
+    // The (tile, chunk) sequence of a pass is walked as one flat stream so that the 16-byte packed chunks can
+    // be prefetched PF deep across tile boundaries (the loads come from HBM: ~1 us each if not in flight early).
     const int r = (warp - 4) * 32 + lane;  // row within the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const int w4 = p.row_bytes >> 4;
+    constexpr int PF = 8;
+    const int64_t my_tiles = (p.ntiles > blockIdx.x) ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total = my_tiles * nchunks;
+    auto load_chunk = [&](int64_t f) -> uint4 {
+      if (f >= total) return make_uint4(0u, 0u, 0u, 0u);
+      const int64_t ti = f / nchunks;
+      const int kc = (int)(f - ti * nchunks);
+      const int64_t row = (p.tile_first + (blockIdx.x + ti * gridDim.x) * p.tile_stride) * TILE_ROWS + r;
+      if (row >= p.n) return make_uint4(0u, 0u, 0u, 0u);
+      return __ldg(reinterpret_cast<const uint4*>(p.codes + row * (int64_t)p.row_bytes) + kc);
+    };
     uint32_t stage = 0, sphase = 0;
     for (int pass = 0; pass < p.passes; pass++) {
-      for (int64_t i = blockIdx.x; i < p.ntiles; i += gridDim.x) {
-        const int64_t row = (p.tile_first + i * p.tile_stride) * TILE_ROWS + r;
-        const uint4* src = reinterpret_cast<const uint4*>(p.codes + row * (int64_t)p.row_bytes);
-        const bool valid = row < p.n;
-        for (int kc = 0; kc < nchunks; kc++) {
-          const uint4 x = (valid && kc < w4) ? __ldg(src + kc) : make_uint4(0u, 0u, 0u, 0u);
-          uint32_t e[32];
-          const uint32_t ws[4] = {x.x, x.y, x.z, x.w};
+      uint4 q[PF];
 #pragma unroll
-          for (int g = 0; g < 4; g++) {
-            const uint32_t lo = ws[g], hi = ws[g] >> 4;
+      for (int i = 0; i < PF; i++) q[i] = load_chunk(i);
+      for (int64_t f0 = 0; f0 < total; f0 += PF) {
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-              e[8 * g + b] = lo & (0x01010101u << b);      // u = b     : bit b   of each packed byte, weight 2^b
-              e[8 * g + 4 + b] = hi & (0x01010101u << b);  // u = 4 + b : bit 4+b of each packed byte, weight 2^b
+        for (int i = 0; i < PF; i++) {
+          if (f0 + i < total) {
+            const uint4 x = q[i];
+            q[i] = load_chunk(f0 + i + PF);
+            uint32_t e[32];
+            const uint32_t ws[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+              const uint32_t lo = ws[g], hi = ws[g] >> 4;
+#pragma unroll
+              for (int b = 0; b < 4; b++) {
+                e[8 * g + b] = lo & (0x01010101u << b);      // u = b     : bit b   of each packed byte, weight 2^b
+                e[8 * g + 4 + b] = hi & (0x01010101u << b);  // u = 4 + b : bit 4+b of each packed byte, weight 2^b
+              }
             }
-          }
-          mbar_wait(a_empty + stage, sphase ^ 1u);
-          tc_fence_after();
-          tc_st32(lane_addr + a_col + stage * 32u, e);
-          tc_wait_st();
-          tc_fence_before();
-          mbar_arrive(a_full + stage);
-          if (++stage == (uint32_t)nstage) {
-            stage = 0;
-            sphase ^= 1u;
+            mbar_wait(a_empty + stage, sphase ^ 1u);
+            tc_fence_after();
+            tc_st32(lane_addr + a_col + stage * 32u, e);
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(a_full + stage);
+            if (++stage == (uint32_t)nstage) {
+              stage = 0;
+              sphase ^= 1u;
+            }
           }
         }
       }
     }
   } else if (warp >= 8) {
-    // ===== epilogue: screen (fp32) + exact replay (f64) + candidate append =====
-    const int r = (warp - 8) * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const int et = threadIdx.x - 256;  // 0..127 within the epilogue group
+    // ===== epilogue: screen (fp32, branch-free over 16 queries) + exact replay (f64) + candidate append =====
+    const int ew = warp - 8;                       // 0 .. MMA_EPI_WARPS-1
+    const int quarter = ew & 3;                    // TMEM lane quarter this warp may touch (== warp % 4)
+    const int sub = ew >> 2;                       // which of the quarter's warps: takes chunks sub, sub+NSUB, ...
+    constexpr int NSUB = MMA_EPI_WARPS / 4;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const int et = threadIdx.x - 256;              // 0 .. MMA_EPI_WARPS*32-1 within the epilogue group
     uint32_t tcount = 0;
     for (int pass = 0; pass < p.passes; pass++) {
       // per-pass query constants -> shared memory (epilogue warps only: named barrier 1)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(MMA_EPI_WARPS * 32) : "memory");
       const int q0 = pass * p.n_tile;
       const int nv = min(p.n_tile, p.nq - q0);
-      for (int c = et; c < p.n_tile; c += 128) {
+      for (int c = et; c < p.n_tile; c += MMA_EPI_WARPS * 32) {
         if (MODE == SCAN_FILTER) qs_s[c] = p.qscreen[q0 + c];
         if (c < nv) qt_s[c] = p.qterms[q0 + c];
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(MMA_EPI_WARPS * 32) : "memory");
       for (int64_t i = blockIdx.x; i < p.ntiles; i += gridDim.x) {
         const int64_t row = (p.tile_first + i * p.tile_stride) * TILE_ROWS + r;
         const bool valid = row < p.n;
         double ax = 0, lx = 0, addx = 0, x1 = 0;
-        float rv = 0.f, x1f = 0.f, gv = INFINITY, iv = 0.f;
-        bool always = true;
+        // screen constants of this row; defaults make an out-of-range row fail every screen
+        float rv = 0.f, x1f = 0.f, gv = -INFINITY, iv = 0.f;
+        bool always = false;
         if (valid) {
           ax = p.lower[row];
           lx = p.upper[row] - ax;
           addx = p.addc[row];
           x1 = (double)p.compsum[row];
+          always = true;  // degenerate correctives: every pair of this row goes to the exact replay
           if (MODE == SCAN_FILTER && lx > 0 && bbqn::js_isfinite(lx) && bbqn::js_isfinite(ax) &&
               bbqn::js_isfinite(addx)) {
             const double inv = 1.0 / lx;
@@ -448,35 +484,50 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const MmaParams p) 
         mbar_wait(acc_full + buf, bphase);
         tc_fence_after();
         const uint32_t d_addr = lane_addr + buf * (uint32_t)p.n_tile;
-        for (int c0 = 0; c0 < nv; c0 += 16) {
-          int acc[16];
+        // software pipeline over this warp's 16-column chunks: the next chunk's TMEM load is in flight
+        // while the current one is screened
+        int acc[16], nxt[16];
+        int c0 = sub * 16;
+        if (c0 < nv) {
           tc_ld16(d_addr + (uint32_t)c0, acc);
           tc_wait_ld();
+        }
+        for (; c0 < nv; c0 += NSUB * 16) {
+          const int c1 = c0 + NSUB * 16;
+          if (c1 < nv) tc_ld16(d_addr + (uint32_t)c1, nxt);
+          if (MODE == SCAN_DUMP) {
+            if (valid) {
 #pragma unroll
-          for (int j = 0; j < 16; j++) {
-            const int c = c0 + j;
-            if (c < nv) {
-              bool pass_screen = true;
-              if (MODE == SCAN_FILTER) {
-                const float4 a = *reinterpret_cast<const float4*>(&qs_s[c]);
-                const float f = fmaf(a.x, (float)acc[j], fmaf(rv, a.y, fmaf(x1f, a.z, fmaf(a.w, iv, gv))));
-                pass_screen = f >= 0.f;
-                if (SIM == bbqn::SIM_EUCLIDEAN) pass_screen = pass_screen && !(f > qs_s[c].wadj * iv);
-                pass_screen = pass_screen || always;
-              }
-              if (pass_screen && valid) {
-                const float score = bbqn::score_f32((double)(acc[j] >> 3), ax, lx, addx, x1, qt_s[c], p.dim, p.cdp, SIM,
-                                                    p.one_bit_query != 0);
-                const int q = q0 + c;
-                if (MODE == SCAN_DUMP) {
-                  p.dump[(int64_t)q * p.dump_ld + i * TILE_ROWS + r] = score;
-                } else if (score >= qs_s[c].tau) {
-                  const uint32_t pos = atomicAdd(p.cand_cnt + q, 1u);
-                  if (pos < p.cap) p.cand[(size_t)q * p.cap + pos] = bbqn::topk_key(score, id);
-                  else *p.overflow = 1u;
-                }
+              for (int j = 0; j < 16; j++) {
+                const int c = c0 + j;
+                if (c < nv)
+                  p.dump[(int64_t)(q0 + c) * p.dump_ld + i * TILE_ROWS + r] = bbqn::score_f32(
+                      (double)(acc[j] >> 3), ax, lx, addx, x1, qt_s[c], p.dim, p.cdp, SIM, p.one_bit_query != 0);
               }
             }
+          } else {
+            uint32_t mask = 0u;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              const float4 a = *reinterpret_cast<const float4*>(&qs_s[c0 + j]);
+              const float f = fmaf(a.x, (float)acc[j], fmaf(rv, a.y, fmaf(x1f, a.z, fmaf(a.w, iv, gv))));
+              bool ps = f >= 0.f;
+              if (SIM == bbqn::SIM_EUCLIDEAN) ps = ps && !(f > qs_s[c0 + j].wadj * iv);
+              mask |= ps ? (1u << j) : 0u;
+            }
+            if (always) mask = 0xFFFFu;
+            if (mask != 0u) {
+#pragma unroll
+              for (int j = 0; j < 16; j++)
+                if (mask & (1u << j))
+                  mma_exact_pair<SIM>(p, acc[j], q0 + c0 + j, qs_s[c0 + j].tau, &qt_s[min(c0 + j, nv - 1)], ax, lx, addx,
+                                      x1, id);
+            }
+          }
+          if (c1 < nv) {
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; j++) acc[j] = nxt[j];
           }
         }
         tc_fence_before();
