@@ -78,6 +78,7 @@ struct bbq_ctx {
   // query scratch
   DevBuf qrows, qT, qcodes, qcorr, planes, qterms, tau, dump, cand, cand_cnt, flag, lists_a, lists_b,
       out_idx, out_score, dots, images, qscreen;
+  int query_quantizer = 0;  // BBQ_QQUANT=thread forces the one-thread-per-query form (tests)
   int scan_engine = 0;  // BBQ_SCAN: 0 auto, 1 popcount kernel only, 2 tensor-core kernel whenever it can run
   uint32_t* h_flag = nullptr;  // pinned: [0..nq) candidate counts, [nq] overflow flag
   // profiling (bbq_set_profiling): event pairs per kernel group, drained by bbq_get_stats
@@ -179,6 +180,7 @@ extern "C" int bbq_create(const bbq_config* config, bbq_ctx** out_ctx) {
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaMallocHost(&c->h_flag, (QUERY_BATCH + 1) * sizeof(uint32_t)));
   if (const char* e = getenv("BBQ_FORCE_PATH")) c->force_path = atoi(e);
+  if (const char* e = getenv("BBQ_QQUANT")) c->query_quantizer = !strcmp(e, "thread") ? 1 : 0;
   if (const char* e = getenv("BBQ_SCAN")) c->scan_engine = !strcmp(e, "popc") ? 1 : !strcmp(e, "mma") ? 2 : 0;
   *out_ctx = c;
   return BBQ_OK;
@@ -648,14 +650,26 @@ static int quantize_queries(bbq_index* ix, const float* d_queries, int nq, cudaS
   TRY(c->qcorr.reserve((size_t)nq * 4 * sizeof(double)));
   TRY(c->planes.reserve((size_t)nq * nb * words * sizeof(uint32_t)));
   TRY(c->qterms.reserve((size_t)nq * sizeof(bbqn::QueryTerms)));
-  float* T = c->qT.as<float>();
   ProfScope prof(c, st, PROF_QUANT);
-  dim3 grid((nq + 31) / 32, (dim + 31) / 32), block(32, 8);
-  LAUNCH(c, k_transpose, grid, block, 0, st, d_queries, (int64_t)nq, dim, T, (int64_t)nq);
-  if (c->cfg.similarity == BBQ_SIM_COSINE)
-    LAUNCH(c, k_normalize_T, (nq + 63) / 64, 64, 0, st, T, (int64_t)nq, (int64_t)nq, dim, 2);
-  LAUNCH(c, k_osq_query, (nq + 63) / 64, 64, 0, st, T, (int64_t)nq, nq, dim, ix->centroid, (int)c->cfg.similarity, nb,
-         c->cfg.lambda, (int)c->cfg.iters, c->qcodes.as<uint8_t>(), code_ld, c->qcorr.as<double>());
+  const int ntimes = c->cfg.similarity == BBQ_SIM_COSINE ? 2 : 0;
+  const size_t per_warp = (size_t)((dim + 3) & ~3) * sizeof(float) + 7 * 33 * sizeof(double);
+  const size_t smem = per_warp * OSQW_WARPS;
+  if (c->query_quantizer != 1 && smem <= 200 * 1024) {
+    // latency form: one warp per query
+    if (smem > 48 * 1024)
+      CU(cudaFuncSetAttribute(k_osq_query_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAUNCH(c, k_osq_query_warp, (nq + OSQW_WARPS - 1) / OSQW_WARPS, OSQW_WARPS * 32, smem, st, d_queries, nq, dim,
+           ix->centroid, (int)c->cfg.similarity, nb, c->cfg.lambda, (int)c->cfg.iters, ntimes, c->qcodes.as<uint8_t>(),
+           code_ld, c->qcorr.as<double>());
+  } else {
+    // throughput form: one thread per query over the transposed scratch (same code as the index build)
+    float* T = c->qT.as<float>();
+    dim3 grid((nq + 31) / 32, (dim + 31) / 32), block(32, 8);
+    LAUNCH(c, k_transpose, grid, block, 0, st, d_queries, (int64_t)nq, dim, T, (int64_t)nq);
+    if (ntimes) LAUNCH(c, k_normalize_T, (nq + 63) / 64, 64, 0, st, T, (int64_t)nq, (int64_t)nq, dim, ntimes);
+    LAUNCH(c, k_osq_query, (nq + 63) / 64, 64, 0, st, T, (int64_t)nq, nq, dim, ix->centroid, (int)c->cfg.similarity, nb,
+           c->cfg.lambda, (int)c->cfg.iters, c->qcodes.as<uint8_t>(), code_ld, c->qcorr.as<double>());
+  }
   const int64_t total = (int64_t)nq * nb * words;
   LAUNCH(c, k_query_planes, (unsigned)((total + 127) / 128), 128, 0, st, c->qcodes.as<uint8_t>(), code_ld,
          c->qcorr.as<double>(), nq, nb, words, c->planes.as<uint32_t>(), c->qterms.as<bbqn::QueryTerms>());
@@ -911,7 +925,13 @@ static int search_filtered(bbq_index* ix, int nq, uint32_t k, int32_t* d_out_idx
     s.tile_stride = stride;
     s.base = (uint32_t)ix->base;
     s.tau_out = c->tau.as<float>();
-    TRY(launch_select<SEL_DENSE>(c, s, s.m, st));
+    if (k <= (uint32_t)TAU_THREADS) {
+      ProfScope prof(c, st, PROF_SELECT);
+      LAUNCH(c, k_tau_from_sample, nq, TAU_THREADS, 0, st, c->dump.as<float>(), (int64_t)SELECT_MAX, s.m, k,
+             c->tau.as<float>());
+    } else {
+      TRY(launch_select<SEL_DENSE>(c, s, s.m, st));
+    }
   }
   uint32_t* cnt = c->cand_cnt.as<uint32_t>();
   CU(cudaMemsetAsync(cnt, 0, (size_t)(nq + 1) * sizeof(uint32_t), st));

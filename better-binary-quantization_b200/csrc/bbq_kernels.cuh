@@ -162,6 +162,211 @@ __global__ void k_osq_query(const float* __restrict__ T, int64_t ld, int nq, int
   qcorr[4 * t + 3] = qsum;
 }
 
+// K4, latency form: ONE WARP per query.  The reference's sums are strictly sequential f64 (any re-association can
+// flip a Math.round), so the per-component terms are computed by the 32 lanes in parallel and each chain is then
+// accumulated in component order by one lane reading the staged terms from shared memory — up to 7 chains run
+// side by side in lanes 0..6.  The coordinate descent is fused: the loss of a candidate interval and the grid
+// sums of that same interval (needed only if it is accepted) share one pass.  Same arithmetic, same order, same
+// bits as bbqn::osq_interval / osq_codes (tests compare both with the oracle).
+template <int K, class Gen>
+__device__ __forceinline__ void warp_seq_sums(int d, int lane, double (*terms)[33], Gen gen, double (&result)[K]) {
+  double acc = 0.0;
+  for (int base = 0; base < d; base += 32) {
+    const int i = base + lane;
+    double t[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) t[k] = 0.0;
+    if (i < d) gen(i, t);
+#pragma unroll
+    for (int k = 0; k < K; k++) terms[k][lane] = t[k];
+    __syncwarp();
+    if (lane < K) {
+      const int cnt = min(32, d - base);
+      const double* row = terms[lane];
+#pragma unroll 8
+      for (int m = 0; m < cnt; m++) acc += row[m];
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int k = 0; k < K; k++) result[k] = __shfl_sync(0xffffffffu, acc, k);
+}
+
+constexpr int OSQW_WARPS = 4;  // queries per CTA
+
+__global__ void __launch_bounds__(OSQW_WARPS * 32) k_osq_query_warp(
+    const float* __restrict__ queries, int nq, int dim, const float* __restrict__ centroid, int sim, int bits,
+    double lambda, int iters, int normalize_times, uint8_t* __restrict__ qcodes, int code_ld,
+    double* __restrict__ qcorr) {
+  extern __shared__ __align__(16) uint8_t osqw_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * OSQW_WARPS + warp;
+  const size_t per_warp = (size_t)((dim + 3) & ~3) * sizeof(float) + 7 * 33 * sizeof(double);
+  double(*terms)[33] = reinterpret_cast<double(*)[33]>(osqw_smem + warp * per_warp);
+  float* vec = reinterpret_cast<float*>(osqw_smem + warp * per_warp + 7 * 33 * sizeof(double));
+  if (q >= nq) return;  // whole warp
+  const float* src = queries + (int64_t)q * dim;
+  for (int i = lane; i < dim; i += 32) vec[i] = src[i];
+  __syncwarp();
+  // normalizeVector (src/vectorOperations.ts:11-34), twice for COSINE queries (binaryQuantizationFormat.ts:337,279)
+  for (int rep = 0; rep < normalize_times; rep++) {
+    double r1[1];
+    warp_seq_sums<1>(dim, lane, terms, [&](int i, double* t) { t[0] = (double)vec[i] * (double)vec[i]; }, r1);
+    const double n = sqrt(r1[0]);
+    for (int i = lane; i < dim; i += 32) vec[i] = (n == 0) ? 0.0f : (float)((double)vec[i] / n);
+    __syncwarp();
+  }
+  auto cen = [&](int i) { return (double)__ldg(centroid + i); };
+  auto w_of = [&](int i) { return (double)(float)((double)vec[i] - cen(i)); };
+  // statistics: centroidDot, mean, norm (three chains) + exact min/max
+  double st[3];
+  warp_seq_sums<3>(dim, lane, terms, [&](int i, double* t) {
+    const double w = w_of(i);
+    t[0] = (sim != bbqn::SIM_EUCLIDEAN) ? (double)vec[i] * cen(i) : 0.0;
+    t[1] = w;
+    t[2] = w * w;
+  }, st);
+  double mn = 1.7976931348623157e308, mx = -1.7976931348623157e308;
+  for (int i = lane; i < dim; i += 32) {
+    const double cv = (double)vec[i] - cen(i);
+    mn = bbqn::js_min(mn, cv);
+    mx = bbqn::js_max(mx, cv);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = bbqn::js_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = bbqn::js_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  const double centroidDot = (sim != bbqn::SIM_EUCLIDEAN) ? st[0] : 0.0;
+  const double mean = st[1] / (double)dim;
+  const double nrm = sqrt(st[2]);
+  double r1[1];
+  warp_seq_sums<1>(dim, lane, terms, [&](int i, double* t) {
+    const double diff = w_of(i) - mean;
+    t[0] = diff * diff;
+  }, r1);
+  const double sd = sqrt(r1[0] / (double)dim);
+  const double g = bbqn::mse_grid(bits);
+  double a = bbqn::js_clamp(-g * sd + mean, mn, mx);
+  double b = bbqn::js_clamp(g * sd + mean, mn, mx);
+  const int points = 1 << bits;
+  const double pm1 = (double)(points - 1);
+  // one pass: loss(ai, bi) [chains 0,1] and the grid sums of (ai, bi) [chains 2..6]
+  auto fused_pass = [&](double ai, double bi, double (&out)[7]) {
+    const double step = (bi - ai) / pm1;      // computeLoss: step, 1/step
+    const double stepInvL = 1.0 / step;
+    const double stepInvG = pm1 / (bi - ai);  // optimizeIntervals: (points-1)/(b-a)
+    warp_seq_sums<7>(dim, lane, terms, [&](int i, double* t) {
+      const double xi = w_of(i);
+      const double clamped = bbqn::js_clamp(xi, ai, bi);
+      const double kl = bbqn::js_round((clamped - ai) * stepInvL);
+      const double xiq = ai + step * kl;
+      const double diff = xi - xiq;
+      t[0] = xi * diff;
+      t[1] = diff * diff;
+      const double kg = bbqn::js_round((clamped - ai) * stepInvG);
+      const double s = kg / pm1;
+      const double oms = 1.0 - s;
+      t[2] = oms * oms;
+      t[3] = oms * s;
+      t[4] = s * s;
+      t[5] = xi * oms;
+      t[6] = xi * s;
+    }, out);
+  };
+  double ps[7];
+  fused_pass(a, b, ps);
+  double loss0 = (1.0 - lambda) * ps[0] * ps[0] / nrm + lambda * ps[1];
+  const double scale = (1.0 - lambda) / nrm;
+  if (bbqn::js_isfinite(scale)) {
+    for (int iter = 0; iter < iters; iter++) {
+      const double daa = ps[2], dab = ps[3], dbb = ps[4], dax = ps[5], dbx = ps[6];
+      const double m0 = scale * dax * dax + lambda * daa;
+      const double m1 = scale * dax * dbx + lambda * dab;
+      const double m2 = scale * dbx * dbx + lambda * dbb;
+      const double det = m0 * m2 - m1 * m1;
+      if (fabs(det) < 1e-12) break;
+      const double aOpt = (m2 * dax - m1 * dbx) / det;
+      const double bOpt = (m0 * dbx - m1 * dax) / det;
+      if (fabs(a - aOpt) < 1e-8 && fabs(b - bOpt) < 1e-8) break;
+      double pn[7];
+      fused_pass(aOpt, bOpt, pn);
+      const double loss1 = (1.0 - lambda) * pn[0] * pn[0] / nrm + lambda * pn[1];
+      if (loss1 > loss0) break;
+      a = aOpt;
+      b = bOpt;
+      loss0 = loss1;
+#pragma unroll
+      for (int k = 0; k < 7; k++) ps[k] = pn[k];
+    }
+  }
+  // codes (src/optimizedScalarQuantizer.ts:192-216); the component sum is a sum of integers (or NaN): any order is exact
+  const int nSteps = points - 1;
+  const double step = nSteps > 0 ? (b - a) / (double)nSteps : 0.0;
+  const double stepInv = step > 0 ? 1.0 / step : 0.0;
+  const double threshold = (a + b) / 2;
+  uint8_t* out = qcodes + (int64_t)q * code_ld;
+  double qsum = 0.0;
+  for (int i = lane; i < code_ld; i += 32) {
+    uint8_t code = 0;
+    if (i < dim) {
+      const double clamped = bbqn::js_clamp(w_of(i), a, b);
+      if (bits == 1) {
+        const int c1 = clamped >= threshold ? 1 : 0;
+        code = (uint8_t)c1;
+        qsum += (double)c1;
+      } else {
+        const double assignment = bbqn::js_round((clamped - a) * stepInv);
+        const double stored = bbqn::js_min(assignment, (double)nSteps);
+        code = (stored != stored) ? (uint8_t)0 : (uint8_t)(((long long)stored) & 0xFF);
+        qsum += assignment;
+      }
+    }
+    out[i] = code;
+  }
+  for (int o = 16; o > 0; o >>= 1) qsum += __shfl_xor_sync(0xffffffffu, qsum, o);
+  if (lane == 0) {
+    qcorr[4 * q + 0] = a;
+    qcorr[4 * q + 1] = b;
+    qcorr[4 * q + 2] = (sim == bbqn::SIM_EUCLIDEAN) ? nrm : centroidDot;
+    qcorr[4 * q + 3] = qsum;
+  }
+}
+
+// Threshold from the sample: tau[q] = k-th largest of the per-thread maxima over the sampled scores.  The k
+// largest maxima belong to k distinct rows, so tau is a valid lower bound of the final k-th best score — and
+// almost as tight as the exact k-th of the sample (the top few rarely share a thread), at a fraction of the cost
+// of sorting the whole sample.  Requires k <= TAU_THREADS.
+constexpr int TAU_THREADS = 512;
+__global__ void __launch_bounds__(TAU_THREADS) k_tau_from_sample(const float* __restrict__ scores, int64_t ld, uint32_t m,
+                                                                  uint32_t k, float* __restrict__ tau) {
+  __shared__ uint32_t keys[TAU_THREADS];
+  const int q = blockIdx.x, tid = threadIdx.x;
+  uint32_t best = 0u;  // ordered-score key; 0 = nothing / NaN
+  for (uint32_t i = tid; i < m; i += TAU_THREADS)
+    best = max(best, (uint32_t)(bbqn::topk_key(scores[(int64_t)q * ld + i], 0u) >> 32));
+  keys[tid] = best;
+  for (uint32_t size = 2; size <= TAU_THREADS; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      if (tid < TAU_THREADS / 2) {
+        const uint32_t i = 2 * tid - (tid & (stride - 1)), j = i + stride;
+        const uint32_t x = keys[i], y = keys[j];
+        const bool desc = (i & size) == 0;
+        if (desc ? (x < y) : (x > y)) {
+          keys[i] = y;
+          keys[j] = x;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float t = -INFINITY;
+    if (k >= 1 && k <= TAU_THREADS && keys[k - 1] != 0u) t = bbqn::topk_key_score((uint64_t)keys[k - 1] << 32);
+    tau[q] = t;
+  }
+}
+
 // Query bit-planes in the index's bit order: plane b, word w holds bit b of codes[32w .. 32w+31],
 // dim 8j+t at bit 7-t of byte j (so `plane & row` pairs equal dims).  Layout [nq][nb][words].
 // Also hoists the per-query score terms (src/batchDotProduct.ts:497-502,573-578).

@@ -27,13 +27,16 @@ def bbq():
     return bbq_b200
 
 
-def make_format(bbq, sim, qb=4, lam=0.1, iters=5, force_path=None, scan=None):
-    """force_path / scan are test knobs read by bbq_create (BBQ_FORCE_PATH, BBQ_SCAN=popc|mma)."""
-    saved = {k: os.environ.pop(k, None) for k in ("BBQ_FORCE_PATH", "BBQ_SCAN")}
+def make_format(bbq, sim, qb=4, lam=0.1, iters=5, force_path=None, scan=None, qquant=None):
+    """force_path / scan / qquant are test knobs read by bbq_create
+    (BBQ_FORCE_PATH, BBQ_SCAN=popc|mma, BBQ_QQUANT=thread)."""
+    saved = {k: os.environ.pop(k, None) for k in ("BBQ_FORCE_PATH", "BBQ_SCAN", "BBQ_QQUANT")}
     if force_path is not None:
         os.environ["BBQ_FORCE_PATH"] = str(force_path)
     if scan is not None:
         os.environ["BBQ_SCAN"] = scan
+    if qquant is not None:
+        os.environ["BBQ_QQUANT"] = qquant
     try:
         return bbq.createBinaryQuantizationFormat(
             {"queryBits": qb, "indexBits": 1, "quantizer": {"similarityFunction": sim, "lambda": lam, "iters": iters}})
@@ -108,9 +111,12 @@ def test_index_build_degenerate_rows(bbq):
 # ---- K4: query quantisation ----------------------------------------------------------------------------
 @pytest.mark.parametrize("sim", SIMS)
 @pytest.mark.parametrize("qb", [1, 2, 4, 7, 8])
-def test_query_quantize_bit_exact(bbq, sim, qb):
+@pytest.mark.parametrize("qquant", [None, "thread"])   # warp-per-query (default) and thread-per-query kernels
+def test_query_quantize_bit_exact(bbq, sim, qb, qquant):
     rows, qs = gaussian(400, 200, 21), gaussian(5, 200, 22)
-    fmt = make_format(bbq, sim, qb=qb)
+    qs[3] = 0                      # zero query: norm == 0 branch under COSINE
+    qs[4] = rows[:400].mean(0)     # ~ centroid: tiny centred vector
+    fmt = make_format(bbq, sim, qb=qb, qquant=qquant)
     qv = fmt.quantizeVectors(rows)["quantizedVectors"]
     for q in qs:
         codes, corr = O.quantize_query_vector(q, qv.getCentroid(), sim=sim, query_bits=qb)
@@ -275,6 +281,21 @@ def test_against_golden_fixtures(bbq, name):
         assert np.bitwise_xor.reduce(fmt.debugScores(q, qv).view(np.uint32)) == g["score_xor"][qi]
         got = fmt.quantizeQueryVector(q, qv)
         assert np.array_equal(got["quantizedQuery"], g["qcodes"][qi])
+
+
+@pytest.mark.parametrize("dim", [8, 33, 1024, 1536])
+def test_query_quantize_dims_and_long_iterations(bbq, dim):
+    rows, qs = gaussian(64, dim, 23 + dim), gaussian(3, dim, 24 + dim)
+    for sim in SIMS:
+        fmt = make_format(bbq, sim, qb=4, lam=0.001, iters=20)
+        qv = fmt.quantizeVectors(rows)["quantizedVectors"]
+        for q in qs:
+            codes, corr = O.quantize_query_vector(q, qv.getCentroid(), sim=sim, query_bits=4, lam=0.001, iters=20)
+            got = fmt.quantizeQueryVector(q, qv)
+            gc = got["queryCorrections"]
+            assert np.array_equal(got["quantizedQuery"], codes)
+            assert bits_equal(np.array([gc["lowerInterval"], gc["upperInterval"], gc["additionalCorrection"],
+                                        gc["quantizedComponentSum"]]), corr)
 
 
 def test_batch_equals_single_and_is_deterministic(bbq):
