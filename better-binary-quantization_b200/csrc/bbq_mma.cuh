@@ -117,6 +117,11 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ int tc_ld1(uint32_t taddr) {
+  int r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // no-swizzle K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
@@ -274,14 +279,23 @@ struct MmaParams {
 
 // The exact replay of one (row, query) pair the screen could not exclude — deliberately out of line: it runs
 // for ~0.1% of the pairs and must not bloat (or serialise) the branch-free screen loop.
+struct ExactCtx {  // passed BY VALUE: taking the address of the kernel parameter block would demote it to local memory
+  double dim, cdp;
+  uint64_t* cand;
+  uint32_t* cand_cnt;
+  uint32_t* overflow;
+  uint32_t cap;
+  int nq;
+  int one_bit_query;
+};
 template <int SIM>
-__device__ __noinline__ void mma_exact_pair(const MmaParams& p, int acc, int q, float tau, const bbqn::QueryTerms* qt,
-                                            double ax, double lx, double addx, double x1, uint32_t id) {
-  const float score = bbqn::score_f32((double)(acc >> 3), ax, lx, addx, x1, *qt, p.dim, p.cdp, SIM, p.one_bit_query != 0);
-  if (q < p.nq && score >= tau) {
-    const uint32_t pos = atomicAdd(p.cand_cnt + q, 1u);
-    if (pos < p.cap) p.cand[(size_t)q * p.cap + pos] = bbqn::topk_key(score, id);
-    else *p.overflow = 1u;
+__device__ __noinline__ void mma_exact_pair(ExactCtx x, int acc, int q, float tau, const bbqn::QueryTerms* qt, double ax,
+                                            double lx, double addx, double x1, uint32_t id) {
+  const float score = bbqn::score_f32((double)(acc >> 3), ax, lx, addx, x1, *qt, x.dim, x.cdp, SIM, x.one_bit_query != 0);
+  if (q < x.nq && score >= tau) {
+    const uint32_t pos = atomicAdd(x.cand_cnt + q, 1u);
+    if (pos < x.cap) x.cand[(size_t)q * x.cap + pos] = bbqn::topk_key(score, id);
+    else *x.overflow = 1u;
   }
 }
 
@@ -485,16 +499,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const MmaParams p) 
         tc_fence_after();
         const uint32_t d_addr = lane_addr + buf * (uint32_t)p.n_tile;
         // software pipeline over this warp's 16-column chunks: the next chunk's TMEM load is in flight
-        // while the current one is screened
-        int acc[16], nxt[16];
-        int c0 = sub * 16;
-        if (c0 < nv) {
-          tc_ld16(d_addr + (uint32_t)c0, acc);
-          tc_wait_ld();
-        }
-        for (; c0 < nv; c0 += NSUB * 16) {
-          const int c1 = c0 + NSUB * 16;
-          if (c1 < nv) tc_ld16(d_addr + (uint32_t)c1, nxt);
+        // while the current one is screened (two register buffers, ping-pong)
+        const ExactCtx xc{p.dim, p.cdp, p.cand, p.cand_cnt, p.overflow, p.cap, p.nq, p.one_bit_query};
+        auto process = [&](const int (&acc)[16], int c0) {
           if (MODE == SCAN_DUMP) {
             if (valid) {
 #pragma unroll
@@ -506,29 +513,42 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const MmaParams p) 
               }
             }
           } else {
+            // branch-free screen of 16 queries; g_j >= 0  <=>  pair j may reach the top-k
+            // (a NaN g_j, e.g. a row past the end of the shard, compares false)
             uint32_t mask = 0u;
 #pragma unroll
             for (int j = 0; j < 16; j++) {
               const float4 a = *reinterpret_cast<const float4*>(&qs_s[c0 + j]);
-              const float f = fmaf(a.x, (float)acc[j], fmaf(rv, a.y, fmaf(x1f, a.z, fmaf(a.w, iv, gv))));
-              bool ps = f >= 0.f;
-              if (SIM == bbqn::SIM_EUCLIDEAN) ps = ps && !(f > qs_s[c0 + j].wadj * iv);
-              mask |= ps ? (1u << j) : 0u;
+              float g = fmaf(a.x, (float)acc[j], fmaf(rv, a.y, fmaf(x1f, a.z, fmaf(a.w, iv, gv))));
+              if (SIM == bbqn::SIM_EUCLIDEAN) g = fminf(g, qs_s[c0 + j].wadj * iv - g);
+              if (g >= 0.f) mask |= (1u << j);
             }
             if (always) mask = 0xFFFFu;
-            if (mask != 0u) {
+            if (mask != 0u) {  // rare: replay this lane's hits exactly
 #pragma unroll
               for (int j = 0; j < 16; j++)
                 if (mask & (1u << j))
-                  mma_exact_pair<SIM>(p, acc[j], q0 + c0 + j, qs_s[c0 + j].tau, &qt_s[min(c0 + j, nv - 1)], ax, lx, addx,
+                  mma_exact_pair<SIM>(xc, acc[j], q0 + c0 + j, qs_s[c0 + j].tau, &qt_s[min(c0 + j, nv - 1)], ax, lx, addx,
                                       x1, id);
             }
           }
-          if (c1 < nv) {
-            tc_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 16; j++) acc[j] = nxt[j];
-          }
+        };
+        int accA[16], accB[16];
+        int c0 = sub * 16;
+        if (c0 < nv) {
+          tc_ld16(d_addr + (uint32_t)c0, accA);
+          tc_wait_ld();
+        }
+        while (c0 < nv) {
+          int c1 = c0 + NSUB * 16;
+          if (c1 < nv) tc_ld16(d_addr + (uint32_t)c1, accB);
+          process(accA, c0);
+          if (c1 >= nv) break;
+          tc_wait_ld();
+          c0 = c1 + NSUB * 16;
+          if (c0 < nv) tc_ld16(d_addr + (uint32_t)c0, accA);
+          process(accB, c1);
+          if (c0 < nv) tc_wait_ld();
         }
         tc_fence_before();
         mbar_arrive(acc_empty + buf);
