@@ -66,6 +66,8 @@ struct DevBuf {  // grow-only device scratch
 };
 
 struct bbq_ctx {
+  int refs = 1;           // the handle itself + one per live index (destroy order must not matter to callers)
+  bool destroyed = false;
   bbq_config cfg;
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -77,7 +79,9 @@ struct bbq_ctx {
   DevBuf T, stage, cacc;
   // query scratch
   DevBuf qrows, qT, qcodes, qcorr, planes, qterms, tau, dump, cand, cand_cnt, flag, lists_a, lists_b,
-      out_idx, out_score, dots, images, qscreen;
+      out_idx, out_score, dots, images, qscreen, tau_bits;
+  uint32_t mma_debug = 0;   // BBQ_MMA_DEBUG: timing-attribution knobs of the tensor-core scan (results become wrong)
+  bool dynamic_tau = true;  // BBQ_DYNTAU=0 keeps the sampled threshold fixed during the tensor-core scan (tests)
   int query_quantizer = 0;  // BBQ_QQUANT=thread forces the one-thread-per-query form (tests)
   int scan_engine = 0;  // BBQ_SCAN: 0 auto, 1 popcount kernel only, 2 tensor-core kernel whenever it can run
   uint32_t* h_flag = nullptr;  // pinned: [0..nq) candidate counts, [nq] overflow flag
@@ -130,6 +134,7 @@ struct bbq_index {
   double cdp = 0.0;
   uint64_t base = 0;
   IndexBounds* bounds = nullptr;  // device; valid for bounds_n rows (tensor-core screen margins)
+  float4* rscreen = nullptr;      // device [capacity]: per-row screen constants, same validity
   uint64_t bounds_n = 0;
   uint64_t capacity = 0;  // rows allocated (== n except while a streaming build is in progress)
 };
@@ -180,19 +185,21 @@ extern "C" int bbq_create(const bbq_config* config, bbq_ctx** out_ctx) {
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaMallocHost(&c->h_flag, (QUERY_BATCH + 1) * sizeof(uint32_t)));
   if (const char* e = getenv("BBQ_FORCE_PATH")) c->force_path = atoi(e);
+  if (const char* e = getenv("BBQ_MMA_DEBUG")) c->mma_debug = (uint32_t)atoi(e);
+  if (const char* e = getenv("BBQ_DYNTAU")) c->dynamic_tau = atoi(e) != 0;
   if (const char* e = getenv("BBQ_QQUANT")) c->query_quantizer = !strcmp(e, "thread") ? 1 : 0;
   if (const char* e = getenv("BBQ_SCAN")) c->scan_engine = !strcmp(e, "popc") ? 1 : !strcmp(e, "mma") ? 2 : 0;
   *out_ctx = c;
   return BBQ_OK;
 }
 
-extern "C" void bbq_destroy(bbq_ctx* c) {
-  if (!c) return;
+static void ctx_release(bbq_ctx* c) {
+  if (--c->refs > 0) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (DevBuf* b : {&c->T, &c->stage, &c->cacc, &c->qrows, &c->qT, &c->qcodes, &c->qcorr, &c->planes, &c->qterms,
                     &c->tau, &c->dump, &c->cand, &c->cand_cnt, &c->flag, &c->lists_a, &c->lists_b, &c->out_idx,
-                    &c->out_score, &c->dots, &c->images, &c->qscreen})
+                    &c->out_score, &c->dots, &c->images, &c->qscreen, &c->tau_bits})
     b->release();
   if (c->h_flag) cudaFreeHost(c->h_flag);
   for (auto& p : c->ev_pending) {
@@ -202,6 +209,12 @@ extern "C" void bbq_destroy(bbq_ctx* c) {
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
+}
+
+extern "C" void bbq_destroy(bbq_ctx* c) {
+  if (!c || c->destroyed) return;
+  c->destroyed = true;  // indexes that are still alive keep the context (its stream and scratch) until they go
+  ctx_release(c);
 }
 
 extern "C" int bbq_get_stats(bbq_ctx* c, bbq_stats* out) {
@@ -252,6 +265,7 @@ extern "C" int bbq_reset_profiling(bbq_ctx* c) {
 static int index_alloc(bbq_ctx* c, uint64_t n, uint32_t dim, bbq_index** out) {
   bbq_index* ix = new bbq_index();
   ix->ctx = c;
+  c->refs++;
   ix->n = n;
   ix->dim = dim;
   ix->row_bytes = row_bytes_for(dim);
@@ -278,7 +292,10 @@ extern "C" void bbq_index_destroy(bbq_index* ix) {
   cudaFree(ix->compsum);
   cudaFree(ix->centroid);
   if (ix->bounds) cudaFree(ix->bounds);
+  if (ix->rscreen) cudaFree(ix->rscreen);
+  bbq_ctx* c = ix->ctx;
   delete ix;
+  ctx_release(c);
 }
 
 static int finish_centroid(bbq_index* ix) {
@@ -684,9 +701,10 @@ struct MmaPlan {
 static bool mma_plan(const bbq_index* ix, int nq, MmaPlan* out) {
   const bbq_ctx* c = ix->ctx;
   if (c->scan_engine == 1 || c->cfg.query_bits > 5) return false;
+  if (ix->row_bytes * 8 > 4096 || nq > 4096) return false;  // parked-hit word: 20-bit accumulator, 12-bit query
   MmaPlan pl;
   pl.kbytes = ix->row_bytes * 8;
-  const size_t budget = 227 * 1024 - 1024;
+  const size_t budget = 227 * 1024 - 1024 - (HIT_RING * sizeof(uint64_t) + 64);
   int n_cap = (int)(budget / ((size_t)pl.kbytes + 64)) / 16 * 16;
   n_cap = std::min(n_cap, MMA_N_MAX);
   if (n_cap < 16) return false;
@@ -694,7 +712,7 @@ static bool mma_plan(const bbq_index* ix, int nq, MmaPlan* out) {
   pl.passes = (nq + n_cap - 1) / n_cap;
   pl.n_tile = (((nq + pl.passes - 1) / pl.passes) + 15) / 16 * 16;
   pl.nstage = std::min(8, (512 - 2 * pl.n_tile) / 32);
-  pl.smem = (size_t)pl.n_tile * pl.kbytes + (size_t)pl.n_tile * (sizeof(QScreen) + sizeof(bbqn::QueryTerms)) + 23 * 8 + 16;
+  pl.smem = (size_t)pl.n_tile * pl.kbytes + (size_t)pl.n_tile * (sizeof(QScreen) + sizeof(bbqn::QueryTerms)) + 24 * 8 + sizeof(HitCtx) + HIT_RING * sizeof(uint64_t) + 16 + 16;
   *out = pl;
   return true;
 }
@@ -703,9 +721,10 @@ static int ensure_bounds(bbq_index* ix, cudaStream_t st) {
   bbq_ctx* c = ix->ctx;
   if (ix->bounds && ix->bounds_n == ix->n) return BBQ_OK;
   if (!ix->bounds) CU(cudaMalloc(&ix->bounds, sizeof(IndexBounds)));
+  if (!ix->rscreen) CU(cudaMalloc(&ix->rscreen, (size_t)ix->capacity * sizeof(float4)));
   CU(cudaMemsetAsync(ix->bounds, 0, sizeof(IndexBounds), st));
-  LAUNCH(c, k_index_bounds, 296, 256, 0, st, ix->lower, ix->upper, ix->addc, ix->compsum, (int64_t)ix->n,
-         reinterpret_cast<uint32_t*>(ix->bounds));
+  LAUNCH(c, k_index_bounds, 592, 256, 0, st, ix->lower, ix->upper, ix->addc, ix->compsum, (int64_t)ix->n,
+         (int)c->cfg.similarity, reinterpret_cast<uint32_t*>(ix->bounds), ix->rscreen);
   ix->bounds_n = ix->n;
   return BBQ_OK;
 }
@@ -716,6 +735,7 @@ static int prepare_mma_operands(bbq_index* ix, int nq, const MmaPlan& pl, cudaSt
   const size_t bytes = (size_t)pl.passes * pl.n_tile * pl.kbytes;
   TRY(c->images.reserve(bytes));
   TRY(c->qscreen.reserve((size_t)pl.passes * pl.n_tile * sizeof(QScreen)));
+  TRY(c->tau_bits.reserve((size_t)pl.passes * pl.n_tile * sizeof(uint32_t)));
   ProfScope prof(c, st, PROF_QUANT);
   const int64_t threads = (int64_t)pl.passes * pl.n_tile * (pl.kbytes / 16);
   LAUNCH(c, k_query_tiles, (unsigned)((threads + 255) / 256), 256, 0, st, c->qcodes.as<uint8_t>(), ix->row_bytes * 8, nq,
@@ -741,7 +761,7 @@ static int launch_mma_sim(bbq_ctx* c, int sim, unsigned grid, size_t smem, cudaS
   return BBQ_OK;
 }
 
-static int launch_scan_mma(bbq_index* ix, int mode, int nq, const MmaPlan& pl, int64_t tile_first, int64_t tile_stride,
+static int launch_scan_mma(bbq_index* ix, int mode, int nq, uint32_t k, const MmaPlan& pl, int64_t tile_first, int64_t tile_stride,
                            int64_t ntiles, float* dump, int64_t dump_ld, uint64_t* cand, uint32_t* cand_cnt,
                            uint32_t cap, uint32_t* overflow, cudaStream_t st) {
   bbq_ctx* c = ix->ctx;
@@ -756,6 +776,11 @@ static int launch_scan_mma(bbq_index* ix, int mode, int nq, const MmaPlan& pl, i
   p.kbytes = pl.kbytes;
   p.images = c->images.as<uint8_t>();
   p.qscreen = c->qscreen.as<QScreen>();
+  p.rscreen = ix->rscreen;
+  p.tau_bits = c->tau_bits.as<uint32_t>();
+  p.bounds = ix->bounds;
+  p.k = c->dynamic_tau ? k : 0xFFFFFFFFu;
+  p.debug = c->mma_debug;
   p.qterms = c->qterms.as<bbqn::QueryTerms>();
   p.nq = nq;
   p.n_tile = pl.n_tile;
@@ -911,7 +936,7 @@ static int search_filtered(bbq_index* ix, int nq, uint32_t k, int32_t* d_out_idx
     p.dump = c->dump.as<float>();
     p.dump_ld = SELECT_MAX;
     if (use_mma)
-      TRY(launch_scan_mma(ix, SCAN_DUMP, nq, pl, 0, stride, stiles, c->dump.as<float>(), SELECT_MAX, nullptr, nullptr, 0,
+      TRY(launch_scan_mma(ix, SCAN_DUMP, nq, k, pl, 0, stride, stiles, c->dump.as<float>(), SELECT_MAX, nullptr, nullptr, 0,
                           nullptr, st));
     else
       TRY(launch_scan(ix, SCAN_DUMP, p, stiles, st));
@@ -948,9 +973,9 @@ static int search_filtered(bbq_index* ix, int nq, uint32_t k, int32_t* d_out_idx
         const int nq_pad = pl.passes * pl.n_tile;
         LAUNCH(c, k_query_screen, (nq_pad + 127) / 128, 128, 0, st, c->qterms.as<bbqn::QueryTerms>(), c->tau.as<float>(),
                nq, nq_pad, (double)ix->dim, ix->cdp, (int)c->cfg.similarity, c->cfg.query_bits == 1 ? 1 : 0, ix->bounds,
-               c->qscreen.as<QScreen>());
+               c->qscreen.as<QScreen>(), c->tau_bits.as<uint32_t>());
       }
-      TRY(launch_scan_mma(ix, SCAN_FILTER, nq, pl, 0, 1, ntiles, nullptr, 0, p.cand, cnt, CAND_CAP, cnt + nq, st));
+      TRY(launch_scan_mma(ix, SCAN_FILTER, nq, k, pl, 0, 1, ntiles, nullptr, 0, p.cand, cnt, CAND_CAP, cnt + nq, st));
     } else {
       TRY(launch_scan(ix, SCAN_FILTER, p, ntiles, st));
     }

@@ -73,6 +73,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// wait with a suspend-time hint: for producers that run far ahead and should not steal issue slots by polling
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(20000u)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst_smem)),
@@ -165,19 +194,29 @@ __global__ void k_query_tiles(const uint8_t* __restrict__ qcodes, int code_ld, i
   *dst = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// maxima of lx, |ax|, lx*x1, |addx| over the shard (finite, lx > 0 rows only)
+// One pass over the shard's correctives: (1) maxima of lx, |ax|, lx*x1, |addx| (finite rows with lx > 0) for the
+// screen's error margin; (2) the per-row screen constants {ax/lx, x1, c*addx/lx, 1/lx} as one float4 per row
+// (c = -1/2 for EUCLIDEAN, 1 otherwise).  A row whose correctives are degenerate gets 1/lx = 0, which the scan
+// reads as "send every pair of this row to the exact replay".
 __global__ void k_index_bounds(const double* __restrict__ lower, const double* __restrict__ upper,
                                const double* __restrict__ addc, const uint32_t* __restrict__ compsum, int64_t n,
-                               uint32_t* __restrict__ out4) {
+                               int sim, uint32_t* __restrict__ out4, float4* __restrict__ rscreen) {
   float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double ax = lower[i], lx = upper[i] - ax, ad = addc[i];
+    float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lx > 0 && bbqn::js_isfinite(lx) && bbqn::js_isfinite(ax) && bbqn::js_isfinite(ad)) {
       m0 = fmaxf(m0, __double2float_ru(lx));
       m1 = fmaxf(m1, __double2float_ru(fabs(ax)));
       m2 = fmaxf(m2, __double2float_ru(lx * (double)compsum[i]));
       m3 = fmaxf(m3, __double2float_ru(fabs(ad)));
+      const double inv = 1.0 / lx;
+      const float rv = (float)(ax * inv), gv = (float)((sim == bbqn::SIM_EUCLIDEAN ? -0.5 * ad : ad) * inv),
+                  iv = (float)inv;
+      if (bbqn::js_isfinite((double)rv) && bbqn::js_isfinite((double)gv) && bbqn::js_isfinite((double)iv) && iv > 0.f)
+        rs = make_float4(rv, (float)compsum[i], gv, iv);
     }
+    rscreen[i] = rs;
   }
   for (int o = 16; o > 0; o >>= 1) {
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
@@ -201,52 +240,64 @@ __global__ void k_index_bounds(const double* __restrict__ lower, const double* _
 // Dividing by lx > 0:  F = ly*dot + (ax/lx)*A_q + x1*ay + (c*addx)/lx - L/lx  >= 0  [and F <= W/lx].
 // F is evaluated in fp32; `margin` (in s units) bounds every rounding in that chain and the f32 rounding
 // of the score itself, so the screen only ever errs towards admitting a pair to the exact f64 replay.
-__global__ void k_query_screen(const bbqn::QueryTerms* __restrict__ qterms, const float* __restrict__ tau, int nq,
-                               int nq_pad, double dim, double cdp, int sim, int one_bit_query,
-                               const IndexBounds* __restrict__ bounds, QScreen* __restrict__ out) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nq_pad) return;
+__device__ __forceinline__ QScreen make_qscreen(const bbqn::QueryTerms& t, float tau, double dim, double cdp, int sim,
+                                                int one_bit_query, const IndexBounds& b) {
   QScreen s;
   s.ly8 = s.aq = s.ay = 0.f;
-  s.negl = (q < nq) ? INFINITY : -INFINITY;  // real query: admit everything unless bounded below; padding: admit nothing
+  s.negl = INFINITY;  // admit everything unless a finite lower bound can be derived
   s.wadj = INFINITY;
-  s.tau = (q < nq) ? -INFINITY : INFINITY;
+  s.tau = tau;
   s.pad0 = s.pad1 = 0.f;
-  if (q < nq) {
-    const bbqn::QueryTerms t = qterms[q];
-    const double tq = (double)tau[q];
-    s.tau = tau[q];
-    const double aq = t.ay * dim + t.ly * t.y1;
-    double L = 0, W = INFINITY;
-    bool ok = tq > 0 && bbqn::js_isfinite(tq) && bbqn::js_isfinite(aq) && bbqn::js_isfinite(t.ay) &&
-              bbqn::js_isfinite(t.ly) && bbqn::js_isfinite(t.addq);
-    if (ok) {
-      if (sim == bbqn::SIM_EUCLIDEAN) {
-        L = (t.addq + 1.0 - 1.0 / tq) / 2;
-        W = 1.0 / (2 * tq);
-      } else if (sim == bbqn::SIM_COSINE) {
-        L = 2 * tq - 1.0 - t.addq + cdp;
-      } else {
-        const double S = one_bit_query ? 1.0 : (1.0 / 15.0);
-        L = (tq >= 1 ? (tq - 1.0) * S : (1.0 - 1.0 / tq) * S) - t.addq + cdp;
-      }
-      const IndexBounds b = *bounds;
-      const double eps = 1.0 / 16777216.0;  // 2^-24
-      const double wv = (sim == bbqn::SIM_EUCLIDEAN) ? 0.5 * b.wv : b.wv;
-      double margin = 32.0 * eps * ((double)b.lx * fabs(t.ly) * fabs(t.y1) + (double)b.ax * fabs(aq) + (double)b.mv * fabs(t.ay) +
-                                    wv + fabs(L)) +
-                      16.0 * eps * (fabs(L) + 1.0 + fabs(t.addq) + fabs(cdp) + fabs(W == INFINITY ? 0.0 : W));
-      ok = bbqn::js_isfinite(margin) && bbqn::js_isfinite(L);
-      if (ok) {
-        s.ly8 = (float)(t.ly / 8);
-        s.aq = (float)aq;
-        s.ay = (float)t.ay;
-        s.negl = __double2float_ru(-(L - margin));
-        s.wadj = (W == INFINITY) ? INFINITY : __double2float_ru(W + 2 * margin);
-      }
+  const double tq = (double)tau;
+  const double aq = t.ay * dim + t.ly * t.y1;
+  double L = 0, W = INFINITY;
+  bool ok = tq > 0 && bbqn::js_isfinite(tq) && bbqn::js_isfinite(aq) && bbqn::js_isfinite(t.ay) &&
+            bbqn::js_isfinite(t.ly) && bbqn::js_isfinite(t.addq);
+  if (ok) {
+    if (sim == bbqn::SIM_EUCLIDEAN) {
+      L = (t.addq + 1.0 - 1.0 / tq) / 2;
+      W = 1.0 / (2 * tq);
+    } else if (sim == bbqn::SIM_COSINE) {
+      L = 2 * tq - 1.0 - t.addq + cdp;
+    } else {
+      const double S = one_bit_query ? 1.0 : (1.0 / 15.0);
+      L = (tq >= 1 ? (tq - 1.0) * S : (1.0 - 1.0 / tq) * S) - t.addq + cdp;
+    }
+    const double eps = 1.0 / 16777216.0;  // 2^-24
+    const double wv = (sim == bbqn::SIM_EUCLIDEAN) ? 0.5 * b.wv : b.wv;
+    const double margin = 32.0 * eps * ((double)b.lx * fabs(t.ly) * fabs(t.y1) + (double)b.ax * fabs(aq) +
+                                        (double)b.mv * fabs(t.ay) + wv + fabs(L)) +
+                          16.0 * eps * (fabs(L) + 1.0 + fabs(t.addq) + fabs(cdp) + fabs(W == INFINITY ? 0.0 : W));
+    if (bbqn::js_isfinite(margin) && bbqn::js_isfinite(L)) {
+      s.ly8 = (float)(t.ly / 8);
+      s.aq = (float)aq;
+      s.ay = (float)t.ay;
+      s.negl = __double2float_ru(-(L - margin));
+      s.wadj = (W == INFINITY) ? INFINITY : __double2float_ru(W + 2 * margin);
     }
   }
-  out[q] = s;
+  return s;
+}
+
+__global__ void k_query_screen(const bbqn::QueryTerms* __restrict__ qterms, const float* __restrict__ tau, int nq,
+                               int nq_pad, double dim, double cdp, int sim, int one_bit_query,
+                               const IndexBounds* __restrict__ bounds, QScreen* __restrict__ out,
+                               uint32_t* __restrict__ tau_bits) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq_pad) return;
+  if (q < nq) {
+    out[q] = make_qscreen(qterms[q], tau[q], dim, cdp, sim, one_bit_query, *bounds);
+    tau_bits[q] = (uint32_t)(bbqn::topk_key(tau[q], 0u) >> 32);
+  } else {  // padding column of the last query block: admits nothing
+    QScreen s;
+    s.ly8 = s.aq = s.ay = 0.f;
+    s.negl = -INFINITY;
+    s.wadj = INFINITY;
+    s.tau = INFINITY;
+    s.pad0 = s.pad1 = 0.f;
+    out[q] = s;
+    tau_bits[q] = 0xFFFFFFFFu;
+  }
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
@@ -260,7 +311,12 @@ struct MmaParams {
   int row_bytes;           // packed bytes per row (multiple of 16)
   int kbytes;              // expanded K bytes per row = row_bytes * 8
   const uint8_t* images;   // [passes][n_tile * kbytes]
-  const QScreen* qscreen;  // [passes * n_tile]
+  QScreen* qscreen;        // [passes * n_tile]; tightened in place while the scan runs (see mma_retighten)
+  uint32_t* tau_bits;      // [passes * n_tile] ordered-key form of tau, atomicMax'ed
+  const IndexBounds* bounds;
+  uint32_t k;              // top-k size (dynamic tightening needs k <= RETIGHTEN_KMAX)
+  uint32_t debug;          // profiling knobs (BBQ_MMA_DEBUG): 1 = epilogue skips the screen, 2 = hits are ignored, 4 = no TMEM loads
+  const float4* rscreen;   // [n] per-row screen constants (k_index_bounds)
   const bbqn::QueryTerms* qterms;
   int nq, n_tile, passes, nstage;
   double dim, cdp;
@@ -279,28 +335,165 @@ struct MmaParams {
 
 // The exact replay of one (row, query) pair the screen could not exclude — deliberately out of line: it runs
 // for ~0.1% of the pairs and must not bloat (or serialise) the branch-free screen loop.
-struct ExactCtx {  // passed BY VALUE: taking the address of the kernel parameter block would demote it to local memory
+// The exact replay of one (row, query) pair the screen could not exclude — deliberately out of line: it runs for
+// ~0.1% of the pairs and must not bloat (or serialise) the branch-free screen loop.  `p` points at the kernel's
+// __grid_constant__ parameter block; the row's f64 correctives are fetched here, only when needed.
+struct RowTerms {  // the row's f64 correctives, loaded once per tile (asynchronously) for the rare exact replays
+  double ax, ux, addx;
+  uint32_t x1;
+};
+
+// everything the (rare, out-of-line) hit path needs, kept in shared memory so that calling it costs no
+// per-chunk parameter marshalling in the hot screen loop
+struct HitCtx {
   double dim, cdp;
   uint64_t* cand;
   uint32_t* cand_cnt;
   uint32_t* overflow;
-  uint32_t cap;
-  int nq;
-  int one_bit_query;
+  QScreen* qscreen;
+  uint32_t* tau_bits;
+  const bbqn::QueryTerms* qterms;
+  const IndexBounds* bounds;
+  const double* lower;
+  const double* upper;
+  const double* addc;
+  const uint32_t* compsum;
+  uint32_t cap, k, base;
+  int nq, one_bit_query;
 };
+
+constexpr uint32_t RETIGHTEN_KMAX = 32;    // k up to which the running threshold is tightened inside the scan
+constexpr uint32_t RETIGHTEN_EVERY = 16;   // ... once per this many appended candidates of a query
+constexpr uint32_t HIT_RING = 512;         // CTA-wide ring of parked hits (8 B each)
+
+// ---- hits: parked by the epilogue warps, replayed by a dedicated "drainer" warp -------------------------------
+// A lane that replayed its own hit would serialise its whole warp behind a ~100-instruction f64 routine plus two
+// dependent global round trips (measured: 1.0 ms of a 2.2 ms scan).  Instead the epilogue lanes only PARK a hit —
+// one 64-bit word (row+1 | query | accumulator) into a CTA-wide shared-memory ring — and warp 3 drains the ring,
+// one lane per hit: exact f64 replay, comparison with the query's CURRENT threshold, candidate append, and the
+// threshold tightening below.  A ring word is published by a single 64-bit store and consumed in order.
+__device__ __forceinline__ uint64_t hit_pack(uint32_t row, uint32_t q, uint32_t acc) {
+  return ((uint64_t)(row + 1u) << 32) | ((uint64_t)(q & 0xFFFu) << 20) | (uint64_t)(acc & 0xFFFFFu);
+}
+
+__device__ __noinline__ void mma_park_hits(uint64_t* ring, uint32_t* tail_s, const uint32_t* head_s, uint32_t mask,
+                                           uint32_t row, int q0c0, int a0, int a1, int a2, int a3, int a4, int a5, int a6,
+                                           int a7, int a8, int a9, int a10, int a11, int a12, int a13, int a14, int a15) {
+  const int acc[16] = {a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15};
+  while (mask) {
+    const int j = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const uint32_t slot = atomicAdd(tail_s, 1u);
+    while (slot - *((volatile const uint32_t*)head_s) >= HIT_RING) __nanosleep(100);  // ring full: wait for the drainer
+    *((volatile uint64_t*)(ring + (slot % HIT_RING))) = hit_pack(row, (uint32_t)(q0c0 + j), (uint32_t)acc[j]);
+  }
+}
+
+// The running threshold.  tau[q] starts as a lower bound of the final k-th best score taken from a sample; while
+// the scan runs, whenever a query's candidate count passes a multiple of 16 the drainer warp recomputes the k-th
+// best key among (up to 256 of) the candidates appended so far — every one of them is a real row, so that key's
+// score is again a valid lower bound — raises tau[q] with an atomicMax and rewrites the query's screen constants
+// in global memory; every CTA re-reads them once per tile.  Published values only ever tighten and each 32-bit
+// field is a valid bound by itself, so readers need no synchronisation.  Cuts the exact replays ~10x.
 template <int SIM>
-__device__ __noinline__ void mma_exact_pair(ExactCtx x, int acc, int q, float tau, const bbqn::QueryTerms* qt, double ax,
-                                            double lx, double addx, double x1, uint32_t id) {
-  const float score = bbqn::score_f32((double)(acc >> 3), ax, lx, addx, x1, *qt, x.dim, x.cdp, SIM, x.one_bit_query != 0);
-  if (q < x.nq && score >= tau) {
-    const uint32_t pos = atomicAdd(x.cand_cnt + q, 1u);
-    if (pos < x.cap) x.cand[(size_t)q * x.cap + pos] = bbqn::topk_key(score, id);
-    else *x.overflow = 1u;
+__device__ void mma_retighten_warp(const HitCtx* cx, int q, int lane) {  // whole warp, convergent
+  const uint32_t k = cx->k;
+  uint32_t n = 0;
+  if (lane == 0) n = min(*((volatile uint32_t*)(cx->cand_cnt + q)), cx->cap);
+  n = __shfl_sync(0xffffffffu, n, 0);  // one read, so that every lane takes the same branches below
+  if (n < k) return;
+  const uint32_t first = n > 256u ? n - 256u : 0u;  // any subset gives a valid bound; the latest are the best
+  const uint64_t* list = cx->cand + (size_t)q * cx->cap;
+  uint64_t mine[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t e = first + (uint32_t)(i * 32 + lane);
+    mine[i] = e < n ? __ldcg(list + e) : 0ull;  // 0 = slot reserved but not written yet: ranks below everything
+  }
+  uint64_t bound = ~0ull;
+  for (uint32_t t = 0; t < k; t++) {  // k-th largest by k rounds of "largest key below the previous one"
+    uint64_t m = 0ull;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if (mine[i] < bound && mine[i] > m) m = mine[i];
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint64_t other = __shfl_xor_sync(0xffffffffu, m, o);
+      m = other > m ? other : m;
+    }
+    bound = m;
+    if (m == 0ull) return;  // fewer than k visible candidates
+  }
+  const uint32_t bits = (uint32_t)(bound >> 32);
+  if (bits == 0u) return;  // NaN-scored k-th: no bound
+  if (lane == 0) {
+    const uint32_t old = atomicMax(cx->tau_bits + q, bits);
+    if (bits > old) {
+      const float tnew = bbqn::topk_key_score(bound);
+      const QScreen s = make_qscreen(cx->qterms[q], tnew, cx->dim, cx->cdp, SIM, cx->one_bit_query, *cx->bounds);
+      QScreen* dst = cx->qscreen + q;
+      if (s.ly8 == dst->ly8 && s.aq == dst->aq && s.ay == dst->ay) {  // same query terms: only the bounds move
+        dst->negl = fminf(dst->negl, s.negl);
+        dst->wadj = fminf(dst->wadj, s.wadj);
+        dst->tau = fmaxf(dst->tau, tnew);
+      }
+    }
+  }
+}
+
+template <int SIM>
+__device__ void mma_drain_ring(const HitCtx* cx, uint64_t* ring, const uint32_t* tail_s, uint32_t* head_s,
+                               const uint32_t* done_s, int lane) {
+  uint32_t head = 0;
+  for (;;) {
+    const uint64_t e = *((volatile uint64_t*)(ring + ((head + (uint32_t)lane) % HIT_RING)));
+    const uint32_t valid = __ballot_sync(0xffffffffu, e != 0ull);
+    const uint32_t n = (valid == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~valid) - 1);  // contiguous published prefix
+    if (n == 0u) {
+      if (*((volatile const uint32_t*)done_s) == (uint32_t)MMA_EPI_WARPS && head == *((volatile const uint32_t*)tail_s)) break;
+      __nanosleep(200);
+      continue;
+    }
+    int tighten_q = -1;
+    if ((uint32_t)lane < n) {
+      const int64_t row = (int64_t)((uint32_t)(e >> 32) - 1u);
+      const int q = (int)((e >> 20) & 0xFFFu);
+      const int acc = (int)(e & 0xFFFFFu);
+      float score = 0.f, tau = INFINITY;
+      if (q < cx->nq) {  // (a degenerate row parks the padding columns of the last query block too)
+        const double ax = __ldg(cx->lower + row), ux = __ldg(cx->upper + row), addx = __ldg(cx->addc + row);
+        const double x1 = (double)__ldg(cx->compsum + row);
+        const bbqn::QueryTerms qt = cx->qterms[q];
+        tau = __ldcg(&cx->qscreen[q].tau);
+        score = bbqn::score_f32((double)(acc >> 3), ax, ux - ax, addx, x1, qt, cx->dim, cx->cdp, SIM, cx->one_bit_query != 0);
+      }
+      if (q < cx->nq && score >= tau) {
+        const uint32_t pos = atomicAdd(cx->cand_cnt + q, 1u);
+        if (pos < cx->cap) {
+          cx->cand[(size_t)q * cx->cap + pos] = bbqn::topk_key(score, cx->base + (uint32_t)row);
+          if (cx->k <= RETIGHTEN_KMAX && pos + 1 >= 2 * cx->k && (pos + 1) % RETIGHTEN_EVERY == 0) tighten_q = q;
+        } else {
+          *cx->overflow = 1u;
+        }
+      }
+      *((volatile uint64_t*)(ring + ((head + (uint32_t)lane) % HIT_RING))) = 0ull;  // slot is free again
+    }
+    __threadfence_block();
+    __syncwarp();
+    head += n;
+    if (lane == 0) *((volatile uint32_t*)head_s) = head;
+    // tightening requests of this batch, one query at a time, the whole warp on each
+    uint32_t want = __ballot_sync(0xffffffffu, tighten_q >= 0);
+    if (want) __threadfence();
+    while (want) {
+      const int src = __ffs(want) - 1;
+      want &= want - 1;
+      mma_retighten_warp<SIM>(cx, __shfl_sync(0xffffffffu, tighten_q, src), lane);
+    }
   }
 }
 
 template <int MODE, int SIM>
-__global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const MmaParams p) {
+__global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_constant__ MmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // layout: [B image n_tile*kbytes][QScreen n_tile][QueryTerms n_tile][barriers][tmem ptr]
   uint8_t* b_smem = smem_raw;
@@ -314,6 +507,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const MmaParams p) 
   uint64_t* b_full = bars + 20;
   uint64_t* b_empty = bars + 21;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 22);
+  HitCtx* hit_s = reinterpret_cast<HitCtx*>(bars + 24);
+  uint64_t* ring_s = reinterpret_cast<uint64_t*>(hit_s + 1);            // [HIT_RING] parked hits
+  uint32_t* ring_ctl_s = reinterpret_cast<uint32_t*>(ring_s + HIT_RING);  // tail, head, done
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nstage = p.nstage;
@@ -330,8 +526,28 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const MmaParams p) 
     }
     mbar_init(b_full, 1);
     mbar_init(b_empty, 1);
+    hit_s->dim = p.dim;
+    hit_s->cdp = p.cdp;
+    hit_s->cand = p.cand;
+    hit_s->cand_cnt = p.cand_cnt;
+    hit_s->overflow = p.overflow;
+    hit_s->qscreen = p.qscreen;
+    hit_s->tau_bits = p.tau_bits;
+    hit_s->qterms = p.qterms;
+    hit_s->bounds = p.bounds;
+    hit_s->lower = p.lower;
+    hit_s->upper = p.upper;
+    hit_s->addc = p.addc;
+    hit_s->compsum = p.compsum;
+    hit_s->cap = p.cap;
+    hit_s->k = p.k;
+    hit_s->base = p.base;
+    hit_s->nq = p.nq;
+    hit_s->one_bit_query = p.one_bit_query;
+    ring_ctl_s[0] = ring_ctl_s[1] = ring_ctl_s[2] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (uint32_t i = threadIdx.x; i < HIT_RING; i += MMA_THREADS) ring_s[i] = 0ull;
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
                  "r"(512u)
@@ -350,7 +566,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const MmaParams p) 
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)p.n_tile * (uint32_t)p.kbytes;
       for (int pass = 0; pass < p.passes; pass++) {
-        mbar_wait(b_empty, (uint32_t)((pass & 1) ^ 1));  // previous pass's MMAs have drained
+        // previous pass's MMAs have drained (a whole pass away: poll lazily, do not steal issue slots)
+        while (!mbar_try(b_empty, (uint32_t)((pass & 1) ^ 1))) __nanosleep(1000);
         mbar_expect_tx(b_full, bytes);
         const uint8_t* src = p.images + (size_t)pass * bytes;
         for (uint32_t off = 0; off < bytes; off += 32768u) {
@@ -397,6 +614,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const MmaParams p) 
       if (lane == 0) tc_commit(b_empty);  // all MMAs of this pass done -> B may be replaced
       __syncwarp();
     }
+  } else if (warp == 3) {
+    // ===== drainer: exact replay of the parked hits, candidate append, threshold tightening =====
+    if (MODE == SCAN_FILTER) mma_drain_ring<SIM>(hit_s, ring_s, ring_ctl_s + 0, ring_ctl_s + 1, ring_ctl_s + 2, lane);
   } else if (warp >= 4 && warp < 8) {
     // ===== expansion: packed 1-bit row -> weighted u8 A operand, straight into TMEM =====
     // The (tile, chunk) sequence of a pass is walked as one flat stream so that the 16-byte packed chunks can
@@ -406,25 +626,34 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const MmaParams p) 
     constexpr int PF = 8;
     const int64_t my_tiles = (p.ntiles > blockIdx.x) ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t total = my_tiles * nchunks;
-    auto load_chunk = [&](int64_t f) -> uint4 {
-      if (f >= total) return make_uint4(0u, 0u, 0u, 0u);
-      const int64_t ti = f / nchunks;
-      const int kc = (int)(f - ti * nchunks);
-      const int64_t row = (p.tile_first + (blockIdx.x + ti * gridDim.x) * p.tile_stride) * TILE_ROWS + r;
-      if (row >= p.n) return make_uint4(0u, 0u, 0u, 0u);
-      return __ldg(reinterpret_cast<const uint4*>(p.codes + row * (int64_t)p.row_bytes) + kc);
+    // cursor of the NEXT chunk to prefetch: (tile ordinal, chunk within the row)
+    int64_t pf_tile = 0;
+    int pf_kc = 0;
+    auto load_next = [&]() -> uint4 {
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (pf_tile < my_tiles) {
+        const int64_t row = (p.tile_first + (blockIdx.x + pf_tile * gridDim.x) * p.tile_stride) * TILE_ROWS + r;
+        if (row < p.n) v = __ldg(reinterpret_cast<const uint4*>(p.codes + row * (int64_t)p.row_bytes) + pf_kc);
+        if (++pf_kc == nchunks) {
+          pf_kc = 0;
+          pf_tile++;
+        }
+      }
+      return v;
     };
     uint32_t stage = 0, sphase = 0;
     for (int pass = 0; pass < p.passes; pass++) {
       uint4 q[PF];
+      pf_tile = 0;
+      pf_kc = 0;
 #pragma unroll
-      for (int i = 0; i < PF; i++) q[i] = load_chunk(i);
+      for (int i = 0; i < PF; i++) q[i] = load_next();
       for (int64_t f0 = 0; f0 < total; f0 += PF) {
 #pragma unroll
         for (int i = 0; i < PF; i++) {
           if (f0 + i < total) {
             const uint4 x = q[i];
-            q[i] = load_chunk(f0 + i + PF);
+            q[i] = load_next();
             uint32_t e[32];
             const uint32_t ws[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
@@ -436,7 +665,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const MmaParams p) 
                 e[8 * g + 4 + b] = hi & (0x01010101u << b);  // u = 4 + b : bit 4+b of each packed byte, weight 2^b
               }
             }
-            mbar_wait(a_empty + stage, sphase ^ 1u);
+            mbar_wait_relaxed(a_empty + stage, sphase ^ 1u);
             tc_fence_after();
             tc_st32(lane_addr + a_col + stage * 32u, e);
             tc_wait_st();
@@ -470,91 +699,103 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const MmaParams p) 
         if (c < nv) qt_s[c] = p.qterms[q0 + c];
       }
       asm volatile("bar.sync 1, %0;" ::"n"(MMA_EPI_WARPS * 32) : "memory");
+      auto row_of = [&](int64_t ti) { return (p.tile_first + ti * p.tile_stride) * TILE_ROWS + r; };
+      // per-row screen constants: prefetched one tile ahead.  Rows past the end of the shard fail every screen.
+      const float4 rs_none = make_float4(0.f, 0.f, -INFINITY, 1.f);
+      auto load_rs = [&](int64_t ti) -> float4 {
+        if (MODE != SCAN_FILTER || ti >= p.ntiles) return rs_none;
+        const int64_t rw = row_of(ti);
+        return rw < p.n ? __ldg(p.rscreen + rw) : rs_none;
+      };
+      float4 rs_next = load_rs(blockIdx.x);
       for (int64_t i = blockIdx.x; i < p.ntiles; i += gridDim.x) {
-        const int64_t row = (p.tile_first + i * p.tile_stride) * TILE_ROWS + r;
+        const int64_t row = row_of(i);
         const bool valid = row < p.n;
-        double ax = 0, lx = 0, addx = 0, x1 = 0;
-        // screen constants of this row; defaults make an out-of-range row fail every screen
-        float rv = 0.f, x1f = 0.f, gv = -INFINITY, iv = 0.f;
-        bool always = false;
-        if (valid) {
-          ax = p.lower[row];
-          lx = p.upper[row] - ax;
-          addx = p.addc[row];
-          x1 = (double)p.compsum[row];
-          always = true;  // degenerate correctives: every pair of this row goes to the exact replay
-          if (MODE == SCAN_FILTER && lx > 0 && bbqn::js_isfinite(lx) && bbqn::js_isfinite(ax) &&
-              bbqn::js_isfinite(addx)) {
-            const double inv = 1.0 / lx;
-            rv = (float)(ax * inv);
-            x1f = (float)x1;
-            gv = (float)((SIM == bbqn::SIM_EUCLIDEAN ? -0.5 * addx : addx) * inv);
-            iv = (float)inv;
-            always = !(bbqn::js_isfinite((double)rv) && bbqn::js_isfinite((double)gv) && bbqn::js_isfinite((double)iv));
-          }
+        const float4 rs = rs_next;
+        rs_next = load_rs(i + gridDim.x);
+        const float rv = rs.x, x1f = rs.y, gv = rs.z, iv = rs.w;
+        const bool always = valid && !(iv > 0.f);  // degenerate correctives: every pair goes to the exact replay
+        // f64 correctives: issued now, consumed only by the (rare) exact replays, so their latency stays hidden
+        RowTerms rt{0.0, 0.0, 0.0, 0u};
+        if (MODE == SCAN_DUMP && valid) {
+          rt.ax = __ldg(p.lower + row);
+          rt.ux = __ldg(p.upper + row);
+          rt.addx = __ldg(p.addc + row);
+          rt.x1 = __ldg(p.compsum + row);
         }
-        const uint32_t id = p.base + (uint32_t)row;
         const uint32_t buf = tcount & 1u, bphase = (tcount >> 1) & 1u;
         mbar_wait(acc_full + buf, bphase);
         tc_fence_after();
         const uint32_t d_addr = lane_addr + buf * (uint32_t)p.n_tile;
-        // software pipeline over this warp's 16-column chunks: the next chunk's TMEM load is in flight
-        // while the current one is screened (two register buffers, ping-pong)
-        const ExactCtx xc{p.dim, p.cdp, p.cand, p.cand_cnt, p.overflow, p.cap, p.nq, p.one_bit_query};
-        auto process = [&](const int (&acc)[16], int c0) {
+        // this tile's refresh of the (possibly tightened) screen constants: loads issued now, stored after the tile
+        const bool refresh = MODE == SCAN_FILTER && p.k <= RETIGHTEN_KMAX && et < nv;
+        float4 fr0 = make_float4(0.f, 0.f, 0.f, 0.f), fr1 = fr0;
+        if (refresh) {
+          const float4* src = reinterpret_cast<const float4*>(p.qscreen + q0 + et);
+          fr0 = __ldcg(src);
+          fr1 = __ldcg(src + 1);
+        }
+        // software pipeline over this warp's 16-column chunks: the next chunk's TMEM load is in flight while the
+        // current one is screened
+        int acc[16], nxt[16];
+        int c0 = sub * 16;
+        if (c0 < nv) {
+          tc_ld16(d_addr + (uint32_t)c0, acc);
+          tc_wait_ld();
+        }
+        if (p.debug & 4u) c0 = nv;
+        while (c0 < nv) {
+          const int c1 = c0 + NSUB * 16;
+          if (c1 < nv) tc_ld16(d_addr + (uint32_t)c1, nxt);
           if (MODE == SCAN_DUMP) {
             if (valid) {
 #pragma unroll
               for (int j = 0; j < 16; j++) {
                 const int c = c0 + j;
                 if (c < nv)
-                  p.dump[(int64_t)(q0 + c) * p.dump_ld + i * TILE_ROWS + r] = bbqn::score_f32(
-                      (double)(acc[j] >> 3), ax, lx, addx, x1, qt_s[c], p.dim, p.cdp, SIM, p.one_bit_query != 0);
+                  p.dump[(int64_t)(q0 + c) * p.dump_ld + i * TILE_ROWS + r] =
+                      bbqn::score_f32((double)(acc[j] >> 3), rt.ax, rt.ux - rt.ax, rt.addx, (double)rt.x1, qt_s[c], p.dim,
+                                      p.cdp, SIM, p.one_bit_query != 0);
               }
             }
           } else {
             // branch-free screen of 16 queries; g_j >= 0  <=>  pair j may reach the top-k
             // (a NaN g_j, e.g. a row past the end of the shard, compares false)
             uint32_t mask = 0u;
+            if (!(p.debug & 1u)) {
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-              const float4 a = *reinterpret_cast<const float4*>(&qs_s[c0 + j]);
-              float g = fmaf(a.x, (float)acc[j], fmaf(rv, a.y, fmaf(x1f, a.z, fmaf(a.w, iv, gv))));
-              if (SIM == bbqn::SIM_EUCLIDEAN) g = fminf(g, qs_s[c0 + j].wadj * iv - g);
-              if (g >= 0.f) mask |= (1u << j);
+              for (int j = 0; j < 16; j++) {
+                const float4 a = *reinterpret_cast<const float4*>(&qs_s[c0 + j]);
+                float g = fmaf(a.x, (float)acc[j], fmaf(rv, a.y, fmaf(x1f, a.z, fmaf(a.w, iv, gv))));
+                if (SIM == bbqn::SIM_EUCLIDEAN) g = fminf(g, qs_s[c0 + j].wadj * iv - g);
+                if (g >= 0.f) mask |= (1u << j);
+              }
             }
             if (always) mask = 0xFFFFu;
-            if (mask != 0u) {  // rare: replay this lane's hits exactly
-#pragma unroll
-              for (int j = 0; j < 16; j++)
-                if (mask & (1u << j))
-                  mma_exact_pair<SIM>(xc, acc[j], q0 + c0 + j, qs_s[c0 + j].tau, &qt_s[min(c0 + j, nv - 1)], ax, lx, addx,
-                                      x1, id);
-            }
+            if (p.debug & 2u) mask = 0u;
+            if (mask != 0u)  // rare: park the hits for the drainer warp
+              mma_park_hits(ring_s, ring_ctl_s + 0, ring_ctl_s + 1, mask, (uint32_t)row, q0 + c0, acc[0], acc[1], acc[2],
+                            acc[3], acc[4], acc[5], acc[6], acc[7], acc[8], acc[9], acc[10], acc[11], acc[12], acc[13],
+                            acc[14], acc[15]);
           }
-        };
-        int accA[16], accB[16];
-        int c0 = sub * 16;
-        if (c0 < nv) {
-          tc_ld16(d_addr + (uint32_t)c0, accA);
-          tc_wait_ld();
-        }
-        while (c0 < nv) {
-          int c1 = c0 + NSUB * 16;
-          if (c1 < nv) tc_ld16(d_addr + (uint32_t)c1, accB);
-          process(accA, c0);
           if (c1 >= nv) break;
           tc_wait_ld();
-          c0 = c1 + NSUB * 16;
-          if (c0 < nv) tc_ld16(d_addr + (uint32_t)c0, accA);
-          process(accB, c1);
-          if (c0 < nv) tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; j++) acc[j] = nxt[j];
+          c0 = c1;
+        }
+        if (refresh) {
+          float4* dst = reinterpret_cast<float4*>(qs_s + et);
+          dst[0] = fr0;
+          dst[1] = fr1;
         }
         tc_fence_before();
         mbar_arrive(acc_empty + buf);
         tcount++;
       }
     }
+    __syncwarp();
+    if (lane == 0) atomicAdd(ring_ctl_s + 2, 1u);  // this epilogue warp will park nothing more
   }
 
   tc_fence_before();

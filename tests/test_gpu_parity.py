@@ -27,10 +27,12 @@ def bbq():
     return bbq_b200
 
 
-def make_format(bbq, sim, qb=4, lam=0.1, iters=5, force_path=None, scan=None, qquant=None):
+def make_format(bbq, sim, qb=4, lam=0.1, iters=5, force_path=None, scan=None, qquant=None, dyntau=None):
     """force_path / scan / qquant are test knobs read by bbq_create
     (BBQ_FORCE_PATH, BBQ_SCAN=popc|mma, BBQ_QQUANT=thread)."""
-    saved = {k: os.environ.pop(k, None) for k in ("BBQ_FORCE_PATH", "BBQ_SCAN", "BBQ_QQUANT")}
+    saved = {k: os.environ.pop(k, None) for k in ("BBQ_FORCE_PATH", "BBQ_SCAN", "BBQ_QQUANT", "BBQ_DYNTAU")}
+    if dyntau is not None:
+        os.environ["BBQ_DYNTAU"] = str(dyntau)
     if force_path is not None:
         os.environ["BBQ_FORCE_PATH"] = str(force_path)
     if scan is not None:
@@ -335,6 +337,26 @@ def test_mma_scan_matches_oracle_and_popcount(bbq, sim, n, dim, nq, k, qb):
     for qi in range(0, nq, max(1, nq // 6)):
         wi, ws = O.search_nearest_neighbors(qs[qi], idx, k, query_bits=qb, mode="canonical")
         assert mi[qi].tolist() == wi.tolist() and bits_equal(ms[qi], ws)
+
+
+@pytest.mark.parametrize("sim", SIMS)
+def test_mma_running_threshold_does_not_change_results(bbq, sim):
+    """The in-kernel tightening of tau only prunes work: same answers with it off, far fewer candidates with it on."""
+    rows, qs = gaussian(150000, 128, 121), gaussian(128, 128, 122)
+    on = make_format(bbq, sim, scan="mma")
+    off = make_format(bbq, sim, scan="mma", dyntau=0)
+    cen = np.zeros(128, np.float32)
+    qa = on.quantizeVectors(rows, centroid=cen)["quantizedVectors"]
+    qb_ = off.quantizeVectors(rows, centroid=cen)["quantizedVectors"]
+    ai, asc = on.searchBatch(qs, qa, 10)
+    bi, bsc = off.searchBatch(qs, qb_, 10)
+    assert np.array_equal(ai, bi) and bits_equal(asc, bsc)
+    assert on.stats()["last_engine"] == 2 and off.stats()["last_engine"] == 2
+    assert on.stats()["last_candidates"] < off.stats()["last_candidates"]
+    pp = make_format(bbq, sim, scan="popc")
+    qc = pp.quantizeVectors(rows, centroid=cen)["quantizedVectors"]
+    ci, csc = pp.searchBatch(qs, qc, 10)
+    assert np.array_equal(ai, ci) and bits_equal(asc, csc)
 
 
 def test_mma_scan_ties_and_degenerate_rows(bbq):
