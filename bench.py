@@ -55,11 +55,12 @@ def gen_queries(nq, dim):
 
 
 def load_peaks():
+    """-> (hbm GB/s, bf16 dense TFLOP/s burst, source)"""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(d["hbm_gbs"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -282,21 +283,42 @@ def run_gpu(args, w, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
-    # --- roofline of the dominant kernel (the scan; CUDA events on its own stream inside the library) --------
-    peak, peak_src = load_peaks()
+    # --- roofline of the dominant kernel (the filtered scan; CUDA events on its own stream inside the library) ---
+    hbm_peak, bf16_peak, peak_src = load_peaks()
     rows_local = r1 - r0
     bvec = (dim + 7) // 8 + 16                  # algorithmic bytes / scanned vector
-    scan_ms = st["scan_ms"] / max(st["scan_launches"], 1)
-    # the filtered scan is the launch that carries the step; its sample pre-pass is a second, small launch
+    scan_launch_ms = st["scan_ms"] / max(st["scan_launches"], 1)     # average duration of one scan launch
     scan_ms_step = st["scan_ms"] / args.steps
-    algo_bytes = rows_local * bvec
-    achieved = algo_bytes / (scan_ms_step * 1e-3) / 1e9 if scan_ms_step > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "bbqk::k_scan",
-                "algorithmic_bytes_per_step": algo_bytes, "scan_ms_per_step": scan_ms_step,
-                "scan_launches_per_step": st["scan_launches"] / args.steps, "avg_scan_launch_ms": scan_ms,
-                "query_effective_GBps": nq * algo_bytes / (scan_ms_step * 1e-3) / 1e9 if scan_ms_step > 0 else 0.0,
-                "quantize_ms_per_step": st["quantize_ms"] / args.steps, "select_ms_per_step": st["select_ms"] / args.steps}
+    algo_bytes = rows_local * bvec              # one pass over the shard serves the whole query batch
+    index_gbps = algo_bytes / (scan_launch_ms * 1e-3) / 1e9 if scan_launch_ms > 0 else 0.0
+    engine = {1: "popcount (LOP3+POPC)", 2: "tcgen05 kind::i8"}.get(st["last_engine"], "popcount (LOP3+POPC)")
+    if st["last_engine"] == 2:
+        # batched scan = integer contraction [rows x dim] . [dim x queries]: 2*rows*queries*dim ops per launch.
+        # Peak: kind::i8 runs at twice the bf16 rate on B200 (4.5 vs 2.25 PFLOP/s dense nominal); the measured
+        # denominator is therefore 2 x the measured cuBLAS bf16 burst figure.
+        ops = 2.0 * rows_local * nq * dim
+        achieved = ops / (scan_launch_ms * 1e-3) / 1e12
+        peak = 2.0 * bf16_peak
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s (int8, = TFLOP/s)",
+                    "frac": achieved / peak, "traffic": None,
+                    "peak_source": peak_src + ": 2 x bf16_tflops (int8 = 2 x bf16 rate)",
+                    "kernel": "bbqk::k_scan_mma<SCAN_FILTER>", "algorithmic_ops_per_launch": ops,
+                    "queries_resident_per_pass": st["mma_n_tile"], "passes_over_shard": st["mma_passes"],
+                    "hbm_view": {"algorithmic_bytes_per_launch": algo_bytes, "index_GBps": index_gbps,
+                                 "streamed_GBps": index_gbps * st["mma_passes"], "frac_of_hbm_peak": index_gbps / hbm_peak}}
+    else:
+        roofline = {"bound": "hbm", "achieved": index_gbps, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": index_gbps / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "kernel": "bbqk::k_scan<NB,SCAN_FILTER>", "algorithmic_bytes_per_launch": algo_bytes}
+    roofline.update({"avg_scan_launch_ms": scan_launch_ms, "scan_ms_per_step": scan_ms_step,
+                     "scan_launches_per_step": st["scan_launches"] / args.steps,
+                     "sample_ms_per_step": st["sample_ms"] / args.steps,
+                     "quantize_ms_per_step": st["quantize_ms"] / args.steps,
+                     "select_ms_per_step": st["select_ms"] / args.steps,
+                     "query_effective_GBps": nq * algo_bytes / (scan_launch_ms * 1e-3) / 1e9 if scan_launch_ms > 0 else 0.0,
+                     "scan_engine": engine})
+    peak = hbm_peak
+    achieved = index_gbps
 
     # --- CPU baseline beside it (rank 0, N=1 only): the oracle over THIS index's bytes, bounded sample --------
     cpu = None
@@ -316,7 +338,8 @@ def run_gpu(args, w, rank, world, local_rank):
 
     line = {"metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u32 popcount dot + f64 epilogue -> f32 score", "data": "synthetic",
+            "dtype": ("u8 x u8 -> s32 (tcgen05 kind::i8) + f32 screen + f64 exact replay -> f32 score" if st["last_engine"] == 2
+                      else "u32 AND+popcount dot + f64 epilogue -> f32 score"), "data": "synthetic",
             "config": {"workload": w["name"], "rows_total": n, "rows_per_gpu": rows_local, "dim": dim, "k": k,
                        "queries_per_step": nq, "similarity": sim, "query_bits": 4, "index_bits": 1,
                        "sharding": f"row-wise x{world}, NCCL all_gather top-k merge" if world > 1 else "single shard",
@@ -324,7 +347,7 @@ def run_gpu(args, w, rank, world, local_rank):
                        "corpus": f"N(0,1) f32, {'device' if device_gen else 'host'}-generated per 65536-row chunk, "
                                  f"explicit zero centroid; index build {build_s:.1f}s (untimed)",
                        "path": {0: "direct", 1: "sampled threshold + filtered scan", 2: "exact chunked"}[st["last_path"]]},
-            "index_GBps": achieved, "index_frac_of_hbm_peak": achieved / peak,
+            "index_GBps": index_gbps, "index_frac_of_hbm_peak": index_gbps / hbm_peak,
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}

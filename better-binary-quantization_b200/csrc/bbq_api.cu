@@ -80,6 +80,7 @@ struct bbq_ctx {
   // query scratch
   DevBuf qrows, qT, qcodes, qcorr, planes, qterms, tau, dump, cand, cand_cnt, flag, lists_a, lists_b,
       out_idx, out_score, dots, images, qscreen, tau_bits;
+  int64_t sample_tiles_dyn = 128;  // BBQ_SAMPLE_TILES: sample size when the running threshold is on
   uint32_t mma_debug = 0;   // BBQ_MMA_DEBUG: timing-attribution knobs of the tensor-core scan (results become wrong)
   bool dynamic_tau = true;  // BBQ_DYNTAU=0 keeps the sampled threshold fixed during the tensor-core scan (tests)
   int query_quantizer = 0;  // BBQ_QQUANT=thread forces the one-thread-per-query form (tests)
@@ -92,7 +93,7 @@ struct bbq_ctx {
   std::vector<cudaEvent_t> ev_pool;
 };
 
-enum { PROF_SCAN = 0, PROF_QUANT = 1, PROF_SELECT = 2 };
+enum { PROF_SCAN = 0, PROF_QUANT = 1, PROF_SELECT = 2, PROF_SAMPLE = 3 };
 struct ProfScope {  // records an event pair around a group of launches when profiling is on
   bbq_ctx* c;
   cudaStream_t st;
@@ -185,6 +186,7 @@ extern "C" int bbq_create(const bbq_config* config, bbq_ctx** out_ctx) {
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaMallocHost(&c->h_flag, (QUERY_BATCH + 1) * sizeof(uint32_t)));
   if (const char* e = getenv("BBQ_FORCE_PATH")) c->force_path = atoi(e);
+  if (const char* e = getenv("BBQ_SAMPLE_TILES")) c->sample_tiles_dyn = std::max(1, std::min(128, atoi(e)));
   if (const char* e = getenv("BBQ_MMA_DEBUG")) c->mma_debug = (uint32_t)atoi(e);
   if (const char* e = getenv("BBQ_DYNTAU")) c->dynamic_tau = atoi(e) != 0;
   if (const char* e = getenv("BBQ_QQUANT")) c->query_quantizer = !strcmp(e, "thread") ? 1 : 0;
@@ -227,6 +229,8 @@ extern "C" int bbq_get_stats(bbq_ctx* c, bbq_stats* out) {
       c->stats.scan_ms += ms;
     } else if (p.kind == PROF_QUANT) {
       c->stats.quantize_ms += ms;
+    } else if (p.kind == PROF_SAMPLE) {
+      c->stats.sample_ms += ms;
     } else {
       c->stats.select_ms += ms;
     }
@@ -248,7 +252,7 @@ extern "C" int bbq_reset_profiling(bbq_ctx* c) {
   bbq_stats tmp;
   TRY(bbq_get_stats(c, &tmp));
   c->stats.scan_launches = 0;
-  c->stats.scan_ms = c->stats.quantize_ms = c->stats.select_ms = 0.0;
+  c->stats.scan_ms = c->stats.quantize_ms = c->stats.select_ms = c->stats.sample_ms = 0.0;
   return BBQ_OK;
 }
 
@@ -638,8 +642,9 @@ static int launch_scan(bbq_index* ix, int mode, ScanParams p, int64_t ntiles, cu
   while (qb > 1 && smem_for(qb) > 160 * 1024) qb /= 2;
   if (smem_for(qb) > 227 * 1024) return fail(BBQ_ERR_UNSUPPORTED, "dimension too large for the scan tile");
   p.q_block = qb;
-  ProfScope prof(c, st, PROF_SCAN);
-  c->stats.scan_launches++;
+  const bool is_sample = mode == SCAN_DUMP && p.tile_stride > 1;
+  ProfScope prof(c, st, is_sample ? PROF_SAMPLE : PROF_SCAN);
+  if (!is_sample) c->stats.scan_launches++;
   dim3 grid((unsigned)ntiles, (unsigned)((p.nq + qb - 1) / qb));
   if (mode == SCAN_DUMP) return launch_scan_nb<SCAN_DUMP>(c, nb, grid, smem_for(qb), st, p);
   return launch_scan_nb<SCAN_FILTER>(c, nb, grid, smem_for(qb), st, p);
@@ -800,8 +805,10 @@ static int launch_scan_mma(bbq_index* ix, int mode, int nq, uint32_t k, const Mm
   p.cand_cnt = cand_cnt;
   p.cap = cap;
   p.overflow = overflow;
-  ProfScope prof(c, st, PROF_SCAN);
-  c->stats.scan_launches++;
+  ProfScope prof(c, st, mode == SCAN_DUMP ? PROF_SAMPLE : PROF_SCAN);
+  if (mode != SCAN_DUMP) c->stats.scan_launches++;
+  c->stats.mma_n_tile = (uint32_t)pl.n_tile;
+  c->stats.mma_passes = (uint32_t)pl.passes;
   const unsigned grid = (unsigned)std::min<int64_t>(ntiles, c->sm_count);
   if (mode == SCAN_DUMP) return launch_mma_sim<SCAN_DUMP>(c, p.sim, grid, pl.smem, st, p);
   return launch_mma_sim<SCAN_FILTER>(c, p.sim, grid, pl.smem, st, p);
@@ -917,14 +924,16 @@ static int search_filtered(bbq_index* ix, int nq, uint32_t k, int32_t* d_out_idx
   bbq_ctx* c = ix->ctx;
   const int64_t n = (int64_t)ix->n;
   const int64_t ntiles = (n + TILE_ROWS - 1) / TILE_ROWS, full_tiles = n / TILE_ROWS;
-  const int64_t stiles = std::min<int64_t>(SAMPLE_TILES, full_tiles);
+  MmaPlan pl;
+  const bool use_mma = mma_plan(ix, nq, &pl);
+  // with the running threshold of the tensor-core scan a quarter of the sample is enough to start from
+  const int64_t want_tiles = (use_mma && c->dynamic_tau && k <= RETIGHTEN_KMAX) ? c->sample_tiles_dyn : SAMPLE_TILES;
+  const int64_t stiles = std::min<int64_t>(want_tiles, full_tiles);
   const int64_t stride = std::max<int64_t>(1, full_tiles / stiles);
   TRY(c->dump.reserve((size_t)nq * SELECT_MAX * sizeof(float)));
   TRY(c->tau.reserve((size_t)nq * sizeof(float)));
   TRY(c->cand.reserve((size_t)nq * CAND_CAP * sizeof(uint64_t)));
   TRY(c->cand_cnt.reserve((size_t)(nq + 1) * sizeof(uint32_t)));
-  MmaPlan pl;
-  const bool use_mma = mma_plan(ix, nq, &pl);
   c->stats.last_engine = use_mma ? 2 : 1;
   if (use_mma) {
     TRY(prepare_mma_operands(ix, nq, pl, st));

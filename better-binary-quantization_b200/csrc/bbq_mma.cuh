@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 8; i++) {
-      mbar_init(a_full + i, 128);
+      mbar_init(a_full + i, 4);
       mbar_init(a_empty + i, 1);
     }
     for (int i = 0; i < 2; i++) {
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
     // be prefetched PF deep across tile boundaries (the loads come from HBM: ~1 us each if not in flight early).
     const int r = (warp - 4) * 32 + lane;  // row within the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    constexpr int PF = 8;
+    constexpr int PF = 4;
     const int64_t my_tiles = (p.ntiles > blockIdx.x) ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t total = my_tiles * nchunks;
     // cursor of the NEXT chunk to prefetch: (tile ordinal, chunk within the row)
@@ -670,7 +670,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
             tc_st32(lane_addr + a_col + stage * 32u, e);
             tc_wait_st();
             tc_fence_before();
-            mbar_arrive(a_full + stage);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full + stage);  // one arrival per expansion warp
             if (++stage == (uint32_t)nstage) {
               stage = 0;
               sphase ^= 1u;

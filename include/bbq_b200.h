@@ -171,6 +171,9 @@ typedef struct {
   double scan_ms;
   double quantize_ms;         /* query quantisation (K4) launches */
   double select_ms;           /* selection / merge (K3) launches */
+  double sample_ms;           /* threshold-sample scan launches (not counted in scan_ms / scan_launches) */
+  uint32_t mma_n_tile;        /* last tensor-core scan: queries resident per pass */
+  uint32_t mma_passes;        /* ... and passes over the shard */
 } bbq_stats;
 int bbq_get_stats(bbq_ctx* ctx, bbq_stats* out);
 /* Off by default.  When on, search calls bracket their kernel groups with CUDA events (recorded on the launch
