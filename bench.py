@@ -75,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
         except Exception:
@@ -264,7 +264,9 @@ def run_gpu(args, w, rank, world, local_rank):
     fmt.resetProfiling()
     l0 = fmt.stats()["kernel_launches"]
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms_total, clocks = timed(lambda: searcher.search_device(dq, k), args.steps, 0, sampler)
+    if sampler:
+        sampler.start()
+    ms_total, _ = timed(lambda: searcher.search_device(dq, k), args.steps, 0)
     st = fmt.stats()
     launches = st["kernel_launches"] - l0
     fmt.setProfiling(False)
@@ -273,6 +275,7 @@ def run_gpu(args, w, rank, world, local_rank):
 
     # --- e2e: pinned host queries -> H2D -> search (+ all_gather + merge) -> D2H, every step ------------------
     e2e_ms, _ = timed(lambda: searcher.search(hq, k), args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
     e2e_qps = nq / (e2e_ms / args.steps * 1e-3)
     h2d = nq * dim * 4 * world
     d2h = nq * k * 8 * world

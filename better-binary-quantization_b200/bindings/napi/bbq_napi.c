@@ -1,0 +1,178 @@
+/* bbq_napi.c — the N-API addon that sits between the reference's unchanged TypeScript surface
+ * (createBinaryQuantizationFormat / quickQuantize / quickSearch, src/index.ts:20-139) and libbbq_b200.so.
+ * Synchronous, like the reference: every call blocks until the CUDA stream is idle.
+ * Handles are napi externals with finalizers; the C library reference-counts the context, so the GC may
+ * finalize the format and its indexes in any order.  Errors become `throw new Error(<reference message>)`
+ * (the message table lives in ts/errors.ts; here the status code and (vector, position) are forwarded).
+ *
+ *   cc -shared -fPIC bbq_napi.c -I<node>/include/node -I../../../include -L../.. -lbbq_b200 -o bbq_b200.node
+ * Without Node headers (this container): cc -fsyntax-only -I. -I../../../include bbq_napi.c  (compile check only). */
+#ifdef BBQ_USE_REAL_NODE_API
+#include <node_api.h>
+#else
+#include "node_api_min.h"
+#endif
+#include <stdio.h>
+#include <string.h>
+#include "bbq_b200.h"
+
+#define ARGS(n)                                                          \
+  size_t argc = (n);                                                     \
+  napi_value argv[(n)];                                                  \
+  if (napi_get_cb_info(env, info, &argc, argv, NULL, NULL) != napi_ok) return NULL
+
+static napi_value throw_status(napi_env env, int status) {
+  int64_t vec = -1, pos = -1;
+  char code[64];
+  bbq_last_error_pos(&vec, &pos);
+  /* code = "BBQ:<status>:<vector>:<position>"; ts/errors.ts maps it to the reference's message text */
+  snprintf(code, sizeof code, "BBQ:%d:%lld:%lld", status, (long long)vec, (long long)pos);
+  napi_throw_error(env, code, bbq_last_error());
+  return NULL;
+}
+static void fin_ctx(napi_env env, void* data, void* hint) { (void)env; (void)hint; bbq_destroy((bbq_ctx*)data); }
+static void fin_index(napi_env env, void* data, void* hint) { (void)env; (void)hint; bbq_index_destroy((bbq_index*)data); }
+
+static int get_f32(napi_env env, napi_value v, const float** p, size_t* len) {
+  napi_typedarray_type t;
+  void* data;
+  if (napi_get_typedarray_info(env, v, &t, len, &data, NULL, NULL) != napi_ok || t != napi_float32_array) return 0;
+  *p = (const float*)data;
+  return 1;
+}
+
+/* create(queryBits, indexBits, similarity(0|1|2), lambda, iters, device) -> external ctx
+ * replaces `new BinaryQuantizationFormat(config)`, src/binaryQuantizationFormat.ts:141-158 */
+static napi_value n_create(napi_env env, napi_callback_info info) {
+  ARGS(6);
+  bbq_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  int64_t dev = -1;
+  napi_get_value_uint32(env, argv[0], &cfg.query_bits);
+  napi_get_value_uint32(env, argv[1], &cfg.index_bits);
+  napi_get_value_uint32(env, argv[2], &cfg.similarity);
+  napi_get_value_double(env, argv[3], &cfg.lambda);
+  napi_get_value_uint32(env, argv[4], &cfg.iters);
+  napi_get_value_int64(env, argv[5], &dev);
+  cfg.device = (int32_t)dev;
+  bbq_ctx* ctx = NULL;
+  const int st = bbq_create(&cfg, &ctx);
+  if (st != BBQ_OK) return throw_status(env, st);
+  napi_value out;
+  napi_create_external(env, ctx, fin_ctx, NULL, &out);
+  return out;
+}
+
+/* build(ctx, rowsFlat Float32Array[n*dim], n, dim, centroid Float32Array|null) -> external index
+ * replaces format.quantizeVectors(vectors), src/binaryQuantizationFormat.ts:165-263 (the TS side flattens
+ * Float32Array[] and raises the ragged-dimension error itself, as :185-193 does) */
+static napi_value n_build(napi_env env, napi_callback_info info) {
+  ARGS(5);
+  void* ctx;
+  const float *rows, *cen = NULL;
+  size_t len, clen;
+  int64_t n;
+  uint32_t dim;
+  napi_valuetype ct;
+  napi_get_value_external(env, argv[0], &ctx);
+  if (!get_f32(env, argv[1], &rows, &len)) return throw_status(env, BBQ_ERR_INVALID_ARG);
+  napi_get_value_int64(env, argv[2], &n);
+  napi_get_value_uint32(env, argv[3], &dim);
+  napi_typeof(env, argv[4], &ct);
+  if (ct == napi_object && !get_f32(env, argv[4], &cen, &clen)) return throw_status(env, BBQ_ERR_INVALID_ARG);
+  bbq_index* ix = NULL;
+  const int st = bbq_index_build((bbq_ctx*)ctx, rows, (uint64_t)n, dim, cen, &ix);
+  if (st != BBQ_OK) return throw_status(env, st);
+  napi_value out;
+  napi_create_external(env, ix, fin_index, NULL, &out);
+  return out;
+}
+
+/* info(index) -> {size, dimension, centroid: Float32Array, centroidDP}
+ * BinarizedByteVectorValues.size()/dimension()/getCentroid()/getCentroidDP(), src/types.ts:32-49 */
+static napi_value n_info(napi_env env, napi_callback_info info) {
+  ARGS(1);
+  void* ix;
+  napi_get_value_external(env, argv[0], &ix);
+  const uint32_t dim = bbq_index_dim((bbq_index*)ix);
+  napi_value out, ab, cen, v;
+  void* data;
+  double cdp = 0;
+  napi_create_object(env, &out);
+  napi_create_arraybuffer(env, dim * sizeof(float), &data, &ab);
+  bbq_index_centroid((bbq_index*)ix, (float*)data, &cdp);
+  napi_create_typedarray(env, napi_float32_array, dim, ab, 0, &cen);
+  napi_create_double(env, (double)bbq_index_size((bbq_index*)ix), &v);
+  napi_set_named_property(env, out, "size", v);
+  napi_create_uint32(env, dim, &v);
+  napi_set_named_property(env, out, "dimension", v);
+  napi_set_named_property(env, out, "centroid", cen);
+  napi_create_double(env, cdp, &v);
+  napi_set_named_property(env, out, "centroidDP", v);
+  return out;
+}
+
+/* search(index, queriesFlat Float32Array[nq*dim], nq, k) -> {indices: Int32Array[nq*count], scores: Float32Array, count}
+ * replaces format.searchNearestNeighbors(query, targetVectors, k), src/binaryQuantizationFormat.ts:308-412;
+ * nq > 1 is the additive batched entry. */
+static napi_value n_search(napi_env env, napi_callback_info info) {
+  ARGS(4);
+  void* ix;
+  const float* q;
+  size_t len;
+  uint32_t nq, count = 0;
+  int64_t k;
+  napi_get_value_external(env, argv[0], &ix);
+  if (!get_f32(env, argv[1], &q, &len)) return throw_status(env, BBQ_ERR_NULL);
+  napi_get_value_uint32(env, argv[2], &nq);
+  napi_get_value_int64(env, argv[3], &k);
+  if (len != (size_t)nq * bbq_index_dim((bbq_index*)ix)) return throw_status(env, BBQ_ERR_DIM_MISMATCH);
+  const size_t slots = (size_t)nq * (size_t)(k > 0 ? k : 0);
+  napi_value out, abi, abs_, ti, ts, v;
+  void *pi, *ps;
+  napi_create_arraybuffer(env, (slots ? slots : 1) * sizeof(int32_t), &pi, &abi);
+  napi_create_arraybuffer(env, (slots ? slots : 1) * sizeof(float), &ps, &abs_);
+  const int st = bbq_search((bbq_index*)ix, q, nq, k, (int32_t*)pi, (float*)ps, &count);
+  if (st != BBQ_OK) return throw_status(env, st);
+  napi_create_typedarray(env, napi_int32_array, slots, abi, 0, &ti);
+  napi_create_typedarray(env, napi_float32_array, slots, abs_, 0, &ts);
+  napi_create_object(env, &out);
+  napi_set_named_property(env, out, "indices", ti);
+  napi_set_named_property(env, out, "scores", ts);
+  napi_create_uint32(env, count, &v);
+  napi_set_named_property(env, out, "count", v);
+  return out;
+}
+
+/* rows(index, first, count) -> {packed: Uint8Array, corrections: Float64Array[count*4]}
+ * vectorValue(ord) / getCorrectiveTerms(ord), src/types.ts:36-42 — lazy device->host copy */
+static napi_value n_rows(napi_env env, napi_callback_info info) {
+  ARGS(3);
+  void* ix;
+  int64_t first, count;
+  napi_get_value_external(env, argv[0], &ix);
+  napi_get_value_int64(env, argv[1], &first);
+  napi_get_value_int64(env, argv[2], &count);
+  const size_t p = (bbq_index_dim((bbq_index*)ix) + 7) / 8;
+  napi_value out, ab1, ab2, t1, t2;
+  void *d1, *d2;
+  napi_create_arraybuffer(env, (size_t)count * p, &d1, &ab1);
+  napi_create_arraybuffer(env, (size_t)count * 4 * sizeof(double), &d2, &ab2);
+  const int st = bbq_index_export((bbq_index*)ix, (uint64_t)first, (uint64_t)count, (uint8_t*)d1, (double*)d2);
+  if (st != BBQ_OK) return throw_status(env, st);
+  napi_create_typedarray(env, napi_uint8_array, (size_t)count * p, ab1, 0, &t1);
+  napi_create_typedarray(env, napi_float64_array, (size_t)count * 4, ab2, 0, &t2);
+  napi_create_object(env, &out);
+  napi_set_named_property(env, out, "packed", t1);
+  napi_set_named_property(env, out, "corrections", t2);
+  return out;
+}
+
+NAPI_MODULE_INIT() {
+  const napi_property_descriptor props[] = {
+      {"create", NULL, n_create, NULL, NULL, NULL, 0, NULL}, {"build", NULL, n_build, NULL, NULL, NULL, 0, NULL},
+      {"info", NULL, n_info, NULL, NULL, NULL, 0, NULL},     {"search", NULL, n_search, NULL, NULL, NULL, 0, NULL},
+      {"rows", NULL, n_rows, NULL, NULL, NULL, 0, NULL}};
+  napi_define_properties(env, exports, sizeof props / sizeof props[0], props);
+  return exports;
+}
