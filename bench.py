@@ -300,7 +300,8 @@ def run_gpu(args, w, rank, world, local_rank):
         # batched scan = integer contraction [rows x dim] . [dim x queries]: 2*rows*queries*dim ops per launch.
         # Peak: kind::i8 runs at twice the bf16 rate on B200 (4.5 vs 2.25 PFLOP/s dense nominal); the measured
         # denominator is therefore 2 x the measured cuBLAS bf16 burst figure.
-        ops = 2.0 * rows_local * nq * dim
+        launches_per_step = max(st["scan_launches"] / args.steps, 1.0)   # the library scans <= 1024 queries per launch
+        ops = 2.0 * rows_local * (nq / launches_per_step) * dim
         achieved = ops / (scan_launch_ms * 1e-3) / 1e12
         peak = 2.0 * bf16_peak
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s (int8, = TFLOP/s)",
@@ -319,7 +320,7 @@ def run_gpu(args, w, rank, world, local_rank):
                      "sample_ms_per_step": st["sample_ms"] / args.steps,
                      "quantize_ms_per_step": st["quantize_ms"] / args.steps,
                      "select_ms_per_step": st["select_ms"] / args.steps,
-                     "query_effective_GBps": nq * algo_bytes / (scan_launch_ms * 1e-3) / 1e9 if scan_launch_ms > 0 else 0.0,
+                     "query_effective_GBps": (nq * algo_bytes / (scan_ms_step * 1e-3) / 1e9) if scan_ms_step > 0 else 0.0,
                      "scan_engine": engine})
     peak = hbm_peak
     achieved = index_gbps
