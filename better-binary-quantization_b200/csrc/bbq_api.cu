@@ -81,6 +81,7 @@ struct bbq_ctx {
   DevBuf qrows, qT, qcodes, qcorr, planes, qterms, tau, dump, cand, cand_cnt, flag, lists_a, lists_b,
       out_idx, out_score, dots, images, qscreen, tau_bits;
   int64_t sample_tiles_dyn = 128;  // BBQ_SAMPLE_TILES: sample size when the running threshold is on
+  int mma_ntile_cap = 0;    // BBQ_MMA_NTILE: cap on the queries resident per pass (tuning experiments)
   uint32_t mma_debug = 0;   // BBQ_MMA_DEBUG: timing-attribution knobs of the tensor-core scan (results become wrong)
   bool dynamic_tau = true;  // BBQ_DYNTAU=0 keeps the sampled threshold fixed during the tensor-core scan (tests)
   int query_quantizer = 0;  // BBQ_QQUANT=thread forces the one-thread-per-query form (tests)
@@ -187,6 +188,7 @@ extern "C" int bbq_create(const bbq_config* config, bbq_ctx** out_ctx) {
   CU(cudaMallocHost(&c->h_flag, (QUERY_BATCH + 1) * sizeof(uint32_t)));
   if (const char* e = getenv("BBQ_FORCE_PATH")) c->force_path = atoi(e);
   if (const char* e = getenv("BBQ_SAMPLE_TILES")) c->sample_tiles_dyn = std::max(1, std::min(128, atoi(e)));
+  if (const char* e = getenv("BBQ_MMA_NTILE")) c->mma_ntile_cap = atoi(e);
   if (const char* e = getenv("BBQ_MMA_DEBUG")) c->mma_debug = (uint32_t)atoi(e);
   if (const char* e = getenv("BBQ_DYNTAU")) c->dynamic_tau = atoi(e) != 0;
   if (const char* e = getenv("BBQ_QQUANT")) c->query_quantizer = !strcmp(e, "thread") ? 1 : 0;
@@ -712,6 +714,7 @@ static bool mma_plan(const bbq_index* ix, int nq, MmaPlan* out) {
   const size_t budget = 227 * 1024 - 1024 - (HIT_RING * sizeof(uint64_t) + 64);
   int n_cap = (int)(budget / ((size_t)pl.kbytes + 64)) / 16 * 16;
   n_cap = std::min(n_cap, MMA_N_MAX);
+  if (c->mma_ntile_cap > 0) n_cap = std::min(n_cap, c->mma_ntile_cap / 16 * 16);
   if (n_cap < 16) return false;
   if (c->scan_engine != 2 && nq < 64) return false;  // small batches: the popcount kernel is HBM/latency bound anyway
   pl.passes = (nq + n_cap - 1) / n_cap;

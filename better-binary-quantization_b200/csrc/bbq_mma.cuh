@@ -315,7 +315,7 @@ struct MmaParams {
   uint32_t* tau_bits;      // [passes * n_tile] ordered-key form of tau, atomicMax'ed
   const IndexBounds* bounds;
   uint32_t k;              // top-k size (dynamic tightening needs k <= RETIGHTEN_KMAX)
-  uint32_t debug;          // profiling knobs (BBQ_MMA_DEBUG): 1 = epilogue skips the screen, 2 = hits are ignored, 4 = no TMEM loads
+  uint32_t debug;          // profiling knobs (BBQ_MMA_DEBUG): 1 = epilogue skips the screen, 2 = hits are ignored, 4 = no TMEM loads, 8 = expansion polls without a suspend hint
   const float4* rscreen;   // [n] per-row screen constants (k_index_bounds)
   const bbqn::QueryTerms* qterms;
   int nq, n_tile, passes, nstage;
@@ -595,6 +595,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
           if (lane == 0) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
+              if (p.debug & 64u) break;
               const uint32_t a_tmem = tmem_base + a_col + stage * 32u + (uint32_t)j * 8u;
               const uint64_t bdesc = make_kmajor_desc(b_addr + (uint32_t)((kc * 4 + j) * 2) * lbo, lbo, 128u);
               tc_mma_i8_ts(d_tmem, a_tmem, bdesc, idesc, (kc | j) != 0 ? 1u : 0u);
@@ -632,7 +633,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
     auto load_next = [&]() -> uint4 {
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if (pf_tile < my_tiles) {
-        const int64_t row = (p.tile_first + (blockIdx.x + pf_tile * gridDim.x) * p.tile_stride) * TILE_ROWS + r;
+        const int64_t row = (p.debug & 16u) ? p.n : (p.tile_first + (blockIdx.x + pf_tile * gridDim.x) * p.tile_stride) * TILE_ROWS + r;
         if (row < p.n) v = __ldg(reinterpret_cast<const uint4*>(p.codes + row * (int64_t)p.row_bytes) + pf_kc);
         if (++pf_kc == nchunks) {
           pf_kc = 0;
@@ -640,6 +641,25 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
         }
       }
       return v;
+    };
+    // Two chunks per hand-off: both tcgen05.st are in flight before the single wait::st, and the second chunk
+    // is expanded while the first store travels — the store latency, not the ALU work, bounds this loop.
+    auto expand = [&](const uint4& x, uint32_t (&e)[32]) {
+      const uint32_t ws[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int g = 0; g < 4; g++) {
+        const uint32_t lo = ws[g], hi = ws[g] >> 4;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          e[8 * g + b] = lo & (0x01010101u << b);      // u = b     : bit b   of each packed byte, weight 2^b
+          e[8 * g + 4 + b] = hi & (0x01010101u << b);  // u = 4 + b : bit 4+b of each packed byte, weight 2^b
+        }
+      }
+    };
+    auto wait_stage = [&](uint32_t st_, uint32_t ph_) {
+      if (p.debug & 8u) mbar_wait(a_empty + st_, ph_ ^ 1u);
+      else mbar_wait_relaxed(a_empty + st_, ph_ ^ 1u);
+      tc_fence_after();
     };
     uint32_t stage = 0, sphase = 0;
     for (int pass = 0; pass < p.passes; pass++) {
@@ -650,31 +670,38 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
       for (int i = 0; i < PF; i++) q[i] = load_next();
       for (int64_t f0 = 0; f0 < total; f0 += PF) {
 #pragma unroll
-        for (int i = 0; i < PF; i++) {
+        for (int i = 0; i < PF; i += 2) {
           if (f0 + i < total) {
-            const uint4 x = q[i];
+            const bool two = f0 + i + 1 < total;
+            uint32_t e0[32], e1[32];
+            expand(q[i], e0);
             q[i] = load_next();
-            uint32_t e[32];
-            const uint32_t ws[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-              const uint32_t lo = ws[g], hi = ws[g] >> 4;
-#pragma unroll
-              for (int b = 0; b < 4; b++) {
-                e[8 * g + b] = lo & (0x01010101u << b);      // u = b     : bit b   of each packed byte, weight 2^b
-                e[8 * g + 4 + b] = hi & (0x01010101u << b);  // u = 4 + b : bit 4+b of each packed byte, weight 2^b
-              }
-            }
-            mbar_wait_relaxed(a_empty + stage, sphase ^ 1u);
-            tc_fence_after();
-            tc_st32(lane_addr + a_col + stage * 32u, e);
-            tc_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_full + stage);  // one arrival per expansion warp
+            const uint32_t s0 = stage, p0 = sphase;
             if (++stage == (uint32_t)nstage) {
               stage = 0;
               sphase ^= 1u;
+            }
+            wait_stage(s0, p0);
+            if (!(p.debug & 32u)) tc_st32(lane_addr + a_col + s0 * 32u, e0);
+            uint32_t s1 = 0;
+            if (two) {
+              expand(q[i + 1], e1);
+              q[i + 1] = load_next();
+              s1 = stage;
+              const uint32_t p1 = sphase;
+              if (++stage == (uint32_t)nstage) {
+                stage = 0;
+                sphase ^= 1u;
+              }
+              wait_stage(s1, p1);
+              if (!(p.debug & 32u)) tc_st32(lane_addr + a_col + s1 * 32u, e1);
+            }
+            if (!(p.debug & 32u)) tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {  // one arrival per expansion warp and stage
+              mbar_arrive(a_full + s0);
+              if (two) mbar_arrive(a_full + s1);
             }
           }
         }

@@ -208,6 +208,28 @@ def test_search_ties_lower_index_first(bbq):
                 assert np.all(np.diff(gi[0][:20]) == 40)   # the best row's duplicates, ascending ids
 
 
+@pytest.mark.parametrize("scan", ["popc", "mma"])
+def test_candidate_overflow_falls_back_to_exact_path(bbq, scan):
+    """Adversarial index: every row is the same vector, so every score ties and no sampled threshold can prune —
+    each query's candidate list overflows and the exact chunked path must take over, still returning the canonical
+    answer (the lowest row ids)."""
+    n, dim, nq, k = 40000, 64, 64, 10
+    row = gaussian(1, dim, 131)
+    idx = O.quantize_vectors(np.concatenate([row, gaussian(3, dim, 132)]), sim="COSINE", want_unpacked=False,
+                             centroid=np.zeros(dim, np.float32))
+    packed, corr = np.repeat(idx.packed[:1], n, 0), np.repeat(idx.corr[:1], n, 0)
+    big = O.OracleIndex(idx.centroid, packed, None, corr, dim, "COSINE", 1)
+    fmt = make_format(bbq, "COSINE", scan=scan)
+    qv = fmt.adoptQuantized(packed, corr, idx.centroid)
+    qs = gaussian(nq, dim, 133)
+    gi, gs = fmt.searchBatch(qs, qv, k)
+    st = fmt.stats()
+    assert st["last_overflow"] == 1 and st["last_path"] == 2
+    for qi in (0, 17, 63):
+        wi, ws = O.search_nearest_neighbors(qs[qi], big, k, mode="canonical")
+        assert gi[qi].tolist() == wi.tolist() == list(range(k)) and bits_equal(gs[qi], ws)
+
+
 def test_search_edge_cases(bbq):
     rows = gaussian(7, 32, 71)
     fmt = make_format(bbq, "COSINE")
