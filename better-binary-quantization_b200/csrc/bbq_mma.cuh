@@ -315,7 +315,7 @@ struct MmaParams {
   uint32_t* tau_bits;      // [passes * n_tile] ordered-key form of tau, atomicMax'ed
   const IndexBounds* bounds;
   uint32_t k;              // top-k size (dynamic tightening needs k <= RETIGHTEN_KMAX)
-  uint32_t debug;          // profiling knobs (BBQ_MMA_DEBUG): 1 = epilogue skips the screen, 2 = hits are ignored, 4 = no TMEM loads, 8 = expansion polls without a suspend hint
+  uint32_t debug;          // profiling knobs (BBQ_MMA_DEBUG): 1 = epilogue skips the screen, 2 = hits are ignored, 4 = no TMEM loads
   const float4* rscreen;   // [n] per-row screen constants (k_index_bounds)
   const bbqn::QueryTerms* qterms;
   int nq, n_tile, passes, nstage;
@@ -595,7 +595,6 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
           if (lane == 0) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-              if (p.debug & 64u) break;
               const uint32_t a_tmem = tmem_base + a_col + stage * 32u + (uint32_t)j * 8u;
               const uint64_t bdesc = make_kmajor_desc(b_addr + (uint32_t)((kc * 4 + j) * 2) * lbo, lbo, 128u);
               tc_mma_i8_ts(d_tmem, a_tmem, bdesc, idesc, (kc | j) != 0 ? 1u : 0u);
@@ -627,18 +626,24 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
     constexpr int PF = 4;
     const int64_t my_tiles = (p.ntiles > blockIdx.x) ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t total = my_tiles * nchunks;
-    // cursor of the NEXT chunk to prefetch: (tile ordinal, chunk within the row)
+    // cursor of the NEXT chunk to prefetch: tile ordinal + a row pointer that is recomputed once per tile
     int64_t pf_tile = 0;
     int pf_kc = 0;
+    const uint4* pf_ptr = nullptr;  // nullptr: the row lies past the end of the shard (zero chunks)
+    auto pf_set_tile = [&]() {
+      pf_ptr = nullptr;
+      if (pf_tile < my_tiles) {
+        const int64_t row = (p.tile_first + (blockIdx.x + pf_tile * gridDim.x) * p.tile_stride) * TILE_ROWS + r;
+        if (row < p.n) pf_ptr = reinterpret_cast<const uint4*>(p.codes + row * (int64_t)p.row_bytes);
+      }
+    };
     auto load_next = [&]() -> uint4 {
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (pf_tile < my_tiles) {
-        const int64_t row = (p.debug & 16u) ? p.n : (p.tile_first + (blockIdx.x + pf_tile * gridDim.x) * p.tile_stride) * TILE_ROWS + r;
-        if (row < p.n) v = __ldg(reinterpret_cast<const uint4*>(p.codes + row * (int64_t)p.row_bytes) + pf_kc);
-        if (++pf_kc == nchunks) {
-          pf_kc = 0;
-          pf_tile++;
-        }
+      if (pf_ptr != nullptr) v = __ldg(pf_ptr + pf_kc);
+      if (++pf_kc == nchunks) {
+        pf_kc = 0;
+        pf_tile++;
+        pf_set_tile();
       }
       return v;
     };
@@ -657,8 +662,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
       }
     };
     auto wait_stage = [&](uint32_t st_, uint32_t ph_) {
-      if (p.debug & 8u) mbar_wait(a_empty + st_, ph_ ^ 1u);
-      else mbar_wait_relaxed(a_empty + st_, ph_ ^ 1u);
+      mbar_wait_relaxed(a_empty + st_, ph_ ^ 1u);
       tc_fence_after();
     };
     uint32_t stage = 0, sphase = 0;
@@ -666,6 +670,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
       uint4 q[PF];
       pf_tile = 0;
       pf_kc = 0;
+      pf_set_tile();
 #pragma unroll
       for (int i = 0; i < PF; i++) q[i] = load_next();
       for (int64_t f0 = 0; f0 < total; f0 += PF) {
@@ -682,7 +687,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
               sphase ^= 1u;
             }
             wait_stage(s0, p0);
-            if (!(p.debug & 32u)) tc_st32(lane_addr + a_col + s0 * 32u, e0);
+            tc_st32(lane_addr + a_col + s0 * 32u, e0);
             uint32_t s1 = 0;
             if (two) {
               expand(q[i + 1], e1);
@@ -694,9 +699,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
                 sphase ^= 1u;
               }
               wait_stage(s1, p1);
-              if (!(p.debug & 32u)) tc_st32(lane_addr + a_col + s1 * 32u, e1);
+              tc_st32(lane_addr + a_col + s1 * 32u, e1);
             }
-            if (!(p.debug & 32u)) tc_wait_st();
+            tc_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {  // one arrival per expansion warp and stage
