@@ -385,6 +385,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--datagen", default="auto", choices=["auto", "host", "device"])
+    ap.add_argument("--nq", type=int, default=0, help="override the queries per step of the workload (experiments)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--cpu-max-queries", type=int, default=16)
@@ -393,7 +394,10 @@ def main():
     ap.add_argument("--ref-queries-per-step", type=int, default=1)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if args.nq > 0:
+        w["nq"] = args.nq
+        w["name"] += f" [queries per step overridden: {args.nq}]"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

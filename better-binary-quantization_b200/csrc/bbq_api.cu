@@ -81,6 +81,7 @@ struct bbq_ctx {
   DevBuf qrows, qT, qcodes, qcorr, planes, qterms, tau, dump, cand, cand_cnt, flag, lists_a, lists_b,
       out_idx, out_score, dots, images, qscreen, tau_bits;
   int64_t sample_tiles_dyn = 128;  // BBQ_SAMPLE_TILES: sample size when the running threshold is on
+  int popc_form = 0;        // BBQ_POPC_FORM=tile forces the shared-memory tile form of the popcount scan (tests)
   int mma_ntile_cap = 0;    // BBQ_MMA_NTILE: cap on the queries resident per pass (tuning experiments)
   uint32_t mma_debug = 0;   // BBQ_MMA_DEBUG: timing-attribution knobs of the tensor-core scan (results become wrong)
   bool dynamic_tau = true;  // BBQ_DYNTAU=0 keeps the sampled threshold fixed during the tensor-core scan (tests)
@@ -188,6 +189,7 @@ extern "C" int bbq_create(const bbq_config* config, bbq_ctx** out_ctx) {
   CU(cudaMallocHost(&c->h_flag, (QUERY_BATCH + 1) * sizeof(uint32_t)));
   if (const char* e = getenv("BBQ_FORCE_PATH")) c->force_path = atoi(e);
   if (const char* e = getenv("BBQ_SAMPLE_TILES")) c->sample_tiles_dyn = std::max(1, std::min(128, atoi(e)));
+  if (const char* e = getenv("BBQ_POPC_FORM")) c->popc_form = !strcmp(e, "tile") ? 1 : 0;
   if (const char* e = getenv("BBQ_MMA_NTILE")) c->mma_ntile_cap = atoi(e);
   if (const char* e = getenv("BBQ_MMA_DEBUG")) c->mma_debug = (uint32_t)atoi(e);
   if (const char* e = getenv("BBQ_DYNTAU")) c->dynamic_tau = atoi(e) != 0;
@@ -608,12 +610,26 @@ extern "C" int bbq_index_export(const bbq_index* ix, uint64_t first, uint64_t co
 // search
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
-static int launch_scan_nb(bbq_ctx* c, int nb, dim3 grid, size_t smem, cudaStream_t st, const ScanParams& p) {
+static int launch_scan_nb(bbq_ctx* c, int nb, bool stream_form, dim3 grid, size_t smem, cudaStream_t st,
+                          const ScanParams& p) {
 #define BBQ_SCAN_CASE(NB)                                                                                          \
   case NB:                                                                                                         \
-    if (smem > 48 * 1024)                                                                                          \
-      CU(cudaFuncSetAttribute(k_scan<NB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-    LAUNCH(c, (k_scan<NB, MODE>), grid, TILE_ROWS, smem, st, p);                                                   \
+    if (stream_form) {                                                                                             \
+      switch (p.row_bytes >> 4) {                                                                                  \
+        case 1: LAUNCH(c, (k_scan_stream<NB, MODE, 1>), dim3(grid.x), TILE_ROWS, 0, st, p); break;                 \
+        case 2: LAUNCH(c, (k_scan_stream<NB, MODE, 2>), dim3(grid.x), TILE_ROWS, 0, st, p); break;                 \
+        case 3: LAUNCH(c, (k_scan_stream<NB, MODE, 3>), dim3(grid.x), TILE_ROWS, 0, st, p); break;                 \
+        case 4: LAUNCH(c, (k_scan_stream<NB, MODE, 4>), dim3(grid.x), TILE_ROWS, 0, st, p); break;                 \
+        case 6: LAUNCH(c, (k_scan_stream<NB, MODE, 6>), dim3(grid.x), TILE_ROWS, 0, st, p); break;                 \
+        case 8: LAUNCH(c, (k_scan_stream<NB, MODE, 8>), dim3(grid.x), TILE_ROWS, 0, st, p); break;                 \
+        case 12: LAUNCH(c, (k_scan_stream<NB, MODE, 12>), dim3(grid.x), TILE_ROWS, 0, st, p); break;               \
+        default: return fail(BBQ_ERR_UNSUPPORTED, "no streaming scan for this row size");                          \
+      }                                                                                                            \
+    } else {                                                                                                       \
+      if (smem > 48 * 1024)                                                                                        \
+        CU(cudaFuncSetAttribute(k_scan<NB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+      LAUNCH(c, (k_scan<NB, MODE>), grid, TILE_ROWS, smem, st, p);                                                 \
+    }                                                                                                              \
     break;
   switch (nb) {
     BBQ_SCAN_CASE(1)
@@ -648,8 +664,11 @@ static int launch_scan(bbq_index* ix, int mode, ScanParams p, int64_t ntiles, cu
   ProfScope prof(c, st, is_sample ? PROF_SAMPLE : PROF_SCAN);
   if (!is_sample) c->stats.scan_launches++;
   dim3 grid((unsigned)ntiles, (unsigned)((p.nq + qb - 1) / qb));
-  if (mode == SCAN_DUMP) return launch_scan_nb<SCAN_DUMP>(c, nb, grid, smem_for(qb), st, p);
-  return launch_scan_nb<SCAN_FILTER>(c, nb, grid, smem_for(qb), st, p);
+  // one or a few queries: the streaming (register/shuffle, HBM-bound) form; it needs >= 2 rows per 512-byte load
+  const bool stream_ok = w4 == 1 || w4 == 2 || w4 == 3 || w4 == 4 || w4 == 6 || w4 == 8 || w4 == 12;  // dims 128..1536
+  const bool stream_form = c->popc_form != 1 && p.nq <= 4 && stream_ok;
+  if (mode == SCAN_DUMP) return launch_scan_nb<SCAN_DUMP>(c, nb, stream_form, grid, smem_for(qb), st, p);
+  return launch_scan_nb<SCAN_FILTER>(c, nb, stream_form, grid, smem_for(qb), st, p);
 }
 
 template <int MODE>

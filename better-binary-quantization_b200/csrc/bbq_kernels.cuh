@@ -518,6 +518,85 @@ __global__ void __launch_bounds__(TILE_ROWS) k_scan(const ScanParams p) {
   }
 }
 
+// K1s: the streaming form of the scan for ONE (or a few) queries — the HBM-bound regime.  No shared memory:
+// a warp reads its 32 rows as a flat stream of 16-byte chunks (32 lanes x 16 B = 512 contiguous bytes per load,
+// all loads of the 32 rows in flight before the first is used), the query's bit-planes for a lane's fixed
+// 128-dim segment sit in registers, partial popcount sums are reduced across the lanes that share a row, and
+// the exact f64 epilogue then runs with one row per lane (coalesced corrective loads, no divergence).
+// Same integers, same scores, same outputs as k_scan; tiles/dump layout identical.
+template <int NB, int MODE, int W4>
+__global__ void __launch_bounds__(TILE_ROWS) k_scan_stream(const ScanParams p) {
+  constexpr int w4 = W4;                  // 16-byte chunks per row (compile-time: 1..16)
+  constexpr int R = 32 / w4;              // rows per load instruction
+  constexpr int iters = (32 + R - 1) / R; // load instructions per 32-row unit
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int seg = lane % w4, grp = lane / w4;      // this lane's segment of a row / which row of the instruction
+  const bool lane_on = lane < R * w4;
+  const int64_t tile = p.tile_first + (int64_t)blockIdx.x * p.tile_stride;
+  const int64_t unit_row0 = tile * TILE_ROWS + warp * 32;  // first row of this warp's unit
+
+  // all loads of the unit first (memory-level parallelism), zero for rows past the end
+  uint4 x[iters];
+#pragma unroll
+  for (int it = 0; it < iters; it++) {
+    x[it] = make_uint4(0u, 0u, 0u, 0u);
+    const int rl = it * R + grp;  // row within the unit
+    const int64_t row = unit_row0 + rl;
+    if (lane_on && rl < 32 && row < p.n)
+      x[it] = __ldg(reinterpret_cast<const uint4*>(p.codes + row * (int64_t)p.row_bytes) + seg);
+  }
+  const int64_t my_row = unit_row0 + lane;  // epilogue: one row per lane
+  const bool valid = my_row < p.n;
+  double ax = 0, lx = 0, addx = 0, x1 = 0;
+  if (valid) {
+    ax = __ldg(p.lower + my_row);
+    lx = __ldg(p.upper + my_row) - ax;
+    addx = __ldg(p.addc + my_row);
+    x1 = (double)__ldg(p.compsum + my_row);
+  }
+  const uint32_t id = p.base + (uint32_t)my_row;
+  const int src_lane = (lane % R) * w4;  // leader lane of the group that held this lane's row
+  for (int q = 0; q < p.nq; q++) {
+    uint4 pl[NB];
+    const uint4* psrc = reinterpret_cast<const uint4*>(p.planes) + (size_t)q * NB * w4;
+#pragma unroll
+    for (int b = 0; b < NB; b++) pl[b] = lane_on ? __ldg(psrc + b * w4 + seg) : make_uint4(0u, 0u, 0u, 0u);
+    int mydot = 0;
+#pragma unroll
+    for (int it = 0; it < iters; it++) {
+      int part = 0;
+#pragma unroll
+      for (int b = 0; b < NB; b++) {
+        const int c = __popc(x[it].x & pl[b].x) + __popc(x[it].y & pl[b].y) + __popc(x[it].z & pl[b].z) +
+                      __popc(x[it].w & pl[b].w);
+        part += c << b;
+      }
+      // sum over the w4 lanes of a row (lanes of a row are contiguous; w4 need not be a power of two)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        if (o < w4) {
+          const int other = __shfl_down_sync(0xffffffffu, part, o);
+          if (seg + o < w4) part += other;
+        }
+      }
+      const int got = __shfl_sync(0xffffffffu, part, src_lane);
+      if (lane / R == it) mydot = got;  // row (it*R + lane%R) == lane
+    }
+    const bbqn::QueryTerms qt = p.qterms[q];
+    const float score = bbqn::score_f32((double)mydot, ax, lx, addx, x1, qt, p.dim, p.cdp, p.sim, p.one_bit_query != 0);
+    if (MODE == SCAN_DUMP) {
+      if (valid) {
+        p.dump[(int64_t)q * p.dump_ld + (int64_t)blockIdx.x * TILE_ROWS + warp * 32 + lane] = score;
+        if (p.dots != nullptr && q == 0) p.dots[my_row] = mydot;
+      }
+    } else if (valid && score >= p.tau[q]) {
+      const uint32_t pos = atomicAdd(p.cand_cnt + q, 1u);
+      if (pos < p.cap) p.cand[(size_t)q * p.cap + pos] = bbqn::topk_key(score, id);
+      else *p.overflow = 1u;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3: deterministic selection.  One CTA per query sorts up to SELECT_MAX 64-bit keys
 // (ordered f32 score << 32 | ~row id) in shared memory (bitonic, descending) and emits the k best —

@@ -27,10 +27,13 @@ def bbq():
     return bbq_b200
 
 
-def make_format(bbq, sim, qb=4, lam=0.1, iters=5, force_path=None, scan=None, qquant=None, dyntau=None):
+def make_format(bbq, sim, qb=4, lam=0.1, iters=5, force_path=None, scan=None, qquant=None, dyntau=None,
+                popc_form=None):
     """force_path / scan / qquant are test knobs read by bbq_create
     (BBQ_FORCE_PATH, BBQ_SCAN=popc|mma, BBQ_QQUANT=thread)."""
-    saved = {k: os.environ.pop(k, None) for k in ("BBQ_FORCE_PATH", "BBQ_SCAN", "BBQ_QQUANT", "BBQ_DYNTAU")}
+    saved = {k: os.environ.pop(k, None) for k in ("BBQ_FORCE_PATH", "BBQ_SCAN", "BBQ_QQUANT", "BBQ_DYNTAU", "BBQ_POPC_FORM")}
+    if popc_form is not None:
+        os.environ["BBQ_POPC_FORM"] = popc_form
     if dyntau is not None:
         os.environ["BBQ_DYNTAU"] = str(dyntau)
     if force_path is not None:
@@ -132,11 +135,12 @@ def test_query_quantize_bit_exact(bbq, sim, qb, qquant):
 # ---- K1: integer dots and corrected scores over the whole index ------------------------------------------
 @pytest.mark.parametrize("sim", SIMS)
 @pytest.mark.parametrize("qb", [1, 4, 8])
-@pytest.mark.parametrize("n,dim", [(3000, 128), (1500, 100), (2000, 768), (700, 1536)])
-def test_qcdist_and_scores_bit_exact(bbq, sim, qb, n, dim):
+@pytest.mark.parametrize("n,dim", [(3000, 128), (1500, 100), (2000, 768), (700, 1536), (300, 2048), (900, 40)])
+@pytest.mark.parametrize("form", [None, "tile"])   # streaming (register/shuffle) and shared-memory tile kernels
+def test_qcdist_and_scores_bit_exact(bbq, sim, qb, n, dim, form):
     rows, qs = gaussian(n, dim, 31 + dim), gaussian(2, dim, 32 + dim)
     idx = O.quantize_vectors(rows, sim=sim, want_unpacked=False)
-    fmt = make_format(bbq, sim, qb=qb)
+    fmt = make_format(bbq, sim, qb=qb, popc_form=form)
     qv = fmt.adoptQuantized(idx.packed, idx.corr, idx.centroid)
     for q in qs:
         _, _, alls, alld = O.search_nearest_neighbors(q, idx, 5, query_bits=qb, want_all=True)
@@ -185,7 +189,7 @@ def test_search_other_query_bits(bbq, qb):
     rows, qs = gaussian(18000, 128, 51), gaussian(4, 128, 52)
     for sim in SIMS:
         idx = O.quantize_vectors(rows, sim=sim, want_unpacked=False)
-        fmt = make_format(bbq, sim, qb=qb)
+        fmt = make_format(bbq, sim, qb=qb, popc_form="tile" if qb == 8 else None)
         qv = fmt.quantizeVectors(rows)["quantizedVectors"]
         _check_search(fmt, qv, idx, qs, 10, qb)
 
