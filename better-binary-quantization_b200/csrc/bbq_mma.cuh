@@ -153,6 +153,26 @@ __device__ __forceinline__ int tc_ld1(uint32_t taddr) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// packed fp32 pairs (Blackwell FFMA2 / FMUL2): two independent IEEE fp32 operations per instruction
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // no-swizzle K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
 // core matrix = 8 rows x 16 B contiguous; LBO = byte step between K-adjacent core matrices,
 // SBO = byte step between row-adjacent core matrices.
@@ -497,8 +517,12 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // layout: [B image n_tile*kbytes][QScreen n_tile][QueryTerms n_tile][barriers][tmem ptr]
   uint8_t* b_smem = smem_raw;
-  QScreen* qs_s = reinterpret_cast<QScreen*>(b_smem + (size_t)p.n_tile * p.kbytes);
-  bbqn::QueryTerms* qt_s = reinterpret_cast<bbqn::QueryTerms*>(qs_s + p.n_tile);
+  // per-pass screen constants, interleaved by query PAIR so that one LDS.128 feeds a packed FFMA2 operand pair:
+  //   qpa[j] = (ly8_2j, ly8_2j+1, aq_2j, aq_2j+1)   qpb[j] = (ay_2j, ay_2j+1, negl_2j, negl_2j+1)   qw[j] = wadj pair
+  float4* qpa_s = reinterpret_cast<float4*>(b_smem + (size_t)p.n_tile * p.kbytes);
+  float4* qpb_s = qpa_s + p.n_tile / 2;
+  float2* qw_s = reinterpret_cast<float2*>(qpb_s + p.n_tile / 2);
+  bbqn::QueryTerms* qt_s = reinterpret_cast<bbqn::QueryTerms*>(qw_s + p.n_tile / 2);  // DUMP mode only
   uint64_t* bars = reinterpret_cast<uint64_t*>(qt_s + p.n_tile);
   uint64_t* a_full = bars;            // [8]
   uint64_t* a_empty = bars + 8;       // [8]
@@ -728,8 +752,18 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
       const int q0 = pass * p.n_tile;
       const int nv = min(p.n_tile, p.nq - q0);
       for (int c = et; c < p.n_tile; c += MMA_EPI_WARPS * 32) {
-        if (MODE == SCAN_FILTER) qs_s[c] = p.qscreen[q0 + c];
-        if (c < nv) qt_s[c] = p.qterms[q0 + c];
+        if (MODE == SCAN_FILTER) {
+          const QScreen qs = p.qscreen[q0 + c];
+          float* pa = reinterpret_cast<float*>(qpa_s + (c >> 1));
+          float* pb = reinterpret_cast<float*>(qpb_s + (c >> 1));
+          float* pw = reinterpret_cast<float*>(qw_s + (c >> 1));
+          pa[c & 1] = qs.ly8;
+          pa[2 + (c & 1)] = qs.aq;
+          pb[c & 1] = qs.ay;
+          pb[2 + (c & 1)] = qs.negl;
+          pw[c & 1] = qs.wadj;
+        }
+        if (MODE == SCAN_DUMP && c < nv) qt_s[c] = p.qterms[q0 + c];
       }
       asm volatile("bar.sync 1, %0;" ::"n"(MMA_EPI_WARPS * 32) : "memory");
       auto row_of = [&](int64_t ti) { return (p.tile_first + ti * p.tile_stride) * TILE_ROWS + r; };
@@ -748,6 +782,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
         rs_next = load_rs(i + gridDim.x);
         const float rv = rs.x, x1f = rs.y, gv = rs.z, iv = rs.w;
         const bool always = valid && !(iv > 0.f);  // degenerate correctives: every pair goes to the exact replay
+        const uint64_t rv2 = f2_pack(rv, rv), x1f2 = f2_pack(x1f, x1f), gv2 = f2_pack(gv, gv), iv2 = f2_pack(iv, iv);
+        const uint64_t neg2 = f2_pack(-1.f, -1.f);
         // f64 correctives: issued now, consumed only by the (rare) exact replays, so their latency stays hidden
         RowTerms rt{0.0, 0.0, 0.0, 0u};
         if (MODE == SCAN_DUMP && valid) {
@@ -797,11 +833,24 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
             uint32_t mask = 0u;
             if (!(p.debug & 1u)) {
 #pragma unroll
-              for (int j = 0; j < 16; j++) {
-                const float4 a = *reinterpret_cast<const float4*>(&qs_s[c0 + j]);
-                float g = fmaf(a.x, (float)acc[j], fmaf(rv, a.y, fmaf(x1f, a.z, fmaf(a.w, iv, gv))));
-                if (SIM == bbqn::SIM_EUCLIDEAN) g = fminf(g, qs_s[c0 + j].wadj * iv - g);
-                if (g >= 0.f) mask |= (1u << j);
+              for (int j = 0; j < 8; j++) {  // two queries per step: 4 FFMA2 for the pair
+                const int pj = (c0 >> 1) + j;
+                const float4 qa = qpa_s[pj], qb = qpb_s[pj];
+                uint64_t t = f2_fma(f2_pack(qb.z, qb.w), iv2, gv2);
+                t = f2_fma(x1f2, f2_pack(qb.x, qb.y), t);
+                t = f2_fma(rv2, f2_pack(qa.z, qa.w), t);
+                const uint64_t f = f2_fma(f2_pack(qa.x, qa.y), f2_pack((float)acc[2 * j], (float)acc[2 * j + 1]), t);
+                float g0, g1;
+                f2_unpack(f, g0, g1);
+                if (SIM == bbqn::SIM_EUCLIDEAN) {
+                  const float2 w = qw_s[pj];
+                  float d0, d1;
+                  f2_unpack(f2_fma(f, neg2, f2_mul(f2_pack(w.x, w.y), iv2)), d0, d1);  // wadj * iv - f
+                  g0 = fminf(g0, d0);
+                  g1 = fminf(g1, d1);
+                }
+                if (g0 >= 0.f) mask |= (1u << (2 * j));
+                if (g1 >= 0.f) mask |= (1u << (2 * j + 1));
               }
             }
             if (always) mask = 0xFFFFu;
@@ -817,10 +866,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
           for (int j = 0; j < 16; j++) acc[j] = nxt[j];
           c0 = c1;
         }
-        if (refresh) {
-          float4* dst = reinterpret_cast<float4*>(qs_s + et);
-          dst[0] = fr0;
-          dst[1] = fr1;
+        if (refresh) {  // fr0 = (ly8, aq, ay, negl), fr1 = (wadj, tau, -, -) of query et
+          float* pb = reinterpret_cast<float*>(qpb_s + (et >> 1));
+          float* pw = reinterpret_cast<float*>(qw_s + (et >> 1));
+          pb[2 + (et & 1)] = fr0.w;
+          pw[et & 1] = fr1.x;
         }
         tc_fence_before();
         mbar_arrive(acc_empty + buf);
