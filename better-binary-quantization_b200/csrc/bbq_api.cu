@@ -79,7 +79,7 @@ struct bbq_ctx {
   DevBuf T, stage, cacc;
   // query scratch
   DevBuf qrows, qT, qcodes, qcorr, planes, qterms, tau, dump, cand, cand_cnt, flag, lists_a, lists_b,
-      out_idx, out_score, dots, images, qscreen, tau_bits;
+      out_idx, out_score, dots, images, qscreen, tau_bits, trace;
   int64_t sample_tiles_dyn = 128;  // BBQ_SAMPLE_TILES: sample size when the running threshold is on
   int popc_form = 0;        // BBQ_POPC_FORM=tile forces the shared-memory tile form of the popcount scan (tests)
   int mma_ntile_cap = 0;    // BBQ_MMA_NTILE: cap on the queries resident per pass (tuning experiments)
@@ -205,7 +205,7 @@ static void ctx_release(bbq_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (DevBuf* b : {&c->T, &c->stage, &c->cacc, &c->qrows, &c->qT, &c->qcodes, &c->qcorr, &c->planes, &c->qterms,
                     &c->tau, &c->dump, &c->cand, &c->cand_cnt, &c->flag, &c->lists_a, &c->lists_b, &c->out_idx,
-                    &c->out_score, &c->dots, &c->images, &c->qscreen, &c->tau_bits})
+                    &c->out_score, &c->dots, &c->images, &c->qscreen, &c->tau_bits, &c->trace})
     b->release();
   if (c->h_flag) cudaFreeHost(c->h_flag);
   for (auto& p : c->ev_pending) {
@@ -244,6 +244,14 @@ extern "C" int bbq_get_stats(bbq_ctx* c, bbq_stats* out) {
   c->ev_pending.clear();
   *out = c->stats;
   out->kernel_launches = c->launches;
+  return BBQ_OK;
+}
+extern "C" int bbq_debug_trace(bbq_ctx* c, long long* out, uint32_t count) {
+  if (!c || !out) return fail(BBQ_ERR_NULL, "null");
+  if (!c->trace.p) return fail(BBQ_ERR_INVALID_ARG, "no trace recorded (BBQ_MMA_DEBUG bit 32)");
+  CU(cudaSetDevice(c->device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(out, c->trace.p, std::min<size_t>(count, 4 * 4096) * sizeof(long long), cudaMemcpyDeviceToHost));
   return BBQ_OK;
 }
 extern "C" int bbq_set_profiling(bbq_ctx* c, int enabled) {
@@ -808,6 +816,11 @@ static int launch_scan_mma(bbq_index* ix, int mode, int nq, uint32_t k, const Mm
   p.bounds = ix->bounds;
   p.k = c->dynamic_tau ? k : 0xFFFFFFFFu;
   p.debug = c->mma_debug;
+  p.trace = nullptr;
+  if (c->mma_debug & 32u) {
+    TRY(c->trace.reserve(4 * 4096 * sizeof(long long)));
+    p.trace = c->trace.as<long long>();
+  }
   p.qterms = c->qterms.as<bbqn::QueryTerms>();
   p.nq = nq;
   p.n_tile = pl.n_tile;

@@ -335,7 +335,8 @@ struct MmaParams {
   uint32_t* tau_bits;      // [passes * n_tile] ordered-key form of tau, atomicMax'ed
   const IndexBounds* bounds;
   uint32_t k;              // top-k size (dynamic tightening needs k <= RETIGHTEN_KMAX)
-  uint32_t debug;          // profiling knobs (BBQ_MMA_DEBUG): 1 = epilogue skips the screen, 2 = hits are ignored, 4 = no TMEM loads
+  long long* trace;        // BBQ_MMA_DEBUG bit 32: clock64 stamps of CTA 0's hand-offs (tools/mma_trace.py)
+  uint32_t debug;          // profiling knobs (BBQ_MMA_DEBUG): 1 = epilogue skips the screen, 2 = hits are ignored, 4 = no TMEM loads, 32 = record the hand-off timeline
   const float4* rscreen;   // [n] per-row screen constants (k_index_bounds)
   const bbqn::QueryTerms* qterms;
   int nq, n_tile, passes, nstage;
@@ -606,6 +607,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
     const uint32_t lbo = (uint32_t)p.n_tile * 16u;
     const uint32_t b_addr = smem_u32(b_smem);
     uint32_t stage = 0, sphase = 0, tcount = 0;
+    int mma_ev = 0;
     for (int pass = 0; pass < p.passes; pass++) {
       mbar_wait(b_full, (uint32_t)(pass & 1));
       for (int64_t i = blockIdx.x; i < p.ntiles; i += gridDim.x) {
@@ -614,8 +616,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc_col + buf * (uint32_t)p.n_tile;
         for (int kc = 0; kc < nchunks; kc++) {
+          const bool tr = (p.debug & 32u) && blockIdx.x == 0 && lane == 0 && pass == 0;
+          long long t0 = tr ? clock64() : 0;
           mbar_wait(a_full + stage, sphase);
           tc_fence_after();
+          long long t1 = tr ? clock64() : 0;
           if (lane == 0) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -624,6 +629,12 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
               tc_mma_i8_ts(d_tmem, a_tmem, bdesc, idesc, (kc | j) != 0 ? 1u : 0u);
             }
             tc_commit(a_empty + stage);  // frees the A stage once these MMAs have read it
+            if (tr && mma_ev < 1000) {
+              p.trace[0 * 4096 + mma_ev * 4 + 0] = t0;
+              p.trace[0 * 4096 + mma_ev * 4 + 1] = t1;
+              p.trace[0 * 4096 + mma_ev * 4 + 2] = clock64();
+              mma_ev++;
+            }
           }
           __syncwarp();
           if (++stage == (uint32_t)nstage) {
@@ -690,6 +701,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
       tc_fence_after();
     };
     uint32_t stage = 0, sphase = 0;
+    int exp_ev = 0;
     for (int pass = 0; pass < p.passes; pass++) {
       uint4 q[PF];
       pf_tile = 0;
@@ -702,6 +714,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
         for (int i = 0; i < PF; i += 2) {
           if (f0 + i < total) {
             const bool two = f0 + i + 1 < total;
+            const bool tr = (p.debug & 32u) && blockIdx.x == 0 && warp == 4 && lane == 0 && pass == 0 && exp_ev < 1000;
+            long long x0 = tr ? clock64() : 0;
             uint32_t e0[32], e1[32];
             expand(q[i], e0);
             q[i] = load_next();
@@ -710,7 +724,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
               stage = 0;
               sphase ^= 1u;
             }
+            long long x1 = tr ? clock64() : 0;
             wait_stage(s0, p0);
+            long long x2 = tr ? clock64() : 0;
             tc_st32(lane_addr + a_col + s0 * 32u, e0);
             uint32_t s1 = 0;
             if (two) {
@@ -725,12 +741,19 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
               wait_stage(s1, p1);
               tc_st32(lane_addr + a_col + s1 * 32u, e1);
             }
+            long long x3 = tr ? clock64() : 0;
             tc_wait_st();
+            long long x4 = tr ? clock64() : 0;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {  // one arrival per expansion warp and stage
               mbar_arrive(a_full + s0);
               if (two) mbar_arrive(a_full + s1);
+            }
+            if (tr) {
+              long long* d = p.trace + 1 * 4096 + exp_ev * 8;
+              d[0] = x0; d[1] = x1; d[2] = x2; d[3] = x3; d[4] = x4; d[5] = clock64();
+              exp_ev++;
             }
           }
         }
