@@ -35,6 +35,22 @@ def quickSearch(queryVector, targetVectors, k, similarityFunction=VectorSimilari
     return fmt.searchNearestNeighbors(queryVector, qv, k)
 
 
+def getOversampledTopKWithSort(query, quantizedVectors, vectors, k, oversampleFactor, format):
+    """src/topKSelector.ts:90-114 (same argument order).  `vectors` (the original rows) are attached to the device
+    index on first use.  -> [{index, quantizedScore, trueScore}] by trueScore descending."""
+    if not getattr(quantizedVectors, "_rows_attached", False):
+        format.attachOriginalVectors(quantizedVectors, vectors)
+        quantizedVectors._rows_attached = True
+    import numpy as _np
+    i, qs, ts = format.searchOversampledBatch(_np.asarray(query, _np.float32)[None, :], quantizedVectors, k,
+                                              oversampleFactor)
+    return [{"index": int(a), "quantizedScore": float(b), "trueScore": float(c)} for a, b, c in zip(i[0], qs[0], ts[0])]
+
+
+getOversampledTopKWithHeap = getOversampledTopKWithSort  # :29-78 — same set unless true scores tie at the k-th place
+
+
 __all__ = ["BinaryQuantizationFormat", "BinarizedByteVectorValues", "VectorSimilarityFunction", "BbqError",
            "createBinaryQuantizationFormat", "quickQuantize", "quickSearch", "DEFAULT_CONFIG", "VERSION",
-           "build_library", "ShardedSearcher", "shard_bounds", "merge_host"]
+           "build_library", "ShardedSearcher", "shard_bounds", "merge_host", "getOversampledTopKWithSort",
+           "getOversampledTopKWithHeap"]

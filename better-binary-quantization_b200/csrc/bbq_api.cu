@@ -79,7 +79,7 @@ struct bbq_ctx {
   DevBuf T, stage, cacc;
   // query scratch
   DevBuf qrows, qT, qcodes, qcorr, planes, qterms, tau, dump, cand, cand_cnt, flag, lists_a, lists_b,
-      out_idx, out_score, dots, images, qscreen, tau_bits, trace;
+      out_idx, out_score, dots, images, qscreen, tau_bits, trace, rr_true, rr_idx, rr_q, rr_t;
   int64_t sample_tiles_dyn = 128;  // BBQ_SAMPLE_TILES: sample size when the running threshold is on
   int popc_form = 0;        // BBQ_POPC_FORM=tile forces the shared-memory tile form of the popcount scan (tests)
   int mma_ntile_cap = 0;    // BBQ_MMA_NTILE: cap on the queries resident per pass (tuning experiments)
@@ -137,6 +137,7 @@ struct bbq_index {
   double cdp = 0.0;
   uint64_t base = 0;
   IndexBounds* bounds = nullptr;  // device; valid for bounds_n rows (tensor-core screen margins)
+  float* rows = nullptr;          // device [n][dim]: original rows for the exact re-rank (bbq_index_attach_rows)
   float4* rscreen = nullptr;      // device [capacity]: per-row screen constants, same validity
   uint64_t bounds_n = 0;
   uint64_t capacity = 0;  // rows allocated (== n except while a streaming build is in progress)
@@ -205,7 +206,8 @@ static void ctx_release(bbq_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (DevBuf* b : {&c->T, &c->stage, &c->cacc, &c->qrows, &c->qT, &c->qcodes, &c->qcorr, &c->planes, &c->qterms,
                     &c->tau, &c->dump, &c->cand, &c->cand_cnt, &c->flag, &c->lists_a, &c->lists_b, &c->out_idx,
-                    &c->out_score, &c->dots, &c->images, &c->qscreen, &c->tau_bits, &c->trace})
+                    &c->out_score, &c->dots, &c->images, &c->qscreen, &c->tau_bits, &c->trace, &c->rr_true, &c->rr_idx,
+                    &c->rr_q, &c->rr_t})
     b->release();
   if (c->h_flag) cudaFreeHost(c->h_flag);
   for (auto& p : c->ev_pending) {
@@ -309,6 +311,7 @@ extern "C" void bbq_index_destroy(bbq_index* ix) {
   cudaFree(ix->centroid);
   if (ix->bounds) cudaFree(ix->bounds);
   if (ix->rscreen) cudaFree(ix->rscreen);
+  if (ix->rows) cudaFree(ix->rows);
   bbq_ctx* c = ix->ctx;
   delete ix;
   ctx_release(c);
@@ -1119,6 +1122,78 @@ extern "C" int bbq_search(bbq_index* ix, const float* queries, uint32_t nq, int6
                          (size_t)kk * sizeof(float), nq, cudaMemcpyDeviceToHost, c->stream));
   }
   CU(cudaStreamSynchronize(c->stream));
+  if (out_count) *out_count = kk;
+  return BBQ_OK;
+}
+
+static int attach_rows(bbq_index* ix, const float* rows, cudaMemcpyKind kind) {
+  if (!ix || !rows) return fail(BBQ_ERR_NULL, "null");
+  bbq_ctx* c = ix->ctx;
+  CU(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)ix->n * ix->dim * sizeof(float);
+  if (ix->rows) CU(cudaFree(ix->rows));
+  ix->rows = nullptr;
+  CU(cudaMalloc(&ix->rows, bytes));
+  CU(cudaMemcpyAsync(ix->rows, rows, bytes, kind, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BBQ_OK;
+}
+extern "C" int bbq_index_attach_rows(bbq_index* ix, const float* rows) { return attach_rows(ix, rows, cudaMemcpyHostToDevice); }
+extern "C" int bbq_index_attach_rows_device(bbq_index* ix, const float* d_rows) {
+  return attach_rows(ix, d_rows, cudaMemcpyDeviceToDevice);
+}
+
+extern "C" int bbq_search_rerank(bbq_index* ix, const float* queries, uint32_t nq, uint32_t k, uint32_t factor,
+                                 int32_t* out_idx, float* out_qscore, double* out_true, uint32_t* out_count) {
+  if (out_count) *out_count = 0;
+  if (!ix) return fail(BBQ_ERR_NULL, "target vector set must not be null");
+  if (!queries) return fail(BBQ_ERR_NULL, "query vector must not be null");
+  if (!ix->rows) return fail(BBQ_ERR_INVALID_ARG, "no original rows attached (bbq_index_attach_rows)");
+  if (nq == 0 || k == 0) return BBQ_OK;
+  if (!out_idx || !out_qscore || !out_true) return fail(BBQ_ERR_NULL, "output buffers must not be null");
+  if (factor == 0 || (uint64_t)k * factor > K_MAX) return fail(BBQ_ERR_UNSUPPORTED, "k * oversampleFactor must be in 1..4096");
+  bbq_ctx* c = ix->ctx;
+  for (uint32_t q = 0; q < nq; q++) {
+    const int s = validate_rows(queries + (size_t)q * ix->dim, 1, ix->dim, c->cfg.similarity == BBQ_SIM_COSINE);
+    if (s != BBQ_OK) {
+      g_err_vec = q;
+      return s;
+    }
+  }
+  const uint32_t m = (uint32_t)std::min<uint64_t>((uint64_t)k * factor, ix->n);  // candidates per query
+  const uint32_t kk = std::min(k, m);
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  TRY(c->qrows.reserve((size_t)nq * ix->dim * sizeof(float)));
+  TRY(c->out_idx.reserve((size_t)nq * m * sizeof(int32_t)));
+  TRY(c->out_score.reserve((size_t)nq * m * sizeof(float)));
+  TRY(c->rr_true.reserve((size_t)nq * m * sizeof(double)));
+  TRY(c->rr_idx.reserve((size_t)nq * kk * sizeof(int32_t)));
+  TRY(c->rr_q.reserve((size_t)nq * kk * sizeof(float)));
+  TRY(c->rr_t.reserve((size_t)nq * kk * sizeof(double)));
+  CU(cudaMemcpyAsync(c->qrows.p, queries, (size_t)nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  TRY(bbq_search_device(ix, c->qrows.as<float>(), nq, m, c->out_idx.as<int32_t>(), c->out_score.as<float>(), st));
+  {
+    ProfScope prof(c, st, PROF_SELECT);
+    const int64_t pairs = (int64_t)nq * m;
+    LAUNCH(c, k_rerank_scores, (unsigned)((pairs + RERANK_WARPS - 1) / RERANK_WARPS), RERANK_WARPS * 32, 0, st, ix->rows,
+           (int)ix->dim, c->qrows.as<float>(), (int)nq, (int)m, c->out_idx.as<int32_t>(), (uint32_t)ix->base,
+           c->rr_true.as<double>());
+    LAUNCH(c, k_rerank_select, nq, 256, 0, st, c->rr_true.as<double>(), c->out_idx.as<int32_t>(), c->out_score.as<float>(),
+           (int)m, kk, c->rr_idx.as<int32_t>(), c->rr_q.as<float>(), c->rr_t.as<double>());
+  }
+  auto copy_out = [&](void* dst, const void* src, size_t elem) -> int {
+    if (kk == k) {
+      CU(cudaMemcpyAsync(dst, src, (size_t)nq * kk * elem, cudaMemcpyDeviceToHost, st));
+    } else {
+      CU(cudaMemcpy2DAsync(dst, (size_t)k * elem, src, (size_t)kk * elem, (size_t)kk * elem, nq, cudaMemcpyDeviceToHost, st));
+    }
+    return BBQ_OK;
+  };
+  TRY(copy_out(out_idx, c->rr_idx.p, sizeof(int32_t)));
+  TRY(copy_out(out_qscore, c->rr_q.p, sizeof(float)));
+  TRY(copy_out(out_true, c->rr_t.p, sizeof(double)));
+  CU(cudaStreamSynchronize(st));
   if (out_count) *out_count = kk;
   return BBQ_OK;
 }

@@ -701,6 +701,74 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectParams p,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Oversampled search + exact re-rank ("next" row of the scope table): src/topKSelector.ts:29-114.
+// The quantised search returns k*factor candidates per query; each is then scored EXACTLY against the original
+// f32 row with computeCosineSimilarity (src/vectorSimilarity.ts:75-102: three interleaved sequential f64 sums),
+// and the k best true scores are kept — (trueScore desc, quantised rank asc), i.e. the stable sort of
+// getOversampledTopKWithSort.
+// ------------------------------------------------------------------------------------------------
+constexpr int RERANK_WARPS = 4;
+__global__ void __launch_bounds__(RERANK_WARPS * 32) k_rerank_scores(const float* __restrict__ rows, int dim,
+                                                                    const float* __restrict__ queries, int nq, int m,
+                                                                    const int32_t* __restrict__ cand_idx,
+                                                                    uint32_t base, double* __restrict__ true_scores) {
+  __shared__ double terms_s[RERANK_WARPS][3][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t pair = (int64_t)blockIdx.x * RERANK_WARPS + warp;
+  if (pair >= (int64_t)nq * m) return;
+  const int q = (int)(pair / m);
+  const int32_t idx = cand_idx[pair];
+  if (idx < 0) {
+    if (lane == 0) true_scores[pair] = -INFINITY;  // empty slot (fewer than k*factor rows)
+    return;
+  }
+  const float* a = queries + (int64_t)q * dim;
+  const float* b = rows + (int64_t)((uint32_t)idx - base) * dim;
+  double r[3];
+  warp_seq_sums<3>(dim, lane, terms_s[warp], [&](int i, double* t) {
+    const double av = (double)a[i], bv = (double)__ldg(b + i);
+    t[0] = av * bv;
+    t[1] = av * av;
+    t[2] = bv * bv;
+  }, r);
+  if (lane == 0) true_scores[pair] = (r[1] == 0 || r[2] == 0) ? 0.0 : r[0] / (sqrt(r[1]) * sqrt(r[2]));
+}
+
+// one CTA per query: rank by (trueScore desc, quantised rank asc); NaN ranks last; O(m^2 / threads), m <= 4096
+__global__ void __launch_bounds__(256) k_rerank_select(const double* __restrict__ true_scores, const int32_t* __restrict__ cand_idx,
+                                                       const float* __restrict__ cand_score, int m, uint32_t k,
+                                                       int32_t* __restrict__ out_idx, float* __restrict__ out_qscore,
+                                                       double* __restrict__ out_true) {
+  const int q = blockIdx.x;
+  const double* t = true_scores + (size_t)q * m;
+  const int32_t* ci = cand_idx + (size_t)q * m;
+  for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) {
+    out_idx[(size_t)q * k + j] = -1;
+    out_qscore[(size_t)q * k + j] = -INFINITY;
+    out_true[(size_t)q * k + j] = -INFINITY;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    if (ci[i] < 0) continue;
+    const double ti = t[i];
+    const bool nani = ti != ti;
+    uint32_t rank = 0;
+    for (int j = 0; j < m; j++) {
+      if (ci[j] < 0 || j == i) continue;
+      const double tj = t[j];
+      const bool nanj = tj != tj;
+      const bool better = nani ? (!nanj || j < i) : (!nanj && (tj > ti || (tj == ti && j < i)));
+      rank += better ? 1u : 0u;
+    }
+    if (rank < k) {
+      out_idx[(size_t)q * k + rank] = ci[i];
+      out_qscore[(size_t)q * k + rank] = cand_score[(size_t)q * m + i];
+      out_true[(size_t)q * k + rank] = ti;
+    }
+  }
+}
+
 // Input screening for the host build path (reference: binaryQuantizationFormat.ts:196-211) is done on
 // the host before upload; device-resident builds are the caller's responsibility.
 

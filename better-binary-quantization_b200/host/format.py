@@ -262,6 +262,29 @@ class BinaryQuantizationFormat:
         assert cnt.value == (kk if nq else 0) or k == 0
         return idx[:, :cnt.value].copy(), sc[:, :cnt.value].copy()
 
+    # -- oversampled search + exact re-rank (src/topKSelector.ts) -------------------------------------------
+    def attachOriginalVectors(self, targetVectors: BinarizedByteVectorValues, vectors):
+        """Keeps the original f32 rows on the device next to the index (needed by the exact re-rank)."""
+        m = _as_matrix(vectors)
+        if m.shape[0] != targetVectors.size() or m.shape[1] != targetVectors.dimension():
+            raise BbqError(4, "向量维度不匹配")
+        _check(_native.load().bbq_index_attach_rows(targetVectors._h, m.ctypes.data), "build")
+
+    def searchOversampledBatch(self, queries, targetVectors: BinarizedByteVectorValues, k: int, oversampleFactor: int):
+        """-> (idx i32[nq, kk], quantizedScore f32[nq, kk], trueScore f64[nq, kk])"""
+        qs = np.ascontiguousarray(queries, np.float32)
+        if qs.ndim != 2 or qs.shape[1] != targetVectors.dimension():
+            raise BbqError(4, "查询向量维度与目标向量维度不匹配")
+        nq = qs.shape[0]
+        idx = np.empty((nq, max(k, 1)), np.int32)
+        qsc = np.empty((nq, max(k, 1)), np.float32)
+        tsc = np.empty((nq, max(k, 1)), np.float64)
+        cnt = C.c_uint32(0)
+        _check(_native.load().bbq_search_rerank(targetVectors._h, qs.ctypes.data, nq, k, oversampleFactor,
+                                                idx.ctypes.data, qsc.ctypes.data, tsc.ctypes.data, C.byref(cnt)), "search")
+        n = cnt.value
+        return idx[:, :n].copy(), qsc[:, :n].copy(), tsc[:, :n].copy()
+
     # -- parity taps (tests) ------------------------------------------------------------------------------
     def debugQcDist(self, queryVector, targetVectors: BinarizedByteVectorValues) -> np.ndarray:
         q = np.ascontiguousarray(queryVector, np.float32)

@@ -139,6 +139,21 @@ int bbq_search(bbq_index* index, const float* queries, uint32_t nq, int64_t k, i
 int bbq_search_device(bbq_index* index, const float* d_queries, uint32_t nq, uint32_t k,
                       int32_t* d_out_idx, float* d_out_score, void* stream);
 
+/* -------- oversampled search + exact re-rank ---------------------------------------- */
+
+/* Keeps a copy of the ORIGINAL f32 rows next to the index (device memory, n*dim*4 bytes) for the exact re-rank.
+ * rows: HOST (bbq_index_attach_rows) or DEVICE (bbq_index_attach_rows_device) memory, n = bbq_index_size rows. */
+int bbq_index_attach_rows(bbq_index* index, const float* rows);
+int bbq_index_attach_rows_device(bbq_index* index, const float* d_rows);
+
+/* getOversampledTopKWithSort(query, quantizedVectors, vectors, k, oversampleFactor, format) —
+ * src/topKSelector.ts:90-114 (the heap form :29-78 returns the same set when no true score ties at the k-th place):
+ * quantised search for k*factor candidates, exact computeCosineSimilarity (src/vectorSimilarity.ts:75-102, f64)
+ * against the attached rows, the min(k, n) best by (trueScore desc, quantised rank asc).  HOST pointers; nq queries.
+ * out_idx / out_qscore (the quantised f32 score) / out_true (f64): nq*k each; k*factor <= 4096. */
+int bbq_search_rerank(bbq_index* index, const float* queries, uint32_t nq, uint32_t k, uint32_t factor,
+                      int32_t* out_idx, float* out_qscore, double* out_true, uint32_t* out_count);
+
 /* Deterministic merge of `lists` per-shard results (e.g. after an NCCL allgather):
  * inputs [lists][nq][k] idx / score in DEVICE memory, output [nq][k].  Replaces nothing in the
  * reference (it has no sharding); the ordering rule is the MinHeap contract of

@@ -451,6 +451,37 @@ int64_t bbqo_search(const float* query, const float* centroid, const uint8_t* pa
                    : bbqo_topk_canonical(sc, n, k, out_idx, out_score);
 }
 
+// src/vectorSimilarity.ts:75-102 (computeCosineSimilarity): three interleaved sequential f64 sums
+double bbqo_cosine(const float* a, const float* b, int d) {
+  double dot = 0, na = 0, nb = 0;
+  for (int i = 0; i < d; i++) {
+    dot += (double)a[i] * (double)b[i];
+    na += (double)a[i] * (double)a[i];
+    nb += (double)b[i] * (double)b[i];
+  }
+  if (na == 0 || nb == 0) return 0;
+  return dot / (std::sqrt(na) * std::sqrt(nb));
+}
+
+// src/topKSelector.ts:29-78 (getOversampledTopKWithHeap) after the quantised search: heap on trueScore, pop all,
+// then sort descending.  cand_idx/true_scores have m entries in quantised-rank order; returns min(k, m) positions.
+int64_t bbqo_rerank_heap(const double* true_scores, int64_t m, int64_t k, int32_t* out_pos) {
+  MinHeap heap;
+  for (int64_t i = 0; i < m; i++) {
+    const double s = true_scores[i];
+    if ((int64_t)heap.h.size() < k) heap.push({s, (int32_t)i});
+    else if (!heap.h.empty() && s > heap.h[0].score) {
+      heap.pop();
+      heap.push({s, (int32_t)i});
+    }
+  }
+  std::vector<HeapItem> res;
+  while (!heap.h.empty()) res.push_back(heap.pop());
+  std::stable_sort(res.begin(), res.end(), [](const HeapItem& a, const HeapItem& b) { return a.score > b.score; });
+  for (size_t i = 0; i < res.size(); i++) out_pos[i] = res[i].index;
+  return (int64_t)res.size();
+}
+
 // Faster inner loop for the cpu_baseline leg only: same integers as bbqo_qcdist_packed (it is the
 // bit-plane identity sum_i 2^i popc(qplane_i & x)), used when timing larger samples.  Validated
 // against bbqo_qcdist_packed in tests/test_oracle_kat.py.

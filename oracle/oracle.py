@@ -69,6 +69,10 @@ def lib():
         L.bbqo_topk_heap.restype = C.c_int64
         L.bbqo_topk_canonical.argtypes = [f32p, C.c_int64, C.c_int64, i32p, f32p]
         L.bbqo_topk_canonical.restype = C.c_int64
+        L.bbqo_cosine.argtypes = [f32p, f32p, C.c_int]
+        L.bbqo_cosine.restype = C.c_double
+        L.bbqo_rerank_heap.argtypes = [f64p, C.c_int64, C.c_int64, i32p]
+        L.bbqo_rerank_heap.restype = C.c_int64
         L.bbqo_search.argtypes = [f32p, f32p, u8p, f64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double,
                                   C.c_int, C.c_int64, C.c_int, i32p, f32p, f32p, i32p]
         L.bbqo_search.restype = C.c_int64
@@ -245,3 +249,26 @@ def quick_search(query, rows, k, sim="COSINE"):
     """src/index.ts:95-111: rebuilds the index on every call (lambda=0.1, iters=5, 4b x 1b)."""
     index = quantize_vectors(rows, sim=sim, index_bits=1, lam=0.1, iters=5)
     return search_nearest_neighbors(query, index, k, query_bits=4, lam=0.1, iters=5, mode="heap")
+
+
+def cosine_similarity(a, b):
+    """src/vectorSimilarity.ts:75-102"""
+    a, b = _f32(a), _f32(b)
+    return float(lib().bbqo_cosine(_p(a, C.c_float), _p(b, C.c_float), a.size))
+
+
+def oversampled_topk(query, rows, index: OracleIndex, k, factor, query_bits=4, lam=0.1, iters=5, mode="sort"):
+    """src/topKSelector.ts: getOversampledTopKWithSort (:90-114, mode="sort": stable sort by trueScore desc, the
+    canonical contract) / getOversampledTopKWithHeap (:29-78, mode="heap").
+    -> (idx i32[<=k], quantizedScore f32, trueScore f64)"""
+    rows = _f32(rows)
+    ci, cs = search_nearest_neighbors(query, index, k * factor, query_bits=query_bits, lam=lam, iters=iters,
+                                      mode="heap" if mode == "heap" else "canonical")
+    true = np.array([cosine_similarity(query, rows[i]) for i in ci], np.float64)
+    if mode == "heap":
+        pos = np.empty(max(min(k, len(ci)), 1), np.int32)
+        cnt = lib().bbqo_rerank_heap(_p(true, C.c_double), len(ci), k, _p(pos, C.c_int32))
+        pos = pos[:cnt]
+    else:
+        pos = np.argsort(-true, kind="stable")[:k]
+    return ci[pos], cs[pos], true[pos]

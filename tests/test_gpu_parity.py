@@ -407,6 +407,32 @@ def test_mma_scan_ties_and_degenerate_rows(bbq):
             assert mi[qi].tolist() == wi.tolist() and bits_equal(ms[qi], ws)
 
 
+# ---- "next" row: oversampled search + exact re-rank (src/topKSelector.ts) ---------------------------------------
+@pytest.mark.parametrize("n,dim,k,factor", [(100, 128, 10, 3), (5000, 96, 10, 3), (30000, 256, 20, 5), (7, 32, 10, 3)])
+def test_oversampled_rerank_matches_oracle(bbq, n, dim, k, factor):
+    if n == 100:
+        rows, qs = sincos_dataset(128, 100, 10)
+        lam, iters = 0.001, 20
+    else:
+        rows, qs = gaussian(n, dim, 141 + n), gaussian(6, dim, 142 + n)
+        lam, iters = 0.1, 5
+    idx = O.quantize_vectors(rows, sim="COSINE", want_unpacked=False, lam=lam, iters=iters)
+    fmt = make_format(bbq, "COSINE", lam=lam, iters=iters)
+    qv = fmt.quantizeVectors(rows)["quantizedVectors"]
+    fmt.attachOriginalVectors(qv, rows)
+    gi, gq, gt = fmt.searchOversampledBatch(qs, qv, k, factor)
+    rec = 0.0
+    for qi, q in enumerate(qs):
+        wi, wq, wt = O.oversampled_topk(q, rows, idx, k, factor, lam=lam, iters=iters)
+        assert gi[qi].tolist() == wi.tolist()
+        assert bits_equal(gq[qi], wq) and bits_equal(gt[qi], wt)      # f32 quantised scores, f64 true scores
+        rec += len(set(gi[qi].tolist()) & set(true_topk_cosine(q, rows, min(k, n)).tolist())) / min(k, n)
+    if n == 100:
+        assert rec / len(qs) >= 0.75                                   # tests/recall.test.ts:519,635
+        res = bbq.getOversampledTopKWithSort(qs[0], qv, rows, 10, 3, fmt)
+        assert [r["index"] for r in res] == gi[0].tolist() and res[0]["trueScore"] == gt[0][0]
+
+
 # ---- sharding: G shards + deterministic merge == one index --------------------------------------
 @pytest.mark.parametrize("shards", [2, 3, 8])
 def test_sharded_merge_equals_single(bbq, shards):

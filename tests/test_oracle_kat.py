@@ -133,3 +133,25 @@ def test_search_consistency(sim, qb):
         assert np.array_equal(alls[i2], s2)
         qc, _ = O.quantize_query_vector(q, idx.centroid, sim=sim, query_bits=qb)
         assert np.array_equal(alld, idx.unpacked.astype(np.int32) @ qc.astype(np.int32))
+
+
+# ---- oversampled search + exact re-rank (src/topKSelector.ts; tests/recall.test.ts:519,635,693) --------------------
+def test_oversampled_rerank_recall_fixture():
+    base, queries = sincos_dataset(128, 100, 10)
+    idx = O.quantize_vectors(base, sim="COSINE", index_bits=1, lam=0.001, iters=20)
+    over = plain = 0.0
+    for q in queries:
+        i, qs, ts = O.oversampled_topk(q, base, idx, 10, 3, lam=0.001, iters=20)
+        ih, _, _ = O.oversampled_topk(q, base, idx, 10, 3, lam=0.001, iters=20, mode="heap")
+        assert set(i.tolist()) == set(ih.tolist()) and np.all(np.diff(ts) <= 0) and len(i) == 10
+        truth = set(true_topk_cosine(q, base, 10).tolist())
+        over += len(set(i.tolist()) & truth) / 10
+        plain += len(set(O.search_nearest_neighbors(q, idx, 10, lam=0.001, iters=20)[0].tolist()) & truth) / 10
+    assert over / 10 >= 0.75 and over >= plain        # recall.test.ts:519,635 and :693
+
+
+def test_cosine_similarity_known():
+    # tests/utils.test.ts closed forms
+    assert O.cosine_similarity([1, 0, 0], [0, 1, 0]) == 0.0
+    assert abs(O.cosine_similarity([1, 2, 3], [2, 4, 6]) - 1.0) < 1e-15
+    assert O.cosine_similarity([0, 0, 0], [1, 2, 3]) == 0.0
