@@ -1022,6 +1022,8 @@ static int search_filtered(bbq_index* ix, int nq, uint32_t k, int32_t* d_out_idx
                nq, nq_pad, (double)ix->dim, ix->cdp, (int)c->cfg.similarity, c->cfg.query_bits == 1 ? 1 : 0, ix->bounds,
                c->qscreen.as<QScreen>(), c->tau_bits.as<uint32_t>());
       }
+      // the running threshold reads candidate slots that may be reserved but not yet written: they must read as 0
+      CU(cudaMemset2DAsync(p.cand, (size_t)CAND_CAP * sizeof(uint64_t), 0, (size_t)RETIGHTEN_ZCAP * sizeof(uint64_t), nq, st));
       TRY(launch_scan_mma(ix, SCAN_FILTER, nq, k, pl, 0, 1, ntiles, nullptr, 0, p.cand, cnt, CAND_CAP, cnt + nq, st));
     } else {
       TRY(launch_scan(ix, SCAN_FILTER, p, ntiles, st));

@@ -38,7 +38,7 @@ struct __align__(16) QScreen {
   float aq;     // A_q = ay * dim + ly * y1
   float ay;
   float negl;   // -(L - margin)
-  float wadj;   // EUCLIDEAN upper window (1/(2 tau) + 2 margin); +inf otherwise
+  float wadj;   // EUCLIDEAN: upper bound U + margin of (s - addx/2) — the pole 1+e = 0 — INDEPENDENT of tau; +inf otherwise
   float tau;
   float pad0, pad1;
 };
@@ -257,7 +257,7 @@ __global__ void k_index_bounds(const double* __restrict__ lower, const double* _
 //   EUCLIDEAN  (addq+1-1/tau)/2 <= s - addx/2 <  (addq+1)/2          (pole at 1+e = 0, clamp below it)
 //   COSINE     s + addx >= 2 tau - 1 - addq + cdp
 //   MIP        s + addx >= g(tau) - addq + cdp,  g = (tau-1)*S for tau >= 1 else (1-1/tau)*S,  S = 1/15 (1 if queryBits==1)
-// Dividing by lx > 0:  F = ly*dot + (ax/lx)*A_q + x1*ay + (c*addx)/lx - L/lx  >= 0  [and F <= W/lx].
+// Dividing by lx > 0:  F0 = ly*dot + (ax/lx)*A_q + x1*ay + (c*addx)/lx;  F0 - L/lx >= 0  [and F0 <= U/lx, U = L + W].
 // F is evaluated in fp32; `margin` (in s units) bounds every rounding in that chain and the f32 rounding
 // of the score itself, so the screen only ever errs towards admitting a pair to the exact f64 replay.
 __device__ __forceinline__ QScreen make_qscreen(const bbqn::QueryTerms& t, float tau, double dim, double cdp, int sim,
@@ -285,15 +285,19 @@ __device__ __forceinline__ QScreen make_qscreen(const bbqn::QueryTerms& t, float
     }
     const double eps = 1.0 / 16777216.0;  // 2^-24
     const double wv = (sim == bbqn::SIM_EUCLIDEAN) ? 0.5 * b.wv : b.wv;
-    const double margin = 32.0 * eps * ((double)b.lx * fabs(t.ly) * fabs(t.y1) + (double)b.ax * fabs(aq) +
-                                        (double)b.mv * fabs(t.ay) + wv + fabs(L)) +
-                          16.0 * eps * (fabs(L) + 1.0 + fabs(t.addq) + fabs(cdp) + fabs(W == INFINITY ? 0.0 : W));
-    if (bbqn::js_isfinite(margin) && bbqn::js_isfinite(L)) {
+    const double terms = (double)b.lx * fabs(t.ly) * fabs(t.y1) + (double)b.ax * fabs(aq) + (double)b.mv * fabs(t.ay) + wv;
+    const double margin = 32.0 * eps * (terms + fabs(L)) + 16.0 * eps * (fabs(L) + 1.0 + fabs(t.addq) + fabs(cdp));
+    // EUCLIDEAN upper bound: s - addx/2 < U = (addq + 1)/2 (= L + W for every tau).  It must NOT move with tau: the
+    // fields of a QScreen are re-published one by one while the scan runs, and an upper bound tied to a newer tau
+    // combined with a lower offset of an older one would cut off the pairs next to the pole — the best ones.
+    const double U = (t.addq + 1.0) / 2;
+    const double margin_u = 32.0 * eps * (terms + fabs(U)) + 16.0 * eps * (fabs(U) + 1.0 + fabs(t.addq));
+    if (bbqn::js_isfinite(margin) && bbqn::js_isfinite(L) && bbqn::js_isfinite(margin_u)) {
       s.ly8 = (float)(t.ly / 8);
       s.aq = (float)aq;
       s.ay = (float)t.ay;
       s.negl = __double2float_ru(-(L - margin));
-      s.wadj = (W == INFINITY) ? INFINITY : __double2float_ru(W + 2 * margin);
+      s.wadj = (W == INFINITY) ? INFINITY : __double2float_ru(U + margin_u);
     }
   }
   return s;
@@ -385,6 +389,7 @@ struct HitCtx {
 
 constexpr uint32_t RETIGHTEN_KMAX = 32;    // k up to which the running threshold is tightened inside the scan
 constexpr uint32_t RETIGHTEN_EVERY = 16;   // ... once per this many appended candidates of a query
+constexpr uint32_t RETIGHTEN_ZCAP = 4096;  // leading slots of every candidate list that the host zeroes before a scan
 constexpr uint32_t HIT_RING = 512;         // CTA-wide ring of parked hits (8 B each)
 
 // ---- hits: parked by the epilogue warps, replayed by a dedicated "drainer" warp -------------------------------
@@ -422,7 +427,10 @@ __device__ void mma_retighten_warp(const HitCtx* cx, int q, int lane) {  // whol
   uint32_t n = 0;
   if (lane == 0) n = min(*((volatile uint32_t*)(cx->cand_cnt + q)), cx->cap);
   n = __shfl_sync(0xffffffffu, n, 0);  // one read, so that every lane takes the same branches below
-  if (n < k) return;
+  // Only the zero-initialised prefix of the list may be read: a slot that has been reserved (count bumped) but not
+  // written yet must read as 0 = "absent".  A stale key there (e.g. the same row from the previous search) would be
+  // counted twice and push the bound ABOVE the true k-th best.
+  if (n < k || n > RETIGHTEN_ZCAP) return;
   const uint32_t first = n > 256u ? n - 256u : 0u;  // any subset gives a valid bound; the latest are the best
   const uint64_t* list = cx->cand + (size_t)q * cx->cap;
   uint64_t mine[8];
@@ -454,7 +462,6 @@ __device__ void mma_retighten_warp(const HitCtx* cx, int q, int lane) {  // whol
       QScreen* dst = cx->qscreen + q;
       if (s.ly8 == dst->ly8 && s.aq == dst->aq && s.ay == dst->ay) {  // same query terms: only the bounds move
         dst->negl = fminf(dst->negl, s.negl);
-        dst->wadj = fminf(dst->wadj, s.wadj);
         dst->tau = fmaxf(dst->tau, tnew);
       }
     }
@@ -821,12 +828,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
         const uint32_t d_addr = lane_addr + buf * (uint32_t)p.n_tile;
         // this tile's refresh of the (possibly tightened) screen constants: loads issued now, stored after the tile
         const bool refresh = MODE == SCAN_FILTER && p.k <= RETIGHTEN_KMAX && et < nv;
-        float4 fr0 = make_float4(0.f, 0.f, 0.f, 0.f), fr1 = fr0;
-        if (refresh) {
-          const float4* src = reinterpret_cast<const float4*>(p.qscreen + q0 + et);
-          fr0 = __ldcg(src);
-          fr1 = __ldcg(src + 1);
-        }
+        float4 fr0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (refresh) fr0 = __ldcg(reinterpret_cast<const float4*>(p.qscreen + q0 + et));
         // software pipeline over this warp's 16-column chunks: the next chunk's TMEM load is in flight while the
         // current one is screened
         int acc[16], nxt[16];
@@ -859,16 +862,16 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
               for (int j = 0; j < 8; j++) {  // two queries per step: 4 FFMA2 for the pair
                 const int pj = (c0 >> 1) + j;
                 const float4 qa = qpa_s[pj], qb = qpb_s[pj];
-                uint64_t t = f2_fma(f2_pack(qb.z, qb.w), iv2, gv2);
-                t = f2_fma(x1f2, f2_pack(qb.x, qb.y), t);
+                // f0 = (s + c*addx) / lx for the two queries; lower test: f0 + negl/lx >= 0; EUCLIDEAN upper: f0 <= wadj/lx
+                uint64_t t = f2_fma(x1f2, f2_pack(qb.x, qb.y), gv2);
                 t = f2_fma(rv2, f2_pack(qa.z, qa.w), t);
-                const uint64_t f = f2_fma(f2_pack(qa.x, qa.y), f2_pack((float)acc[2 * j], (float)acc[2 * j + 1]), t);
+                const uint64_t f0 = f2_fma(f2_pack(qa.x, qa.y), f2_pack((float)acc[2 * j], (float)acc[2 * j + 1]), t);
                 float g0, g1;
-                f2_unpack(f, g0, g1);
+                f2_unpack(f2_fma(f2_pack(qb.z, qb.w), iv2, f0), g0, g1);
                 if (SIM == bbqn::SIM_EUCLIDEAN) {
                   const float2 w = qw_s[pj];
                   float d0, d1;
-                  f2_unpack(f2_fma(f, neg2, f2_mul(f2_pack(w.x, w.y), iv2)), d0, d1);  // wadj * iv - f
+                  f2_unpack(f2_fma(f0, neg2, f2_mul(f2_pack(w.x, w.y), iv2)), d0, d1);  // wadj * iv - f0
                   g0 = fminf(g0, d0);
                   g1 = fminf(g1, d1);
                 }
@@ -889,11 +892,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
           for (int j = 0; j < 16; j++) acc[j] = nxt[j];
           c0 = c1;
         }
-        if (refresh) {  // fr0 = (ly8, aq, ay, negl), fr1 = (wadj, tau, -, -) of query et
+        if (refresh) {  // fr0 = (ly8, aq, ay, negl) of query et: only the lower offset moves with the threshold
           float* pb = reinterpret_cast<float*>(qpb_s + (et >> 1));
-          float* pw = reinterpret_cast<float*>(qw_s + (et >> 1));
           pb[2 + (et & 1)] = fr0.w;
-          pw[et & 1] = fr1.x;
         }
         tc_fence_before();
         mbar_arrive(acc_empty + buf);

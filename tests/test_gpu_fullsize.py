@@ -1,0 +1,119 @@
+"""BASELINE-size checks on the GPU (configs[2]: 1M x 1024, EUCLIDEAN, k=10, batch of 1024 queries; configs[1]:
+100k x 768, MIP, k=100, single query).  The oracle cannot rebuild or scan these whole in seconds, so parity is
+anchored on (a) oracle re-quantisation of SAMPLED rows of the device-built index, (b) full oracle searches of a few
+queries over the exported index, and (c) size-independent properties for every query: descending order, the
+(score desc, id asc) tie rule, scores that re-evaluate to the oracle's for the returned rows, agreement of the two
+scan engines and of sharded vs unsharded search, determinism."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.fixtures import gaussian
+from tests.test_gpu_parity import bits_equal, make_format
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def bbq():
+    import bbq_b200
+    bbq_b200.build_library()
+    return bbq_b200
+
+
+def _device_corpus(n, dim, seed):
+    import torch
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    return torch.randn((n, dim), generator=g, device="cuda", dtype=torch.float32)
+
+
+def test_c3_full_size_properties(bbq):
+    import torch
+    n, dim, k, nq, sim = 1_000_000, 1024, 10, 1024, "EUCLIDEAN"
+    rows_d = _device_corpus(n, dim, 20260101)
+    cen = np.zeros(dim, np.float32)
+    fm = make_format(bbq, sim, scan="mma")
+    fp = make_format(bbq, sim, scan="popc")
+    qm = fm.quantizeVectorsDevice(rows_d.data_ptr(), n, dim, centroid=cen)["quantizedVectors"]
+    assert qm.size() == n
+    # (a) sampled rows: device-built codes/correctives == oracle quantisation of the same f32 rows
+    sample = np.unique(np.concatenate([np.arange(0, 64), np.random.default_rng(1).integers(0, n, 1500), [n - 1]]))
+    rows_s = rows_d[torch.from_numpy(sample).cuda()].cpu().numpy()
+    want = O.quantize_vectors(rows_s, sim=sim, centroid=cen, want_unpacked=False)
+    for j, r in enumerate(sample[:: max(1, len(sample) // 400)]):
+        jj = int(np.searchsorted(sample, r))
+        p, c = qm._export(int(r), 1)
+        assert np.array_equal(p[0], want.packed[jj]) and bits_equal(c[0], want.corr[jj])
+    packed, corr = qm.exportAll()
+    del rows_d
+    torch.cuda.empty_cache()
+    oidx = O.OracleIndex(cen, packed, None, corr, dim, sim, 1)
+    qp = fp.adoptQuantized(packed, corr, cen)
+    qs = gaussian(nq, dim, 20260201)
+    # (c) the whole batch on the tensor-core engine; determinism
+    mi, ms = fm.searchBatch(qs, qm, k)
+    mi2, ms2 = fm.searchBatch(qs, qm, k)
+    assert np.array_equal(mi, mi2) and bits_equal(ms, ms2)
+    assert fm.stats()["last_engine"] == 2 and fm.stats()["last_overflow"] == 0
+    assert mi.shape == (nq, k) and np.all(mi >= 0) and np.all(mi < n)
+    assert np.all(np.diff(ms.astype(np.float64), axis=1) <= 0)                     # descending
+    ties = np.diff(ms, axis=1) == 0
+    assert np.all(np.diff(mi, axis=1)[ties] > 0)                                   # ties: lower id first
+    assert all(len(set(r.tolist())) == k for r in mi)                              # no row twice
+    # every returned score re-evaluates to the oracle's score for that (query, row)
+    for qi in range(0, nq, 64):
+        qc, qcorr = O.quantize_query_vector(qs[qi], cen, sim=sim)
+        sub = packed[mi[qi]]
+        dots = O.qcdist_packed(qc, sub, dim)
+        sc = O.batch_scores(dots, corr[mi[qi]], qcorr, dim, O.centroid_dp(cen), sim, 4)
+        assert bits_equal(sc, ms[qi])
+    # popcount engine on a slice of the batch: identical lists and scores
+    pi, ps = fp.searchBatch(qs[:48], qp, k)
+    assert np.array_equal(pi, mi[:48]) and bits_equal(ps, ms[:48])
+    # (b) full oracle searches (1M rows each) for a few queries
+    for qi in (0, 511, 1023):
+        wi, ws = O.search_nearest_neighbors(qs[qi], oidx, k, mode="canonical")
+        assert mi[qi].tolist() == wi.tolist() and bits_equal(ms[qi], ws)
+    # sharded (4 shards on this GPU) + deterministic merge == unsharded
+    L = bbq._native.load()
+    bounds = [bbq.shard_bounds(n, 4, r) for r in range(4)]
+    dq = torch.from_numpy(qs[:256]).cuda()
+    ai = torch.empty((4, 256, k), dtype=torch.int32, device="cuda")
+    asc = torch.empty((4, 256, k), dtype=torch.float32, device="cuda")
+    keep = []
+    for s, (a, b) in enumerate(bounds):
+        sh = fm.adoptQuantized(packed[a:b], corr[a:b], cen)
+        assert L.bbq_index_set_base(sh._h, a) == 0
+        fm.searchDevice(dq.data_ptr(), 256, sh, k, ai[s].data_ptr(), asc[s].data_ptr())
+        keep.append(sh)
+    torch.cuda.synchronize()
+    oi = torch.empty((256, k), dtype=torch.int32, device="cuda")
+    osc = torch.empty((256, k), dtype=torch.float32, device="cuda")
+    fm.mergeTopKDevice(ai.data_ptr(), asc.data_ptr(), 4, 256, k, oi.data_ptr(), osc.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(oi.cpu().numpy(), mi[:256]) and bits_equal(osc.cpu().numpy(), ms[:256])
+
+
+def test_c2_full_size_single_query(bbq):
+    n, dim, k, sim = 100_000, 768, 100, "MAXIMUM_INNER_PRODUCT"
+    rows = gaussian(n, dim, 20260102)
+    fmt = make_format(bbq, sim)
+    qv = fmt.quantizeVectors(rows)["quantizedVectors"]           # reference-order centroid on the device
+    want_c = O.compute_centroid(rows)
+    assert bits_equal(qv.getCentroid(), want_c)
+    packed, corr = qv.exportAll()
+    sample = np.random.default_rng(2).integers(0, n, 300)
+    for r in sample:
+        codes, c4 = O.scalar_quantize(rows[r], want_c, 1, sim)
+        assert np.array_equal(packed[r], O.pack_as_binary(codes)) and bits_equal(corr[r], c4)
+    oidx = O.OracleIndex(want_c, packed, None, corr, dim, sim, 1)
+    for q in gaussian(3, dim, 20260202):
+        res = fmt.searchNearestNeighbors(q, qv, k)
+        wi, ws = O.search_nearest_neighbors(q, oidx, k, mode="canonical")
+        hi, _ = O.search_nearest_neighbors(q, oidx, k, mode="heap")
+        assert [r["index"] for r in res] == wi.tolist()
+        assert bits_equal(np.array([r["score"] for r in res], np.float32), ws)
+        assert set(hi.tolist()) == set(wi.tolist())              # reference heap == canonical (no boundary tie)
