@@ -81,6 +81,8 @@ struct bbq_ctx {
   DevBuf qrows, qT, qcodes, qcorr, planes, qterms, tau, dump, cand, cand_cnt, flag, lists_a, lists_b,
       out_idx, out_score, dots, images, qscreen, tau_bits, trace, rr_true, rr_idx, rr_q, rr_t;
   int64_t sample_tiles_dyn = 128;  // BBQ_SAMPLE_TILES: sample size when the running threshold is on
+  int k1s_ctas = 4;         // BBQ_K1S_CTAS: persistent CTAs per SM of the streaming scan (huge = one tile per CTA)
+  int csa = 1;              // BBQ_CSA=0: plain popcount accumulation in the streaming scan (A/B, tests)
   int popc_form = 0;        // BBQ_POPC_FORM=tile forces the shared-memory tile form of the popcount scan (tests)
   int mma_ntile_cap = 0;    // BBQ_MMA_NTILE: cap on the queries resident per pass (tuning experiments)
   uint32_t mma_debug = 0;   // BBQ_MMA_DEBUG: timing-attribution knobs of the tensor-core scan (results become wrong)
@@ -190,6 +192,8 @@ extern "C" int bbq_create(const bbq_config* config, bbq_ctx** out_ctx) {
   CU(cudaMallocHost(&c->h_flag, (QUERY_BATCH + 1) * sizeof(uint32_t)));
   if (const char* e = getenv("BBQ_FORCE_PATH")) c->force_path = atoi(e);
   if (const char* e = getenv("BBQ_SAMPLE_TILES")) c->sample_tiles_dyn = std::max(1, std::min(128, atoi(e)));
+  if (const char* e = getenv("BBQ_CSA")) c->csa = atoi(e);
+  if (const char* e = getenv("BBQ_K1S_CTAS")) c->k1s_ctas = std::max(1, atoi(e));
   if (const char* e = getenv("BBQ_POPC_FORM")) c->popc_form = !strcmp(e, "tile") ? 1 : 0;
   if (const char* e = getenv("BBQ_MMA_NTILE")) c->mma_ntile_cap = atoi(e);
   if (const char* e = getenv("BBQ_MMA_DEBUG")) c->mma_debug = (uint32_t)atoi(e);
@@ -623,17 +627,21 @@ extern "C" int bbq_index_export(const bbq_index* ix, uint64_t first, uint64_t co
 template <int MODE>
 static int launch_scan_nb(bbq_ctx* c, int nb, bool stream_form, dim3 grid, size_t smem, cudaStream_t st,
                           const ScanParams& p) {
+#define BBQ_STREAM_LAUNCH(NB, MODE, W)                                                                             \
+  if (NB == 4 && c->csa) LAUNCH(c, (k_scan_stream<NB, MODE, W, NB == 4>), dim3(sgrid), TILE_ROWS, 0, st, p);       \
+  else LAUNCH(c, (k_scan_stream<NB, MODE, W, false>), dim3(sgrid), TILE_ROWS, 0, st, p)
 #define BBQ_SCAN_CASE(NB)                                                                                          \
   case NB:                                                                                                         \
     if (stream_form) {                                                                                             \
+      const unsigned sgrid = std::min<unsigned>(grid.x, (unsigned)c->sm_count * (unsigned)c->k1s_ctas);                             \
       switch (p.row_bytes >> 4) {                                                                                  \
-        case 1: LAUNCH(c, (k_scan_stream<NB, MODE, 1>), dim3(grid.x), TILE_ROWS, 0, st, p); break;                 \
-        case 2: LAUNCH(c, (k_scan_stream<NB, MODE, 2>), dim3(grid.x), TILE_ROWS, 0, st, p); break;                 \
-        case 3: LAUNCH(c, (k_scan_stream<NB, MODE, 3>), dim3(grid.x), TILE_ROWS, 0, st, p); break;                 \
-        case 4: LAUNCH(c, (k_scan_stream<NB, MODE, 4>), dim3(grid.x), TILE_ROWS, 0, st, p); break;                 \
-        case 6: LAUNCH(c, (k_scan_stream<NB, MODE, 6>), dim3(grid.x), TILE_ROWS, 0, st, p); break;                 \
-        case 8: LAUNCH(c, (k_scan_stream<NB, MODE, 8>), dim3(grid.x), TILE_ROWS, 0, st, p); break;                 \
-        case 12: LAUNCH(c, (k_scan_stream<NB, MODE, 12>), dim3(grid.x), TILE_ROWS, 0, st, p); break;               \
+        case 1: BBQ_STREAM_LAUNCH(NB, MODE, 1); break;                                                            \
+        case 2: BBQ_STREAM_LAUNCH(NB, MODE, 2); break;                                                            \
+        case 3: BBQ_STREAM_LAUNCH(NB, MODE, 3); break;                                                            \
+        case 4: BBQ_STREAM_LAUNCH(NB, MODE, 4); break;                                                            \
+        case 6: BBQ_STREAM_LAUNCH(NB, MODE, 6); break;                                                            \
+        case 8: BBQ_STREAM_LAUNCH(NB, MODE, 8); break;                                                            \
+        case 12: BBQ_STREAM_LAUNCH(NB, MODE, 12); break;                                                            \
         default: return fail(BBQ_ERR_UNSUPPORTED, "no streaming scan for this row size");                          \
       }                                                                                                            \
     } else {                                                                                                       \
@@ -655,6 +663,7 @@ static int launch_scan_nb(bbq_ctx* c, int nb, bool stream_form, dim3 grid, size_
       return fail(BBQ_ERR_QUERY_BITS, "queryBits must be in 1..8");
   }
 #undef BBQ_SCAN_CASE
+#undef BBQ_STREAM_LAUNCH
   return BBQ_OK;
 }
 
@@ -675,6 +684,7 @@ static int launch_scan(bbq_index* ix, int mode, ScanParams p, int64_t ntiles, cu
   ProfScope prof(c, st, is_sample ? PROF_SAMPLE : PROF_SCAN);
   if (!is_sample) c->stats.scan_launches++;
   dim3 grid((unsigned)ntiles, (unsigned)((p.nq + qb - 1) / qb));
+  p.ntiles = ntiles;
   // one or a few queries: the streaming (register/shuffle, HBM-bound) form; it needs >= 2 rows per 512-byte load
   const bool stream_ok = w4 == 1 || w4 == 2 || w4 == 3 || w4 == 4 || w4 == 6 || w4 == 8 || w4 == 12;  // dims 128..1536
   const bool stream_form = c->popc_form != 1 && p.nq <= 4 && stream_ok;

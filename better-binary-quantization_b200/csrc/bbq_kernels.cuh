@@ -422,6 +422,7 @@ struct ScanParams {
   double cdp;
   int sim;
   int one_bit_query;
+  int64_t ntiles;         // k_scan_stream (persistent): number of tiles to cover
   uint32_t base;          // global id of row 0
   // tile mapping: CTA x handles tile (tile_first + blockIdx.x * tile_stride)
   int64_t tile_first;
@@ -518,81 +519,177 @@ __global__ void __launch_bounds__(TILE_ROWS) k_scan(const ScanParams p) {
   }
 }
 
+
+// Carry-save form of sum_b 2^b * popc(x & plane_b) over one 16-byte chunk and four query bit-planes: the 16 masks
+// are added as bit-vectors (full adder = 2 LOP3) plane by plane, carries moving up one weight, so 6 POPC (weights
+// 1..32) replace 16.  The scan is bound by the quarter-rate POPC pipe otherwise.  Same integer.
+__device__ __forceinline__ void csa_fa(uint32_t a, uint32_t b, uint32_t c, uint32_t& s, uint32_t& k) {
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s) : "r"(a), "r"(b), "r"(c));
+  asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(k) : "r"(a), "r"(b), "r"(c));
+}
+__device__ __forceinline__ int csa_dot4(const uint4 x, const uint4 p0, const uint4 p1, const uint4 p2, const uint4 p3) {
+  uint32_t s, t, o1, o2, o4, o8, o16, o32, k1a, k1b, k2a, k2b, k2c, k4a, k4b, k4c, k8a, k8b, k8c;
+  csa_fa(x.x & p0.x, x.y & p0.y, x.z & p0.z, s, k1a);
+  {  // half adder with the raw fourth mask: sum = s ^ (x & p), carry = s & x & p — one LOP3 each
+    asm("lop3.b32 %0, %1, %2, %3, 0x78;" : "=r"(o1) : "r"(s), "r"(x.w), "r"(p0.w));   // a ^ (b & c)
+    asm("lop3.b32 %0, %1, %2, %3, 0x80;" : "=r"(k1b) : "r"(s), "r"(x.w), "r"(p0.w));  // a & b & c
+  }
+  csa_fa(x.x & p1.x, x.y & p1.y, x.z & p1.z, s, k2a);
+  csa_fa(x.w & p1.w, k1a, k1b, t, k2b);
+  o2 = s ^ t;
+  k2c = s & t;
+  csa_fa(x.x & p2.x, x.y & p2.y, x.z & p2.z, s, k4a);
+  csa_fa(x.w & p2.w, k2a, k2b, t, k4b);
+  csa_fa(s, t, k2c, o4, k4c);
+  csa_fa(x.x & p3.x, x.y & p3.y, x.z & p3.z, s, k8a);
+  csa_fa(x.w & p3.w, k4a, k4b, t, k8b);
+  csa_fa(s, t, k4c, o8, k8c);
+  csa_fa(k8a, k8b, k8c, o16, o32);
+  return __popc(o1) + 2 * __popc(o2) + 4 * __popc(o4) + 8 * __popc(o8) + 16 * __popc(o16) + 32 * __popc(o32);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1s: the streaming form of the scan for ONE (or a few) queries — the HBM-bound regime.  No shared memory:
-// a warp reads its 32 rows as a flat stream of 16-byte chunks (32 lanes x 16 B = 512 contiguous bytes per load,
-// all loads of the 32 rows in flight before the first is used), the query's bit-planes for a lane's fixed
-// 128-dim segment sit in registers, partial popcount sums are reduced across the lanes that share a row, and
-// the exact f64 epilogue then runs with one row per lane (coalesced corrective loads, no divergence).
+// persistent warps walk 32-row units (4 KB of codes at D=1024); a lane loads 16 bytes of a row per instruction
+// (fully coalesced) and the NEXT unit's loads are issued before the current one is reduced, so every warp always
+// has a unit in flight.  The query's bit-planes for a lane's fixed 128-dim segment sit in registers, the partial
+// dots of the lanes that share a row are combined by a butterfly exchange (power-of-two rows: w4-1 shuffles
+// per unit) and the exact f64 epilogue then runs with one row per lane.
 // Same integers, same scores, same outputs as k_scan; tiles/dump layout identical.
-template <int NB, int MODE, int W4>
-__global__ void __launch_bounds__(TILE_ROWS) k_scan_stream(const ScanParams p) {
+// ------------------------------------------------------------------------------------------------
+template <int NB, int MODE, int W4, bool CSA>
+__global__ void __launch_bounds__(TILE_ROWS, 4) k_scan_stream(const ScanParams p) {
   constexpr int w4 = W4;                  // 16-byte chunks per row (compile-time: 1..16)
   constexpr int R = 32 / w4;              // rows per load instruction
   constexpr int iters = (32 + R - 1) / R; // load instructions per 32-row unit
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr bool POW2 = (w4 & (w4 - 1)) == 0;  // then iters == w4 and the butterfly applies
+  const int lane = threadIdx.x & 31;
   const int seg = lane % w4, grp = lane / w4;      // this lane's segment of a row / which row of the instruction
   const bool lane_on = lane < R * w4;
-  const int64_t tile = p.tile_first + (int64_t)blockIdx.x * p.tile_stride;
-  const int64_t unit_row0 = tile * TILE_ROWS + warp * 32;  // first row of this warp's unit
+  // row (within the unit) whose dot this lane holds after the reduction, hence the row of its epilogue
+  const int out_rl = POW2 ? seg * R + grp : lane;
+  const int src_lane = (lane % R) * w4;            // !POW2: leader lane of the group that held this lane's row
+  const int64_t nunits = p.ntiles * (TILE_ROWS / 32);
+  const int64_t ustride = (int64_t)gridDim.x * (TILE_ROWS / 32);
+  int64_t u = (int64_t)blockIdx.x * (TILE_ROWS / 32) + (threadIdx.x >> 5);
 
-  // all loads of the unit first (memory-level parallelism), zero for rows past the end
-  uint4 x[iters];
-#pragma unroll
-  for (int it = 0; it < iters; it++) {
-    x[it] = make_uint4(0u, 0u, 0u, 0u);
-    const int rl = it * R + grp;  // row within the unit
-    const int64_t row = unit_row0 + rl;
-    if (lane_on && rl < 32 && row < p.n)
-      x[it] = __ldg(reinterpret_cast<const uint4*>(p.codes + row * (int64_t)p.row_bytes) + seg);
+  auto unit_row0 = [&](int64_t uu) -> int64_t {
+    return (p.tile_first + (uu >> 2) * p.tile_stride) * TILE_ROWS + (uu & 3) * 32;
+  };
+  // query-side constants live in shared memory: inside the unit loop the ONLY global loads are the prefetches, so
+  // nothing else waits on the scoreboard they occupy (a predicated-off plane reload there cost 20% of the kernel)
+  constexpr int QMAX = 4;
+  __shared__ uint4 planes_s[QMAX * NB * w4];
+  __shared__ bbqn::QueryTerms qt_s[QMAX];
+  __shared__ float tau_s[QMAX];
+  for (int i = threadIdx.x; i < p.nq * NB * w4; i += TILE_ROWS) planes_s[i] = __ldg(reinterpret_cast<const uint4*>(p.planes) + i);
+  if (threadIdx.x < p.nq) {
+    qt_s[threadIdx.x] = p.qterms[threadIdx.x];
+    tau_s[threadIdx.x] = MODE == SCAN_FILTER ? p.tau[threadIdx.x] : 0.f;
   }
-  const int64_t my_row = unit_row0 + lane;  // epilogue: one row per lane
-  const bool valid = my_row < p.n;
-  double ax = 0, lx = 0, addx = 0, x1 = 0;
-  if (valid) {
-    ax = __ldg(p.lower + my_row);
-    lx = __ldg(p.upper + my_row) - ax;
-    addx = __ldg(p.addc + my_row);
-    x1 = (double)__ldg(p.compsum + my_row);
-  }
-  const uint32_t id = p.base + (uint32_t)my_row;
-  const int src_lane = (lane % R) * w4;  // leader lane of the group that held this lane's row
-  for (int q = 0; q < p.nq; q++) {
-    uint4 pl[NB];
-    const uint4* psrc = reinterpret_cast<const uint4*>(p.planes) + (size_t)q * NB * w4;
+  __syncthreads();
+  if (u >= nunits) return;
+  uint4 pl[NB];
 #pragma unroll
-    for (int b = 0; b < NB; b++) pl[b] = lane_on ? __ldg(psrc + b * w4 + seg) : make_uint4(0u, 0u, 0u, 0u);
-    int mydot = 0;
+  for (int b = 0; b < NB; b++) pl[b] = lane_on ? planes_s[b * w4 + seg] : make_uint4(0u, 0u, 0u, 0u);
+
+  uint4 x[iters], xn[iters];
+  double lo_n = 0, up_n = 0, add_n = 0;
+  uint32_t cs_n = 0;
+  auto fetch = [&](int64_t uu) {
+    const int64_t r0 = unit_row0(uu);
 #pragma unroll
     for (int it = 0; it < iters; it++) {
-      int part = 0;
+      xn[it] = make_uint4(0u, 0u, 0u, 0u);
+      const int rl = it * R + grp;  // row within the unit
+      const int64_t row = r0 + rl;
+      if (lane_on && rl < 32 && row < p.n)
+        xn[it] = __ldg(reinterpret_cast<const uint4*>(p.codes + row * (int64_t)p.row_bytes) + seg);
+    }
+    const int64_t er = r0 + out_rl;
+    lo_n = up_n = add_n = 0;
+    cs_n = 0;
+    if (er < p.n) {
+      lo_n = __ldg(p.lower + er);
+      up_n = __ldg(p.upper + er);
+      add_n = __ldg(p.addc + er);
+      cs_n = __ldg(p.compsum + er);
+    }
+  };
+  fetch(u);
+  for (; u < nunits; u += ustride) {
 #pragma unroll
-      for (int b = 0; b < NB; b++) {
-        const int c = __popc(x[it].x & pl[b].x) + __popc(x[it].y & pl[b].y) + __popc(x[it].z & pl[b].z) +
-                      __popc(x[it].w & pl[b].w);
-        part += c << b;
+    for (int it = 0; it < iters; it++) x[it] = xn[it];
+    const double ax = lo_n, lx = up_n - lo_n, addx = add_n, x1 = (double)cs_n;
+    const int64_t my_row = unit_row0(u) + out_rl;
+    const bool valid = my_row < p.n;
+    if (u + ustride < nunits) fetch(u + ustride);  // next unit in flight while this one is reduced
+
+    const uint32_t id = p.base + (uint32_t)my_row;
+    for (int q = 0; q < p.nq; q++) {
+      if (p.nq > 1) {
+        const uint4* psrc = planes_s + q * NB * w4;
+#pragma unroll
+        for (int b = 0; b < NB; b++) pl[b] = lane_on ? psrc[b * w4 + seg] : make_uint4(0u, 0u, 0u, 0u);
       }
-      // sum over the w4 lanes of a row (lanes of a row are contiguous; w4 need not be a power of two)
+      int part[iters];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        if (o < w4) {
-          const int other = __shfl_down_sync(0xffffffffu, part, o);
-          if (seg + o < w4) part += other;
+      for (int it = 0; it < iters; it++) {
+        if (NB == 4 && CSA) {
+          part[it] = csa_dot4(x[it], pl[0], pl[1 % NB], pl[2 % NB], pl[3 % NB]);
+        } else {
+          int acc = 0;
+#pragma unroll
+          for (int b = 0; b < NB; b++) {
+            const int c = __popc(x[it].x & pl[b].x) + __popc(x[it].y & pl[b].y) + __popc(x[it].z & pl[b].z) +
+                          __popc(x[it].w & pl[b].w);
+            acc += c << b;
+          }
+          part[it] = acc;
         }
       }
-      const int got = __shfl_sync(0xffffffffu, part, src_lane);
-      if (lane / R == it) mydot = got;  // row (it*R + lane%R) == lane
-    }
-    const bbqn::QueryTerms qt = p.qterms[q];
-    const float score = bbqn::score_f32((double)mydot, ax, lx, addx, x1, qt, p.dim, p.cdp, p.sim, p.one_bit_query != 0);
-    if (MODE == SCAN_DUMP) {
-      if (valid) {
-        p.dump[(int64_t)q * p.dump_ld + (int64_t)blockIdx.x * TILE_ROWS + warp * 32 + lane] = score;
-        if (p.dots != nullptr && q == 0) p.dots[my_row] = mydot;
+      int mydot = 0;
+      if (POW2) {
+        // butterfly: at distance s a lane keeps half of its values (the upper half iff seg & s) and receives the
+        // partner's partial sums of the same rows; after log2(w4) steps part[0] is the dot of row seg*R + grp
+#pragma unroll
+        for (int s = w4 / 2; s > 0; s >>= 1) {
+          const bool hi = (seg & s) != 0;
+#pragma unroll
+          for (int j = 0; j < s; j++) {
+            const int a = part[j], b = part[j + s];
+            const int send = hi ? a : b, keep = hi ? b : a;
+            part[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+          }
+        }
+        mydot = part[0];
+      } else {
+#pragma unroll
+        for (int it = 0; it < iters; it++) {
+          int v = part[it];
+          // sum over the w4 lanes of a row (lanes of a row are contiguous)
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            if (o < w4) {
+              const int other = __shfl_down_sync(0xffffffffu, v, o);
+              if (seg + o < w4) v += other;
+            }
+          }
+          const int got = __shfl_sync(0xffffffffu, v, src_lane);
+          if (lane / R == it) mydot = got;  // row (it*R + lane%R) == lane
+        }
       }
-    } else if (valid && score >= p.tau[q]) {
-      const uint32_t pos = atomicAdd(p.cand_cnt + q, 1u);
-      if (pos < p.cap) p.cand[(size_t)q * p.cap + pos] = bbqn::topk_key(score, id);
-      else *p.overflow = 1u;
+      const float score = bbqn::score_f32((double)mydot, ax, lx, addx, x1, qt_s[q], p.dim, p.cdp, p.sim, p.one_bit_query != 0);
+      if (MODE == SCAN_DUMP) {
+        if (valid) {
+          p.dump[(int64_t)q * p.dump_ld + (u >> 2) * TILE_ROWS + (u & 3) * 32 + out_rl] = score;
+          if (p.dots != nullptr && q == 0) p.dots[my_row] = mydot;
+        }
+      } else if (valid && score >= tau_s[q]) {
+        const uint32_t pos = atomicAdd(p.cand_cnt + q, 1u);
+        if (pos < p.cap) p.cand[(size_t)q * p.cap + pos] = bbqn::topk_key(score, id);
+        else *p.overflow = 1u;
+      }
     }
   }
 }
