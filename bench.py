@@ -314,7 +314,8 @@ def run_gpu(args, w, rank, world, local_rank):
     else:
         roofline = {"bound": "hbm", "achieved": index_gbps, "peak": hbm_peak, "unit": "GB/s",
                     "frac": index_gbps / hbm_peak, "traffic": None, "peak_source": peak_src,
-                    "kernel": "bbqk::k_scan<NB,SCAN_FILTER>", "algorithmic_bytes_per_launch": algo_bytes}
+                    "kernel": ("bbqk::k_scan_stream<NB,SCAN_FILTER,W4,CSA>" if nq <= 4 else "bbqk::k_scan<NB,SCAN_FILTER>"),
+                    "algorithmic_bytes_per_launch": algo_bytes}
     roofline.update({"avg_scan_launch_ms": scan_launch_ms, "scan_ms_per_step": scan_ms_step,
                      "scan_launches_per_step": st["scan_launches"] / args.steps,
                      "sample_ms_per_step": st["sample_ms"] / args.steps,
@@ -322,6 +323,7 @@ def run_gpu(args, w, rank, world, local_rank):
                      "select_ms_per_step": st["select_ms"] / args.steps,
                      "query_effective_GBps": (nq * algo_bytes / (scan_ms_step * 1e-3) / 1e9) if scan_ms_step > 0 else 0.0,
                      "scan_engine": engine})
+    roofline["traffic"], roofline["traffic_source"] = load_traffic(args.workload, nq, world, roofline["kernel"])
     peak = hbm_peak
     achieved = index_gbps
 
@@ -375,6 +377,20 @@ def run_gpu(args, w, rank, world, local_rank):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def load_traffic(workload, nq, world, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this same command (profiles/traffic.json names the capture); None when the run is not
+    the captured configuration (other query count, sharded corpus)."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except OSError:
+        return None, None
+    for e in table.get("captures", []):
+        if e["workload"] == workload and e["queries_per_step"] == nq and world == 1 and e["kernel"] in kernel:
+            return e["dram_bytes_per_launch"], e["source"]
+    return None, None
 
 
 def main():
