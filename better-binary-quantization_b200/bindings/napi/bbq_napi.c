@@ -168,11 +168,98 @@ static napi_value n_rows(napi_env env, napi_callback_info info) {
   return out;
 }
 
+/* attachRows(index, rowsFlat Float32Array[n*dim]) — keeps the original rows on the device for the exact re-rank */
+static napi_value n_attach_rows(napi_env env, napi_callback_info info) {
+  ARGS(2);
+  void* ix;
+  const float* rows;
+  size_t len;
+  napi_get_value_external(env, argv[0], &ix);
+  if (!get_f32(env, argv[1], &rows, &len)) return throw_status(env, BBQ_ERR_NULL);
+  if (len != (size_t)bbq_index_size((bbq_index*)ix) * bbq_index_dim((bbq_index*)ix)) return throw_status(env, BBQ_ERR_DIM_MISMATCH);
+  const int st = bbq_index_attach_rows((bbq_index*)ix, rows);
+  if (st != BBQ_OK) return throw_status(env, st);
+  napi_value u;
+  napi_get_undefined(env, &u);
+  return u;
+}
+
+/* searchRerank(index, queriesFlat, nq, k, oversampleFactor) -> {indices, quantizedScores, trueScores, count}
+ * replaces getOversampledTopKWithSort / getOversampledTopKWithHeap, src/topKSelector.ts:29-114 */
+static napi_value n_search_rerank(napi_env env, napi_callback_info info) {
+  ARGS(5);
+  void* ix;
+  const float* q;
+  size_t len;
+  uint32_t nq, k, factor, count = 0;
+  napi_get_value_external(env, argv[0], &ix);
+  if (!get_f32(env, argv[1], &q, &len)) return throw_status(env, BBQ_ERR_NULL);
+  napi_get_value_uint32(env, argv[2], &nq);
+  napi_get_value_uint32(env, argv[3], &k);
+  napi_get_value_uint32(env, argv[4], &factor);
+  if (len != (size_t)nq * bbq_index_dim((bbq_index*)ix)) return throw_status(env, BBQ_ERR_DIM_MISMATCH);
+  const size_t slots = (size_t)nq * k;
+  napi_value out, a1, a2, a3, t1, t2, t3, v;
+  void *p1, *p2, *p3;
+  napi_create_arraybuffer(env, (slots ? slots : 1) * sizeof(int32_t), &p1, &a1);
+  napi_create_arraybuffer(env, (slots ? slots : 1) * sizeof(float), &p2, &a2);
+  napi_create_arraybuffer(env, (slots ? slots : 1) * sizeof(double), &p3, &a3);
+  const int st = bbq_search_rerank((bbq_index*)ix, q, nq, k, factor, (int32_t*)p1, (float*)p2, (double*)p3, &count);
+  if (st != BBQ_OK) return throw_status(env, st);
+  napi_create_typedarray(env, napi_int32_array, slots, a1, 0, &t1);
+  napi_create_typedarray(env, napi_float32_array, slots, a2, 0, &t2);
+  napi_create_typedarray(env, napi_float64_array, slots, a3, 0, &t3);
+  napi_create_object(env, &out);
+  napi_set_named_property(env, out, "indices", t1);
+  napi_set_named_property(env, out, "quantizedScores", t2);
+  napi_set_named_property(env, out, "trueScores", t3);
+  napi_create_uint32(env, count, &v);
+  napi_set_named_property(env, out, "count", v);
+  return out;
+}
+
+static int get_path(napi_env env, napi_value v, char* buf, size_t cap) {
+  size_t n = 0;
+  return napi_get_value_string_utf8(env, v, buf, cap, &n) == napi_ok && n + 1 < cap;
+}
+
+/* saveIndex(index, vebPath, vembPath) / loadIndex(ctx, vebPath, vembPath) -> external index
+ * the on-disk form of serializeVectorData / deserializeVectorData, src/binaryQuantizationFormat.ts:483-560 */
+static napi_value n_save_index(napi_env env, napi_callback_info info) {
+  ARGS(3);
+  void* ix;
+  char veb[4096], vemb[4096];
+  napi_get_value_external(env, argv[0], &ix);
+  if (!get_path(env, argv[1], veb, sizeof veb) || !get_path(env, argv[2], vemb, sizeof vemb)) return throw_status(env, BBQ_ERR_NULL);
+  const int st = bbq_index_save((bbq_index*)ix, veb, vemb);
+  if (st != BBQ_OK) return throw_status(env, st);
+  napi_value u;
+  napi_get_undefined(env, &u);
+  return u;
+}
+static napi_value n_load_index(napi_env env, napi_callback_info info) {
+  ARGS(3);
+  void* ctx;
+  char veb[4096], vemb[4096];
+  napi_get_value_external(env, argv[0], &ctx);
+  if (!get_path(env, argv[1], veb, sizeof veb) || !get_path(env, argv[2], vemb, sizeof vemb)) return throw_status(env, BBQ_ERR_NULL);
+  bbq_index* ix = NULL;
+  const int st = bbq_index_load((bbq_ctx*)ctx, veb, vemb, &ix);
+  if (st != BBQ_OK) return throw_status(env, st);
+  napi_value out;
+  napi_create_external(env, ix, fin_index, NULL, &out);
+  return out;
+}
+
 NAPI_MODULE_INIT() {
   const napi_property_descriptor props[] = {
       {"create", NULL, n_create, NULL, NULL, NULL, 0, NULL}, {"build", NULL, n_build, NULL, NULL, NULL, 0, NULL},
       {"info", NULL, n_info, NULL, NULL, NULL, 0, NULL},     {"search", NULL, n_search, NULL, NULL, NULL, 0, NULL},
-      {"rows", NULL, n_rows, NULL, NULL, NULL, 0, NULL}};
+      {"rows", NULL, n_rows, NULL, NULL, NULL, 0, NULL},
+      {"attachRows", NULL, n_attach_rows, NULL, NULL, NULL, 0, NULL},
+      {"searchRerank", NULL, n_search_rerank, NULL, NULL, NULL, 0, NULL},
+      {"saveIndex", NULL, n_save_index, NULL, NULL, NULL, 0, NULL},
+      {"loadIndex", NULL, n_load_index, NULL, NULL, NULL, 0, NULL}};
   napi_define_properties(env, exports, sizeof props / sizeof props[0], props);
   return exports;
 }

@@ -26,6 +26,7 @@ napi_status napi_get_value_double(napi_env, napi_value, double*);
 napi_status napi_get_value_int64(napi_env, napi_value, int64_t*);
 napi_status napi_get_value_uint32(napi_env, napi_value, uint32_t*);
 napi_status napi_get_value_external(napi_env, napi_value, void**);
+napi_status napi_get_value_string_utf8(napi_env, napi_value, char* buf, size_t bufsize, size_t* result);
 napi_status napi_get_typedarray_info(napi_env, napi_value, napi_typedarray_type*, size_t* length, void** data,
                                      napi_value* arraybuffer, size_t* byte_offset);
 napi_status napi_create_external(napi_env, void* data, napi_finalize, void* hint, napi_value* result);

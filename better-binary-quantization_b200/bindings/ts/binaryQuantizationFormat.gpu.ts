@@ -116,5 +116,37 @@ export class BinaryQuantizationFormat {
     } catch (e) { throw toReferenceError(e, 'search'); }
   }
 
+  /** getOversampledTopKWithSort / ...WithHeap (src/topKSelector.ts:29-114) on the device: quantised top k*factor,
+   *  exact cosine against the attached original rows, best k by true score. */
+  public attachOriginalVectors(targetVectors: BinarizedByteVectorValues, vectors: Float32Array[]): void {
+    const dim = targetVectors.dimension();
+    const flat = new Float32Array(vectors.length * dim);
+    vectors.forEach((v, i) => flat.set(v, i * dim));
+    try { addon.attachRows((targetVectors as DeviceBinarizedByteVectorValues).handle, flat); }
+    catch (e) { throw toReferenceError(e, 'build'); }
+  }
+  public searchOversampled(queryVector: Float32Array, targetVectors: BinarizedByteVectorValues, k: number,
+      oversampleFactor: number): Array<{ index: number; quantizedScore: number; trueScore: number }> {
+    try {
+      const r = addon.searchRerank((targetVectors as DeviceBinarizedByteVectorValues).handle, queryVector, 1, k,
+        oversampleFactor);
+      return Array.from({ length: r.count }, (_u, i) =>
+        ({ index: r.indices[i]!, quantizedScore: r.quantizedScores[i]!, trueScore: r.trueScores[i]! }));
+    } catch (e) { throw toReferenceError(e, 'search'); }
+  }
+
+  /** On-disk form of serializeVectorData / deserializeVectorData (:483-560): `${prefix}.veb` + `${prefix}.vemb`
+   *  (FILE_EXTENSIONS, src/constants.ts:52-57), streamed between the files and device memory natively. */
+  public saveIndex(targetVectors: BinarizedByteVectorValues, prefix: string): void {
+    try { addon.saveIndex((targetVectors as DeviceBinarizedByteVectorValues).handle, `${prefix}.veb`, `${prefix}.vemb`); }
+    catch (e) { throw toReferenceError(e, 'build'); }
+  }
+  public loadIndex(prefix: string): BinarizedByteVectorValues {
+    try {
+      return new DeviceBinarizedByteVectorValues(addon.loadIndex(this.ctx, `${prefix}.veb`, `${prefix}.vemb`)) as
+        BinarizedByteVectorValues;
+    } catch (e) { throw toReferenceError(e, 'build'); }
+  }
+
   public getConfig(): BinaryQuantizationConfig { return this.config; }        // :583
 }

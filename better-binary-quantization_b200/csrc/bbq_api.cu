@@ -621,6 +621,8 @@ extern "C" int bbq_index_export(const bbq_index* ix, uint64_t first, uint64_t co
   return BBQ_OK;
 }
 
+#include "bbq_io.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // search
 // ------------------------------------------------------------------------------------------------

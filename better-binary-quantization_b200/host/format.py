@@ -14,6 +14,7 @@ Everything numeric happens in libbbq_b200.so on the GPU; this file only marshals
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -214,6 +215,24 @@ class BinaryQuantizationFormat:
         _check(_native.load().bbq_index_from_quantized(self._ctx, packed.ctypes.data, corr4.ctypes.data,
                                                        centroid.ctypes.data, packed.shape[0], centroid.size,
                                                        C.byref(h)), "build")
+        return BinarizedByteVectorValues(self, h)
+
+    # -- index image on disk (serializeVectorData / deserializeVectorData, :483-560) ----------------------
+    @staticmethod
+    def _image_paths(prefix: str):
+        # FILE_EXTENSIONS, src/constants.ts:52-57
+        return (os.fsencode(prefix + ".veb"), os.fsencode(prefix + ".vemb"))
+
+    def saveIndex(self, targetVectors: BinarizedByteVectorValues, prefix: str) -> None:
+        """Writes <prefix>.veb (vector data) and <prefix>.vemb (metadata + centroid): bbq_index_save."""
+        veb, vemb = self._image_paths(prefix)
+        _check(_native.load().bbq_index_save(targetVectors._h, veb, vemb), "build")
+
+    def loadIndex(self, prefix: str) -> BinarizedByteVectorValues:
+        """Reads an image written by saveIndex straight into device memory: bbq_index_load."""
+        veb, vemb = self._image_paths(prefix)
+        h = C.c_void_p()
+        _check(_native.load().bbq_index_load(self._ctx, veb, vemb, C.byref(h)), "build")
         return BinarizedByteVectorValues(self, h)
 
     # -- query side -------------------------------------------------------------------------------------

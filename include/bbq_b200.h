@@ -51,6 +51,8 @@ typedef enum {
   BBQ_ERR_NULL = 8,          /* binaryQuantizationFormat.ts:318-323  null query / targets                */
   BBQ_ERR_UNSUPPORTED = 9,   /* config outside what the reference's batch path can run */
   BBQ_ERR_INVALID_ARG = 10,
+  BBQ_ERR_IO = 11,           /* index image: open/read/write failed (message carries errno text)         */
+  BBQ_ERR_FORMAT = 12,       /* index image: bad magic/version, other similarity, truncation, checksum   */
   /* runtime errors: never a silent fallback */
   BBQ_ERR_NO_DEVICE = 100,
   BBQ_ERR_CUDA = 101,
@@ -113,6 +115,16 @@ int bbq_index_from_quantized(bbq_ctx* ctx, const uint8_t* packed, const double* 
 uint64_t bbq_index_size(const bbq_index* index);
 uint32_t bbq_index_dim(const bbq_index* index);
 int bbq_index_centroid(const bbq_index* index, float* out_centroid /* dim */, double* out_centroid_dp);
+
+/* Index image on disk — the working form of serializeVectorData / deserializeVectorData
+ * (src/binaryQuantizationFormat.ts:483-560) behind the reference's own file split: `veb_path` holds the vector data
+ * (FILE_EXTENSIONS.VECTOR_DATA, one VectorDataFormat column per section: binaryValues, lowerInterval, upperInterval,
+ * additionalCorrection, quantizedComponentSum — src/types.ts:78-90), `vemb_path` the MetadataFormat fields
+ * (src/types.ts:95-113) plus the centroid.  Sections are the HBM arrays byte for byte, 4096-byte aligned, each with
+ * a device-computed checksum; layout in csrc/bbq_io.cuh.  bbq_index_load requires a context with the same
+ * similarity function and indexBits = 1 and returns BBQ_ERR_FORMAT otherwise (or on any corruption). */
+int bbq_index_save(const bbq_index* index, const char* veb_path, const char* vemb_path);
+int bbq_index_load(bbq_ctx* ctx, const char* veb_path, const char* vemb_path, bbq_index** out_index);
 
 /* vectorValue(ord) / getCorrectiveTerms(ord) for ord in [first, first+count): lazy device->host copy.
  * packed: count*ceil(dim/8) bytes; corr4: count*4 doubles.  Either may be NULL. */
