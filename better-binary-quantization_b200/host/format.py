@@ -289,6 +289,10 @@ class BinaryQuantizationFormat:
             raise BbqError(4, "向量维度不匹配")
         _check(_native.load().bbq_index_attach_rows(targetVectors._h, m.ctypes.data), "build")
 
+    def attachOriginalVectorsDevice(self, targetVectors: BinarizedByteVectorValues, d_rows_ptr: int):
+        """Same, rows already in device memory ([size, dimension] f32, e.g. a torch tensor's data_ptr())."""
+        _check(_native.load().bbq_index_attach_rows_device(targetVectors._h, d_rows_ptr), "build")
+
     def searchOversampledBatch(self, queries, targetVectors: BinarizedByteVectorValues, k: int, oversampleFactor: int):
         """-> (idx i32[nq, kk], quantizedScore f32[nq, kk], trueScore f64[nq, kk])"""
         qs = np.ascontiguousarray(queries, np.float32)
