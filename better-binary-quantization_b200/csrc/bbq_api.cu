@@ -718,7 +718,7 @@ static int quantize_queries(bbq_index* ix, const float* d_queries, int nq, cudaS
   TRY(c->qterms.reserve((size_t)nq * sizeof(bbqn::QueryTerms)));
   ProfScope prof(c, st, PROF_QUANT);
   const int ntimes = c->cfg.similarity == BBQ_SIM_COSINE ? 2 : 0;
-  const size_t per_warp = (size_t)((dim + 3) & ~3) * sizeof(float) + 7 * 33 * sizeof(double);
+  const size_t per_warp = (size_t)((dim + 3) & ~3) * sizeof(float) + 14 * 33 * sizeof(double);
   const size_t smem = per_warp * OSQW_WARPS;
   if (c->query_quantizer != 1 && smem <= 200 * 1024) {
     // latency form: one warp per query

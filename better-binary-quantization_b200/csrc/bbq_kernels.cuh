@@ -170,22 +170,30 @@ __global__ void k_osq_query(const float* __restrict__ T, int64_t ld, int nq, int
 // bits as bbqn::osq_interval / osq_codes (tests compare both with the oracle).
 template <int K, class Gen>
 __device__ __forceinline__ void warp_seq_sums(int d, int lane, double (*terms)[33], Gen gen, double (&result)[K]) {
+  // `terms` holds TWO buffers of K rows ([2*K][33]).  While the 32 dependent adds of block b run (every lane executes
+  // them, lanes >= K on row 0 and unused), the terms of block b+1 are generated into the other buffer: the two are
+  // independent, so the f64 math of the generator fills the latency slots of the serial chain.  Elements past d are
+  // +0.0 terms: acc + 0.0 == acc bit for bit (acc is never -0.0: it starts at +0.0), so every block adds 32 terms and
+  // the loop body has no branches.
   double acc = 0.0;
-  for (int base = 0; base < d; base += 32) {
-    const int i = base + lane;
+  const int nblk = (d + 31) >> 5;
+  const int chain_row = lane < K ? lane : 0;
+  auto generate = [&](int blk, int buf) {
+    const int i = (blk << 5) + lane;
     double t[K];
 #pragma unroll
     for (int k = 0; k < K; k++) t[k] = 0.0;
     if (i < d) gen(i, t);
 #pragma unroll
-    for (int k = 0; k < K; k++) terms[k][lane] = t[k];
-    __syncwarp();
-    if (lane < K) {
-      const int cnt = min(32, d - base);
-      const double* row = terms[lane];
-#pragma unroll 8
-      for (int m = 0; m < cnt; m++) acc += row[m];
-    }
+    for (int k = 0; k < K; k++) terms[buf * K + k][lane] = t[k];
+  };
+  generate(0, 0);
+  __syncwarp();
+  for (int blk = 0; blk < nblk; blk++) {
+    generate(blk + 1, (blk + 1) & 1);  // past the end: all zeros, never read
+    const double* row = terms[(blk & 1) * K + chain_row];
+#pragma unroll
+    for (int m = 0; m < 32; m++) acc += row[m];
     __syncwarp();
   }
 #pragma unroll
@@ -201,9 +209,9 @@ __global__ void __launch_bounds__(OSQW_WARPS * 32) k_osq_query_warp(
   extern __shared__ __align__(16) uint8_t osqw_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * OSQW_WARPS + warp;
-  const size_t per_warp = (size_t)((dim + 3) & ~3) * sizeof(float) + 7 * 33 * sizeof(double);
+  const size_t per_warp = (size_t)((dim + 3) & ~3) * sizeof(float) + 14 * 33 * sizeof(double);
   double(*terms)[33] = reinterpret_cast<double(*)[33]>(osqw_smem + warp * per_warp);
-  float* vec = reinterpret_cast<float*>(osqw_smem + warp * per_warp + 7 * 33 * sizeof(double));
+  float* vec = reinterpret_cast<float*>(osqw_smem + warp * per_warp + 14 * 33 * sizeof(double));
   if (q >= nq) return;  // whole warp
   const float* src = queries + (int64_t)q * dim;
   for (int i = lane; i < dim; i += 32) vec[i] = src[i];
@@ -810,7 +818,7 @@ __global__ void __launch_bounds__(RERANK_WARPS * 32) k_rerank_scores(const float
                                                                     const float* __restrict__ queries, int nq, int m,
                                                                     const int32_t* __restrict__ cand_idx,
                                                                     uint32_t base, double* __restrict__ true_scores) {
-  __shared__ double terms_s[RERANK_WARPS][3][33];
+  __shared__ double terms_s[RERANK_WARPS][6][33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t pair = (int64_t)blockIdx.x * RERANK_WARPS + warp;
   if (pair >= (int64_t)nq * m) return;

@@ -117,3 +117,87 @@ def test_c2_full_size_single_query(bbq):
         assert [r["index"] for r in res] == wi.tolist()
         assert bits_equal(np.array([r["score"] for r in res], np.float32), ws)
         assert set(hi.tolist()) == set(wi.tolist())              # reference heap == canonical (no boundary tie)
+
+
+def _append_chunks(fmt, shard, r0, r1, dim, seed, chunk=1 << 20):
+    """Rows [r0, r1) of the synthetic corpus, generated per `chunk`-row block from a seed that depends only on the
+    block number — every shard layout sees the same bytes for the same global row."""
+    import torch
+    c = r0 // chunk
+    pos = r0
+    while pos < r1:
+        c0 = c * chunk
+        lo, hi = max(pos, c0), min(r1, c0 + chunk)
+        g = torch.Generator(device="cuda")
+        g.manual_seed(seed + c)
+        rows = torch.randn((chunk, dim), generator=g, device="cuda", dtype=torch.float32)
+        part = rows[lo - c0:hi - c0].contiguous()
+        fmt.appendRows(shard, d_rows_ptr=part.data_ptr(), n=hi - lo)
+        del rows, part
+        pos = hi
+        c += 1
+    torch.cuda.synchronize()
+
+
+def test_c4_full_size_shard_invariance(bbq):
+    """configs[3] at full size on ONE GPU: 100M x 1024 COSINE, k=10.  The oracle cannot touch 100M rows, so the check
+    is the property multi-GPU correctness rests on: the top-k of the whole index == the deterministic merge of the
+    top-k of 4 independently built row shards (ragged: 3 x 26M + 22M), bit for bit, on the tensor-core engine; a few
+    queries are cross-checked on the popcount engine, and the returned rows re-score to the oracle's value."""
+    import torch
+    free, total = torch.cuda.mem_get_info()
+    if total < 100e9:
+        pytest.skip("needs a 180 GB-class GPU")
+    n, dim, k, nq, sim = 100_000_000, 1024, 10, 128, "COSINE"
+    seed = 20270000
+    cen = np.zeros(dim, np.float32)
+    fm = make_format(bbq, sim)   # engine chosen by the library: tensor cores for the batch, popcount for 4 queries
+    whole = fm.reserveIndex(n, dim, cen)
+    _append_chunks(fm, whole, 0, n, dim, seed)
+    assert whole.size() == n
+    qs = gaussian(nq, dim, 20270001)
+    wi, ws = fm.searchBatch(qs, whole, k)
+    assert fm.stats()["last_engine"] == 2 and fm.stats()["last_overflow"] == 0
+    assert np.all(np.diff(ws, axis=1) <= 0) and wi.min() >= 0 and wi.max() < n
+    wi2, ws2 = fm.searchBatch(qs, whole, k)
+    assert np.array_equal(wi, wi2) and bits_equal(ws, ws2)           # determinism at full size
+
+    # popcount engine over the same 100M rows for a few queries (a different kernel, same answer)
+    # (fewer than 64 queries take the popcount path in the same context)
+    pi, ps = fm.searchBatch(qs[:4], whole, k)
+    assert fm.stats()["last_engine"] == 1
+    assert np.array_equal(pi, wi[:4]) and bits_equal(ps, ws[:4])
+
+    # the returned rows re-score to the oracle's f32 value (export 10 rows per checked query)
+    for j in (0, 63, 127):
+        for r, (row, sc) in enumerate(zip(wi[j], ws[j])):
+            p, c = whole._export(int(row), 1)
+            oidx = O.OracleIndex(cen, p, None, c, dim, sim, 1)
+            _, _, alls, _ = O.search_nearest_neighbors(qs[j], oidx, 1, query_bits=4, mode="canonical", want_all=True)
+            assert bits_equal(np.float32(alls[0]), np.float32(sc)), (j, r)
+    del whole
+    torch.cuda.empty_cache()
+
+    # 4 ragged shards built independently, searched separately, merged as the multi-GPU path merges them
+    bounds = [(0, 26_000_000), (26_000_000, 52_000_000), (52_000_000, 78_000_000), (78_000_000, n)]
+    lists_i, lists_s = [], []
+    for r0, r1 in bounds:
+        sh = fm.reserveIndex(r1 - r0, dim, cen)
+        _append_chunks(fm, sh, r0, r1, dim, seed)
+        assert bbq._native.load().bbq_index_set_base(sh._h, r0) == 0
+        si, ss = fm.searchBatch(qs, sh, k)
+        lists_i.append(si)
+        lists_s.append(ss)
+        del sh
+        torch.cuda.empty_cache()
+    # the product's merge (bbq_merge_topk_device, what follows the NCCL all_gather) and its numpy statement
+    all_i = torch.from_numpy(np.stack(lists_i)).cuda()
+    all_s = torch.from_numpy(np.stack(lists_s)).cuda()
+    out_i = torch.empty((nq, k), dtype=torch.int32, device="cuda")
+    out_s = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    fm.mergeTopKDevice(all_i.data_ptr(), all_s.data_ptr(), len(bounds), nq, k, out_i.data_ptr(), out_s.data_ptr(), 0)
+    torch.cuda.synchronize()
+    assert np.array_equal(out_i.cpu().numpy(), wi) and bits_equal(out_s.cpu().numpy(), ws)
+    mi, ms = bbq.merge_host(lists_i, lists_s, k)
+    assert np.array_equal(mi, wi) and bits_equal(ms, ws)
