@@ -180,7 +180,7 @@ def run_reference(args, w, rank):
             "cpu_baseline": {"value": qps, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -373,10 +373,29 @@ def run_gpu(args, w, rank, world, local_rank):
     if cpu:
         line["cpu_baseline"] = cpu
         line["parity"] = parity
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL prints its version banner to stdout) must not break the one-JSON-line contract: from here on
+    file descriptor 1 goes to stderr and only emit() writes to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def load_traffic(workload, nq, world, kernel):
@@ -418,6 +437,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        quiet_stdout()
         run_reference(args, w, rank)
         return
     if world != args.gpus:
@@ -426,6 +446,7 @@ def main():
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                    "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
             os.execv(sys.executable, cmd)
+    quiet_stdout()
     run_gpu(args, w, rank, world, local_rank)
 
 
