@@ -762,7 +762,7 @@ static bool mma_plan(const bbq_index* ix, int nq, MmaPlan* out) {
   pl.passes = (nq + n_cap - 1) / n_cap;
   pl.n_tile = (((nq + pl.passes - 1) / pl.passes) + 15) / 16 * 16;
   pl.nstage = std::min(8, (512 - 2 * pl.n_tile) / 32);
-  pl.smem = (size_t)pl.n_tile * pl.kbytes + (size_t)pl.n_tile * (sizeof(QScreen) + sizeof(bbqn::QueryTerms)) + 24 * 8 + sizeof(HitCtx) + HIT_RING * sizeof(uint64_t) + 16 + 16;
+  pl.smem = (size_t)pl.n_tile * pl.kbytes + (size_t)pl.n_tile * (sizeof(QScreen) + sizeof(bbqn::QueryTerms)) + 26 * 8 + sizeof(HitCtx) + HIT_RING * sizeof(uint64_t) + 16 + 16;
   *out = pl;
   return true;
 }

@@ -28,7 +28,7 @@
 namespace bbqk {
 
 constexpr int MMA_EPI_WARPS = 8;      // epilogue warps: two per TMEM lane quarter, alternating 16-column chunks
-constexpr int MMA_THREADS = (8 + MMA_EPI_WARPS) * 32;  // warp 0 B loader, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4-7 expansion, 8.. epilogue
+constexpr int MMA_THREADS = (8 + MMA_EPI_WARPS) * 32;  // warp 0 B loader, 1-2 MMA issuers (2 also allocates TMEM), 3 drainer, 4-7 expansion, 8.. epilogue
 constexpr int MMA_N_MAX = 224;        // 2 accumulators + >= 2 A stages must fit the 512 TMEM columns
 constexpr int MMA_CHUNK_DIMS = 128;   // dims per A stage (32 TMEM columns)
 
@@ -539,7 +539,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
   uint64_t* b_full = bars + 20;
   uint64_t* b_empty = bars + 21;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 22);
-  HitCtx* hit_s = reinterpret_cast<HitCtx*>(bars + 24);
+  uint64_t* tile_go = bars + 24;      // [2] first MMA of a tile has overwritten the accumulator (issuer 0 -> issuer 1)
+  HitCtx* hit_s = reinterpret_cast<HitCtx*>(bars + 26);
   uint64_t* ring_s = reinterpret_cast<uint64_t*>(hit_s + 1);            // [HIT_RING] parked hits
   uint32_t* ring_ctl_s = reinterpret_cast<uint32_t*>(ring_s + HIT_RING);  // tail, head, done
 
@@ -552,12 +553,14 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
       mbar_init(a_full + i, 4);
       mbar_init(a_empty + i, 1);
     }
+    const uint32_t nissuers = nchunks > 1 ? 2u : 1u;  // every issuer commits its own MMAs
     for (int i = 0; i < 2; i++) {
-      mbar_init(acc_full + i, 1);
+      mbar_init(acc_full + i, nissuers);
       mbar_init(acc_empty + i, MMA_EPI_WARPS * 32);
+      mbar_init(tile_go + i, 1);
     }
     mbar_init(b_full, 1);
-    mbar_init(b_empty, 1);
+    mbar_init(b_empty, nissuers);
     hit_s->dim = p.dim;
     hit_s->cdp = p.cdp;
     hit_s->cand = p.cand;
@@ -608,22 +611,32 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
+  } else if (warp == 1 || (warp == 2 && nchunks > 1)) {
+    // ===== MMA issuers =====
+    // One thread needs ~99 cycles to issue a tcgen05.mma (tools/probe/mma_issue_probe.cu: independent of N and of
+    // TS/SS), so 4 issues + the per-chunk hand-off (barrier wait, fence, commit: ~260 cycles) exceed the ~420
+    // cycles the tensor pipe needs for the chunk, and the pipe idles.  Two issuers take alternate chunks (warp 1 the
+    // even ones, warp 2 the odd ones); integer accumulation commutes, and the one ordering that matters — the
+    // overwriting first MMA of a tile before anything else — is enforced by a commit-signalled barrier.
+    const int me = warp - 1;  // 0: even chunks (and the tile's first MMA), 1: odd chunks
     const uint32_t idesc = make_idesc_i8(128, p.n_tile);
     const uint32_t lbo = (uint32_t)p.n_tile * 16u;
     const uint32_t b_addr = smem_u32(b_smem);
-    uint32_t stage = 0, sphase = 0, tcount = 0;
+    uint32_t gchunk = 0;  // running chunk count of this CTA: stage = gchunk % nstage, phase = (gchunk / nstage) & 1
+    uint32_t tcount = 0;
     int mma_ev = 0;
     for (int pass = 0; pass < p.passes; pass++) {
       mbar_wait(b_full, (uint32_t)(pass & 1));
       for (int64_t i = blockIdx.x; i < p.ntiles; i += gridDim.x) {
         const uint32_t buf = tcount & 1u, bphase = (tcount >> 1) & 1u;
-        mbar_wait(acc_empty + buf, bphase ^ 1u);  // epilogue has drained this accumulator
+        if (me == 0) mbar_wait(acc_empty + buf, bphase ^ 1u);  // epilogue has drained this accumulator
+        else mbar_wait(tile_go + buf, bphase);                 // ... and issuer 0's overwriting MMA has completed
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc_col + buf * (uint32_t)p.n_tile;
-        for (int kc = 0; kc < nchunks; kc++) {
-          const bool tr = (p.debug & 32u) && blockIdx.x == 0 && lane == 0 && pass == 0;
+        for (int kc = me; kc < nchunks; kc += 2) {
+          const uint32_t g = gchunk + (uint32_t)kc;
+          const uint32_t stage = g % (uint32_t)nstage, sphase = (g / (uint32_t)nstage) & 1u;
+          const bool tr = (p.debug & 32u) && blockIdx.x == 0 && lane == 0 && pass == 0 && me == 0;
           long long t0 = tr ? clock64() : 0;
           mbar_wait(a_full + stage, sphase);
           tc_fence_after();
@@ -634,6 +647,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
               const uint32_t a_tmem = tmem_base + a_col + stage * 32u + (uint32_t)j * 8u;
               const uint64_t bdesc = make_kmajor_desc(b_addr + (uint32_t)((kc * 4 + j) * 2) * lbo, lbo, 128u);
               tc_mma_i8_ts(d_tmem, a_tmem, bdesc, idesc, (kc | j) != 0 ? 1u : 0u);
+              if (kc == 0 && j == 0 && nchunks > 1) tc_commit(tile_go + buf);
             }
             tc_commit(a_empty + stage);  // frees the A stage once these MMAs have read it
             if (tr && mma_ev < 1000) {
@@ -644,16 +658,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
             }
           }
           __syncwarp();
-          if (++stage == (uint32_t)nstage) {
-            stage = 0;
-            sphase ^= 1u;
-          }
         }
+        gchunk += (uint32_t)nchunks;
         if (lane == 0) tc_commit(acc_full + buf);
         __syncwarp();
         tcount++;
       }
-      if (lane == 0) tc_commit(b_empty);  // all MMAs of this pass done -> B may be replaced
+      if (lane == 0) tc_commit(b_empty);  // this issuer's MMAs of the pass are done -> B may be replaced
       __syncwarp();
     }
   } else if (warp == 3) {
