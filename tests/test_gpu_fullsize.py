@@ -201,3 +201,28 @@ def test_c4_full_size_shard_invariance(bbq):
     assert np.array_equal(out_i.cpu().numpy(), wi) and bits_equal(out_s.cpu().numpy(), ws)
     mi, ms = bbq.merge_host(lists_i, lists_s, k)
     assert np.array_equal(mi, wi) and bits_equal(ms, ws)
+
+
+def test_c3_repeatability_stress(bbq):
+    """The tensor-core scan is a protocol of mbarriers between six warp roles (two MMA issuers, expansion, epilogue,
+    drainer, loader) with a threshold that tightens concurrently in 148 CTAs: 25 back-to-back searches of the C3
+    batch must give the same bits every time, and equal the popcount engine's answer."""
+    import torch
+    n, dim, k, nq = 1_000_000, 1024, 10, 1024
+    rows_d = _device_corpus(n, dim, 20260303)
+    cen = np.zeros(dim, np.float32)
+    fm = make_format(bbq, "COSINE", scan="mma")
+    qm = fm.quantizeVectorsDevice(rows_d.data_ptr(), n, dim, centroid=cen)["quantizedVectors"]
+    del rows_d
+    torch.cuda.empty_cache()
+    qs = gaussian(nq, dim, 20260304)
+    ref_i, ref_s = fm.searchBatch(qs, qm, k)
+    assert fm.stats()["last_engine"] == 2
+    for rep in range(24):
+        i2, s2 = fm.searchBatch(qs, qm, k)
+        assert np.array_equal(ref_i, i2) and bits_equal(ref_s, s2), rep
+    fp = make_format(bbq, "COSINE", scan="popc")
+    packed, corr = qm.exportAll()
+    qp = fp.adoptQuantized(packed, corr, cen)
+    pi, ps = fp.searchBatch(qs[:96], qp, k)
+    assert np.array_equal(pi, ref_i[:96]) and bits_equal(ps, ref_s[:96])
