@@ -1,6 +1,6 @@
 #!/bin/bash
 # same-box A/B of two builds of the library: tools/ab_libs.sh old.so new.so  (C3 and C4 scan launch times)
-for rep in 1 2; do for lib in "$@"; do
+for rep in ${REPS:-1 2}; do for lib in "$@"; do
   cp "$lib" better-binary-quantization_b200/libbbq_b200.so
   for w in ${WL:-c3 c4}; do
     echo -n "$(basename $lib) $w: "
