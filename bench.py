@@ -243,7 +243,7 @@ def run_gpu(args, w, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, sampler=None):
+    def timed(fn, steps, warmup, sampler=None, cold=True):
         for _ in range(warmup):
             fn()
         barrier()
@@ -251,7 +251,8 @@ def run_gpu(args, w, rank, world, local_rank):
             sampler.start()
         tot = 0.0
         for _ in range(steps):
-            flush.zero_()                      # L2 flush between timed iterations, outside the timed pair
+            if cold:
+                flush.zero_()                  # L2 flush between timed iterations, outside the timed pair
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(searcher.stream)
@@ -286,6 +287,13 @@ def run_gpu(args, w, rank, world, local_rank):
     e2e_ms, _ = timed(lambda: searcher.search(hq, k), args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
     e2e_qps = nq / (e2e_ms / args.steps * 1e-3)
+    # an index smaller than L2 (C2: 11 MB of 126 MB) is L2-resident after the first query: SURVEY §8d asks for the
+    # warm figure beside the cold one (`value` / `e2e` above are cold: L2 flushed before every step)
+    warm = None
+    if (r1 - r0) * ((dim + 7) // 8 + 28) < 100e6:
+        warm_ms, _ = timed(lambda: searcher.search_device(dq, k), args.steps, args.warmup, cold=False)
+        warm = {"value": nq / (warm_ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": warm_ms / args.steps,
+                "note": "same device-resident search, L2 not flushed between steps (index is L2-resident)"}
     h2d = nq * dim * 4 * world
     d2h = nq * k * 8 * world
 
@@ -294,6 +302,7 @@ def run_gpu(args, w, rank, world, local_rank):
             dist.barrier()
             dist.destroy_process_group()
         return
+    extra_warm = {"warm_l2": warm} if warm else {}
 
     # --- roofline of the dominant kernel (the filtered scan; CUDA events on its own stream inside the library) ---
     hbm_peak, bf16_peak, peak_src = load_peaks()
@@ -378,6 +387,7 @@ def run_gpu(args, w, rank, world, local_rank):
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}
+    line.update(extra_warm)
     if cpu:
         line["cpu_baseline"] = cpu
         line["parity"] = parity
