@@ -347,6 +347,8 @@ def test_batch_equals_single_and_is_deterministic(bbq):
     (20000, 768, 64, 100, 4),      # k = 100
     (20000, 128, 96, 10, 1),       # 1-bit queries
     (20000, 128, 96, 10, 5),       # widest query the weighted expansion supports
+    (30000, 384, 80, 10, 4),       # odd number of 128-dim chunks (3): the two MMA issuers split 2 + 1
+    (26000, 640, 130, 10, 4),      # 5 chunks, two passes
 ])
 def test_mma_scan_matches_oracle_and_popcount(bbq, sim, n, dim, nq, k, qb):
     rows, qs = gaussian(n, dim, 101 + n + dim), gaussian(nq, dim, 102 + n)
