@@ -758,7 +758,10 @@ static bool mma_plan(const bbq_index* ix, int nq, MmaPlan* out) {
   n_cap = std::min(n_cap, MMA_N_MAX);
   if (c->mma_ntile_cap > 0) n_cap = std::min(n_cap, c->mma_ntile_cap / 16 * 16);
   if (n_cap < 16) return false;
-  if (c->scan_engine != 2 && nq < 64) return false;  // small batches: the popcount kernel is HBM/latency bound anyway
+  // 1-4 queries: the streaming popcount scan (HBM/latency bound, ~43 us per query and 1M rows).  From 5 queries on the
+  // tensor-core scan wins: one pass over 1M x 1024 costs 0.145 ms whatever the block size (operand-feed bound), the
+  // popcount tile scan 0.03 ms per query (tools/crossover.sh: 8 queries 0.145 vs 0.257 ms, 48 queries 0.154 vs 1.43 ms)
+  if (c->scan_engine != 2 && nq < 5) return false;
   pl.passes = (nq + n_cap - 1) / n_cap;
   pl.n_tile = (((nq + pl.passes - 1) / pl.passes) + 15) / 16 * 16;
   pl.nstage = std::min(8, (512 - 2 * pl.n_tile) / 32);
