@@ -6,7 +6,7 @@ reference-facing operator interface) and bindings/ (the N-API shim + TypeScript 
 """
 from . import _native
 from ._native import build_library
-from .host.sharded import ShardedSearcher, merge_host, shard_bounds
+from .host.sharded import ShardedSearcher, broadcast_comm_id, merge_host, shard_bounds
 from .host.format import (BbqError, BinarizedByteVectorValues, BinaryQuantizationFormat,
                           VectorSimilarityFunction)
 
@@ -52,5 +52,5 @@ getOversampledTopKWithHeap = getOversampledTopKWithSort  # :29-78 — same set u
 
 __all__ = ["BinaryQuantizationFormat", "BinarizedByteVectorValues", "VectorSimilarityFunction", "BbqError",
            "createBinaryQuantizationFormat", "quickQuantize", "quickSearch", "DEFAULT_CONFIG", "VERSION",
-           "build_library", "ShardedSearcher", "shard_bounds", "merge_host", "getOversampledTopKWithSort",
+           "build_library", "ShardedSearcher", "shard_bounds", "merge_host", "broadcast_comm_id", "getOversampledTopKWithSort",
            "getOversampledTopKWithHeap"]

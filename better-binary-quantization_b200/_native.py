@@ -5,6 +5,7 @@ The library is built in-tree by build_library() (nvcc, sm_100a) so it travels wi
 from __future__ import annotations
 
 import ctypes as C
+import glob
 import os
 import subprocess
 
@@ -16,12 +17,11 @@ HEADER = os.path.join(_HERE, "..", "include", "bbq_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 SOURCES = ["bbq_api.cu"]
-DEPS = ["bbq_api.cu", "bbq_kernels.cuh", "bbq_mma.cuh", "bbq_numerics.cuh"]
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA library for sm_100a (cross-compiles without a GPU)."""
-    deps = [os.path.join(CSRC, d) for d in DEPS] + [HEADER]
+    deps = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh"))) + [HEADER]
     stale = force or not os.path.exists(LIB_PATH) or any(
         os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
     if stale:
@@ -76,6 +76,17 @@ SYMBOLS = {
     "bbq_merge_topk_device": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
     "bbq_debug_quantize_query": (C.c_int, [_vp, _vp, _vp, _vp]),
     "bbq_debug_qcdist": (C.c_int, [_vp, _vp, _vp]),
+    "bbq_debug_qcdist_batch": (C.c_int, [_vp, _vp, C.c_uint32, _vp]),
+    "bbq_comm_unique_id": (C.c_int, [_vp]),
+    "bbq_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "bbq_comm_destroy": (C.c_int, [_vp]),
+    "bbq_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "bbq_search_sharded": (C.c_int, [_vp, _vp, C.c_uint32, C.c_int64, _vp, _vp, C.POINTER(C.c_uint32)]),
+    "bbq_search_sharded_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
+    "bbq_quantize_query": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp, _vp]),
+    "bbq_quantization_accuracy": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint64, _vp]),
+    "bbq_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "bbq_host_free": (None, [_vp]),
     "bbq_debug_scores": (C.c_int, [_vp, _vp, _vp]),
     "bbq_get_stats": (C.c_int, [_vp, C.POINTER(BbqStats)]),
     "bbq_set_profiling": (C.c_int, [_vp, C.c_int]),

@@ -1,6 +1,8 @@
 // bbq_api.cu — host side of libbbq_b200.so: the C ABI declared in include/bbq_b200.h.
 // Owns device memory, the stream and the launch sequence; no torch, no CPU fallback.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: the library is dlopen'ed on first use (bbq_comm_*), never linked
 
 #include <algorithm>
 #include <cmath>
@@ -79,7 +81,7 @@ struct bbq_ctx {
   DevBuf T, stage, cacc;
   // query scratch
   DevBuf qrows, qT, qcodes, qcorr, planes, qterms, tau, dump, cand, cand_cnt, flag, lists_a, lists_b,
-      out_idx, out_score, dots, images, qscreen, tau_bits, trace, rr_true, rr_idx, rr_q, rr_t;
+      out_idx, out_score, dots, images, qscreen, tau_bits, trace, rr_true, rr_idx, rr_q, rr_t, cenv;
   int64_t sample_tiles_dyn = 128;  // BBQ_SAMPLE_TILES: sample size when the running threshold is on
   int k1s_ctas = 4;         // BBQ_K1S_CTAS: persistent CTAs per SM of the streaming scan (huge = one tile per CTA)
   int csa = 1;              // BBQ_CSA=0: plain popcount accumulation in the streaming scan (A/B, tests)
@@ -89,7 +91,11 @@ struct bbq_ctx {
   bool dynamic_tau = true;  // BBQ_DYNTAU=0 keeps the sampled threshold fixed during the tensor-core scan (tests)
   int query_quantizer = 0;  // BBQ_QQUANT=thread forces the one-thread-per-query form (tests)
   int scan_engine = 0;  // BBQ_SCAN: 0 auto, 1 popcount kernel only, 2 tensor-core kernel whenever it can run
-  uint32_t* h_flag = nullptr;  // pinned: [0..nq) candidate counts, [nq] overflow flag
+  uint32_t* h_flag = nullptr;  // pinned: [0..nq) candidate counts, [nq] overflow flag, then 2 words: first invalid query
+  // sharded search (bbq_comm_init): one NCCL communicator per context = per GPU = per process
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  DevBuf keys_local, keys_all, loc_idx, loc_score, bad, nglob;
   // profiling (bbq_set_profiling): event pairs per kernel group, drained by bbq_get_stats
   bool profiling = false;
   struct EvPair { cudaEvent_t a, b; int kind; };
@@ -143,11 +149,13 @@ struct bbq_index {
   float4* rscreen = nullptr;      // device [capacity]: per-row screen constants, same validity
   uint64_t bounds_n = 0;
   uint64_t capacity = 0;  // rows allocated (== n except while a streaming build is in progress)
+  uint64_t n_global = 0, n_global_for = ~0ull;  // sharded search: rows over all ranks, valid while n == n_global_for
 };
 
 static constexpr int64_t BUILD_CHUNK = 32768;   // rows per build chunk (transposed scratch = dim*chunk*4 B)
-static constexpr uint32_t QUERY_BATCH = 1024;   // queries per internal pass
-static constexpr int64_t SAMPLE_TILES = 128;    // threshold sample = 128 tiles = 16384 rows
+static constexpr uint32_t QUERY_BATCH = 4096;   // queries per internal pass (12-bit query field of a parked hit)
+static constexpr int64_t SAMPLE_TILES = 128;    // threshold sample = 128 tiles = 16384 rows ...
+static constexpr int64_t SAMPLE_TILES_MAX = 2048;  // ... grown with k*n up to 262144 rows (see search_filtered)
 static constexpr uint32_t CAND_CAP = SELECT_MAX;
 static constexpr uint32_t K_MAX = 4096;
 
@@ -189,7 +197,7 @@ extern "C" int bbq_create(const bbq_config* config, bbq_ctx** out_ctx) {
   c->device = dev;
   c->sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CU(cudaMallocHost(&c->h_flag, (QUERY_BATCH + 1) * sizeof(uint32_t)));
+  CU(cudaMallocHost(&c->h_flag, (QUERY_BATCH + 4) * sizeof(uint32_t)));
   if (const char* e = getenv("BBQ_FORCE_PATH")) c->force_path = atoi(e);
   if (const char* e = getenv("BBQ_SAMPLE_TILES")) c->sample_tiles_dyn = std::max(1, std::min(128, atoi(e)));
   if (const char* e = getenv("BBQ_CSA")) c->csa = atoi(e);
@@ -204,6 +212,7 @@ extern "C" int bbq_create(const bbq_config* config, bbq_ctx** out_ctx) {
   return BBQ_OK;
 }
 
+static void comm_release(bbq_ctx* c);
 static void ctx_release(bbq_ctx* c) {
   if (--c->refs > 0) return;
   cudaSetDevice(c->device);
@@ -211,8 +220,10 @@ static void ctx_release(bbq_ctx* c) {
   for (DevBuf* b : {&c->T, &c->stage, &c->cacc, &c->qrows, &c->qT, &c->qcodes, &c->qcorr, &c->planes, &c->qterms,
                     &c->tau, &c->dump, &c->cand, &c->cand_cnt, &c->flag, &c->lists_a, &c->lists_b, &c->out_idx,
                     &c->out_score, &c->dots, &c->images, &c->qscreen, &c->tau_bits, &c->trace, &c->rr_true, &c->rr_idx,
-                    &c->rr_q, &c->rr_t})
+                    &c->rr_q, &c->rr_t, &c->cenv, &c->keys_local, &c->keys_all, &c->loc_idx, &c->loc_score, &c->bad,
+                    &c->nglob})
     b->release();
+  comm_release(c);
   if (c->h_flag) cudaFreeHost(c->h_flag);
   for (auto& p : c->ev_pending) {
     cudaEventDestroy(p.a);
@@ -339,7 +350,7 @@ static int build_impl(bbq_ctx* c, const float* rows, bool is_host, uint64_t n, u
   if (!rows) return fail(BBQ_ERR_NULL, "rows is null");
   if (n == 0) return fail(BBQ_ERR_EMPTY, "vector set must not be empty");
   if (dim == 0) return fail(BBQ_ERR_INVALID_ARG, "dim must be > 0");
-  if (n > 0xFFFFFFF0ull) return fail(BBQ_ERR_UNSUPPORTED, "more than 2^32 rows per shard");
+  if (n > 0x7FFFFFF0ull) return fail(BBQ_ERR_UNSUPPORTED, "more than 2^31 rows per shard (result ids are int32)");
   if (c->cfg.index_bits != 1)
     return fail(BBQ_ERR_UNSUPPORTED,
                 "indexBits != 1: the reference's batch search path cannot run it (createDirectPackedBuffer throws); "
@@ -707,17 +718,18 @@ static int launch_select(bbq_ctx* c, const SelectParams& p, uint32_t m_max, cuda
   return BBQ_OK;
 }
 
-// K4 for nq queries already in device memory (row-major f32): fills ctx->planes / qterms (/qcodes,qcorr)
-static int quantize_queries(bbq_index* ix, const float* d_queries, int nq, cudaStream_t st) {
-  bbq_ctx* c = ix->ctx;
-  const int dim = (int)ix->dim, nb = (int)c->cfg.query_bits, words = ix->row_bytes / 4, code_ld = ix->row_bytes * 8;
+// K4 for nq queries already in device memory (row-major f32): fills ctx->planes / qterms (/qcodes,qcorr).
+// ntimes = how often a COSINE query is normalised: 2 on the search path (src/binaryQuantizationFormat.ts:337 and
+// :279), 1 for a direct quantizeQueryVector call (:271-299).
+static int quantize_rows(bbq_ctx* c, const float* d_queries, int nq, int dim, int row_bytes, const float* d_centroid,
+                         int ntimes, cudaStream_t st) {
+  const int nb = (int)c->cfg.query_bits, words = row_bytes / 4, code_ld = row_bytes * 8;
   TRY(c->qT.reserve((size_t)nq * dim * sizeof(float)));
   TRY(c->qcodes.reserve((size_t)nq * code_ld));
   TRY(c->qcorr.reserve((size_t)nq * 4 * sizeof(double)));
   TRY(c->planes.reserve((size_t)nq * nb * words * sizeof(uint32_t)));
   TRY(c->qterms.reserve((size_t)nq * sizeof(bbqn::QueryTerms)));
   ProfScope prof(c, st, PROF_QUANT);
-  const int ntimes = c->cfg.similarity == BBQ_SIM_COSINE ? 2 : 0;
   const size_t per_warp = (size_t)((dim + 3) & ~3) * sizeof(float) + 14 * 33 * sizeof(double);
   const size_t smem = per_warp * OSQW_WARPS;
   if (c->query_quantizer != 1 && smem <= 200 * 1024) {
@@ -725,7 +737,7 @@ static int quantize_queries(bbq_index* ix, const float* d_queries, int nq, cudaS
     if (smem > 48 * 1024)
       CU(cudaFuncSetAttribute(k_osq_query_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LAUNCH(c, k_osq_query_warp, (nq + OSQW_WARPS - 1) / OSQW_WARPS, OSQW_WARPS * 32, smem, st, d_queries, nq, dim,
-           ix->centroid, (int)c->cfg.similarity, nb, c->cfg.lambda, (int)c->cfg.iters, ntimes, c->qcodes.as<uint8_t>(),
+           d_centroid, (int)c->cfg.similarity, nb, c->cfg.lambda, (int)c->cfg.iters, ntimes, c->qcodes.as<uint8_t>(),
            code_ld, c->qcorr.as<double>());
   } else {
     // throughput form: one thread per query over the transposed scratch (same code as the index build)
@@ -733,13 +745,18 @@ static int quantize_queries(bbq_index* ix, const float* d_queries, int nq, cudaS
     dim3 grid((nq + 31) / 32, (dim + 31) / 32), block(32, 8);
     LAUNCH(c, k_transpose, grid, block, 0, st, d_queries, (int64_t)nq, dim, T, (int64_t)nq);
     if (ntimes) LAUNCH(c, k_normalize_T, (nq + 63) / 64, 64, 0, st, T, (int64_t)nq, (int64_t)nq, dim, ntimes);
-    LAUNCH(c, k_osq_query, (nq + 63) / 64, 64, 0, st, T, (int64_t)nq, nq, dim, ix->centroid, (int)c->cfg.similarity, nb,
+    LAUNCH(c, k_osq_query, (nq + 63) / 64, 64, 0, st, T, (int64_t)nq, nq, dim, d_centroid, (int)c->cfg.similarity, nb,
            c->cfg.lambda, (int)c->cfg.iters, c->qcodes.as<uint8_t>(), code_ld, c->qcorr.as<double>());
   }
   const int64_t total = (int64_t)nq * nb * words;
   LAUNCH(c, k_query_planes, (unsigned)((total + 127) / 128), 128, 0, st, c->qcodes.as<uint8_t>(), code_ld,
          c->qcorr.as<double>(), nq, nb, words, c->planes.as<uint32_t>(), c->qterms.as<bbqn::QueryTerms>());
   return BBQ_OK;
+}
+static int quantize_queries(bbq_index* ix, const float* d_queries, int nq, cudaStream_t st) {
+  bbq_ctx* c = ix->ctx;
+  return quantize_rows(c, d_queries, nq, (int)ix->dim, ix->row_bytes, ix->centroid,
+                       c->cfg.similarity == BBQ_SIM_COSINE ? 2 : 0, st);
 }
 
 // ---- tensor-core scan (K2) -------------------------------------------------------------------------
@@ -816,7 +833,7 @@ static int launch_mma_sim(bbq_ctx* c, int sim, unsigned grid, size_t smem, cudaS
 
 static int launch_scan_mma(bbq_index* ix, int mode, int nq, uint32_t k, const MmaPlan& pl, int64_t tile_first, int64_t tile_stride,
                            int64_t ntiles, float* dump, int64_t dump_ld, uint64_t* cand, uint32_t* cand_cnt,
-                           uint32_t cap, uint32_t* overflow, cudaStream_t st) {
+                           uint32_t cap, uint32_t* overflow, cudaStream_t st, int32_t* dots = nullptr) {
   bbq_ctx* c = ix->ctx;
   MmaParams p{};
   p.codes = ix->codes;
@@ -854,6 +871,7 @@ static int launch_scan_mma(bbq_index* ix, int mode, int nq, uint32_t k, const Mm
   p.ntiles = ntiles;
   p.dump = dump;
   p.dump_ld = dump_ld;
+  p.dots = dots;
   p.cand = cand;
   p.cand_cnt = cand_cnt;
   p.cap = cap;
@@ -979,11 +997,23 @@ static int search_filtered(bbq_index* ix, int nq, uint32_t k, int32_t* d_out_idx
   const int64_t ntiles = (n + TILE_ROWS - 1) / TILE_ROWS, full_tiles = n / TILE_ROWS;
   MmaPlan pl;
   const bool use_mma = mma_plan(ix, nq, &pl);
-  // with the running threshold of the tensor-core scan a quarter of the sample is enough to start from
-  const int64_t want_tiles = (use_mma && c->dynamic_tau && k <= RETIGHTEN_KMAX) ? c->sample_tiles_dyn : SAMPLE_TILES;
+  // Sample size.  With the running threshold of the tensor-core scan (k <= RETIGHTEN_KMAX) the sample only has to
+  // give the scan something to start from.  With a FIXED threshold about k * n / sample_rows rows pass it, so the
+  // sample grows with k * n until that expectation is a quarter of a candidate list (otherwise a large k or a large
+  // shard would overflow the lists on perfectly ordinary data and fall back to the exact chunked path every time).
+  const bool running = use_mma && c->dynamic_tau && k <= RETIGHTEN_KMAX;
+  int64_t want_tiles = running ? c->sample_tiles_dyn : SAMPLE_TILES;
+  if (!running) {
+    const int64_t need_rows = (int64_t)std::min<double>(4.0 * (double)k * (double)n / (double)CAND_CAP, 1e12);
+    want_tiles = std::max(want_tiles, std::min<int64_t>(SAMPLE_TILES_MAX, (need_rows + TILE_ROWS - 1) / TILE_ROWS));
+    if (k > (uint32_t)TAU_THREADS) want_tiles = std::min<int64_t>(want_tiles, SELECT_MAX / TILE_ROWS);  // k_select sorts the sample
+    // the sample's scores are dumped densely: keep that scratch below ~1 GiB whatever the batch size
+    want_tiles = std::max<int64_t>(SAMPLE_TILES, std::min<int64_t>(want_tiles, (int64_t)(1ll << 28) / ((int64_t)nq * TILE_ROWS)));
+  }
   const int64_t stiles = std::min<int64_t>(want_tiles, full_tiles);
   const int64_t stride = std::max<int64_t>(1, full_tiles / stiles);
-  TRY(c->dump.reserve((size_t)nq * SELECT_MAX * sizeof(float)));
+  const int64_t sample_ld = stiles * TILE_ROWS;
+  TRY(c->dump.reserve((size_t)nq * sample_ld * sizeof(float)));
   TRY(c->tau.reserve((size_t)nq * sizeof(float)));
   TRY(c->cand.reserve((size_t)nq * CAND_CAP * sizeof(uint64_t)));
   TRY(c->cand_cnt.reserve((size_t)(nq + 1) * sizeof(uint32_t)));
@@ -996,9 +1026,9 @@ static int search_filtered(bbq_index* ix, int nq, uint32_t k, int32_t* d_out_idx
     ScanParams p = base_scan_params(ix, nq);
     p.tile_stride = stride;
     p.dump = c->dump.as<float>();
-    p.dump_ld = SELECT_MAX;
+    p.dump_ld = sample_ld;
     if (use_mma)
-      TRY(launch_scan_mma(ix, SCAN_DUMP, nq, k, pl, 0, stride, stiles, c->dump.as<float>(), SELECT_MAX, nullptr, nullptr, 0,
+      TRY(launch_scan_mma(ix, SCAN_DUMP, nq, k, pl, 0, stride, stiles, c->dump.as<float>(), sample_ld, nullptr, nullptr, 0,
                           nullptr, st));
     else
       TRY(launch_scan(ix, SCAN_DUMP, p, stiles, st));
@@ -1006,7 +1036,7 @@ static int search_filtered(bbq_index* ix, int nq, uint32_t k, int32_t* d_out_idx
     s.nq = nq;
     s.k = k;
     s.scores = c->dump.as<float>();
-    s.ld = SELECT_MAX;
+    s.ld = sample_ld;
     s.m = (uint32_t)(stiles * TILE_ROWS);
     s.tile_first = 0;
     s.tile_stride = stride;
@@ -1014,7 +1044,7 @@ static int search_filtered(bbq_index* ix, int nq, uint32_t k, int32_t* d_out_idx
     s.tau_out = c->tau.as<float>();
     if (k <= (uint32_t)TAU_THREADS) {
       ProfScope prof(c, st, PROF_SELECT);
-      LAUNCH(c, k_tau_from_sample, nq, TAU_THREADS, 0, st, c->dump.as<float>(), (int64_t)SELECT_MAX, s.m, k,
+      LAUNCH(c, k_tau_from_sample, nq, TAU_THREADS, 0, st, c->dump.as<float>(), sample_ld, s.m, k,
              c->tau.as<float>());
     } else {
       TRY(launch_select<SEL_DENSE>(c, s, s.m, st));
@@ -1102,6 +1132,30 @@ extern "C" int bbq_search_device(bbq_index* ix, const float* d_queries, uint32_t
   return BBQ_OK;
 }
 
+// Query screening on the device (k_validate_queries): enqueue -> [search] -> finish (D2H of the verdict into the
+// pinned flag block) -> the caller's stream synchronisation -> report.
+static int enqueue_query_validation(bbq_index* ix, float* d_queries, uint32_t nq, cudaStream_t st) {
+  bbq_ctx* c = ix->ctx;
+  TRY(c->bad.reserve(sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(c->bad.p, 0xFF, sizeof(unsigned long long), st));
+  LAUNCH(c, k_validate_queries, (nq + 3) / 4, 128, 0, st, d_queries, (int)nq, (int)ix->dim,
+         c->cfg.similarity == BBQ_SIM_COSINE ? 1 : 0, c->bad.as<unsigned long long>());
+  return BBQ_OK;
+}
+static int finish_query_validation(bbq_ctx* c, cudaStream_t st, bool sync) {
+  CU(cudaMemcpyAsync(c->h_flag + QUERY_BATCH + 2, c->bad.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  if (sync) CU(cudaStreamSynchronize(st));
+  return BBQ_OK;
+}
+static int report_query_validation(bbq_ctx* c) {
+  unsigned long long v;
+  memcpy(&v, c->h_flag + QUERY_BATCH + 2, sizeof v);
+  if (v == ~0ull) return BBQ_OK;
+  const int64_t q = (int64_t)(v >> 34), pos = (int64_t)(v & 0xFFFFFFFFull);
+  if (((v >> 32) & 3ull) == 2ull) return fail(BBQ_ERR_INF, "vector contains Infinity", q, pos);
+  return fail(BBQ_ERR_NAN, "vector contains NaN", q, pos);
+}
+
 extern "C" int bbq_search(bbq_index* ix, const float* queries, uint32_t nq, int64_t k, int32_t* out_idx,
                           float* out_score, uint32_t* out_count) {
   if (out_count) *out_count = 0;
@@ -1112,14 +1166,6 @@ extern "C" int bbq_search(bbq_index* ix, const float* queries, uint32_t nq, int6
   if (k == 0 || nq == 0) return BBQ_OK;
   if (!out_idx || !out_score) return fail(BBQ_ERR_NULL, "output buffers must not be null");
   bbq_ctx* c = ix->ctx;
-  // scalarQuantize validates the (normalised) query: optimizedScalarQuantizer.ts:138-148
-  for (uint32_t q = 0; q < nq; q++) {
-    const int s = validate_rows(queries + (size_t)q * ix->dim, 1, ix->dim, c->cfg.similarity == BBQ_SIM_COSINE);
-    if (s != BBQ_OK) {
-      g_err_vec = q;
-      return s;
-    }
-  }
   const uint32_t kk = (uint32_t)std::min<int64_t>(k, (int64_t)ix->n);  // :385 k2 = min(k, vectorCount)
   if (kk > K_MAX) return fail(BBQ_ERR_UNSUPPORTED, "k > 4096 is not supported by the device top-k");
   CU(cudaSetDevice(c->device));
@@ -1127,7 +1173,11 @@ extern "C" int bbq_search(bbq_index* ix, const float* queries, uint32_t nq, int6
   TRY(c->out_idx.reserve((size_t)nq * kk * sizeof(int32_t)));
   TRY(c->out_score.reserve((size_t)nq * kk * sizeof(float)));
   CU(cudaMemcpyAsync(c->qrows.p, queries, (size_t)nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  // scalarQuantize validates the (normalised) query, optimizedScalarQuantizer.ts:138-148: done on the device, ahead
+  // of the search in the same stream (an offending query is zeroed), and read back at the one synchronisation below
+  TRY(enqueue_query_validation(ix, c->qrows.as<float>(), nq, c->stream));
   TRY(bbq_search_device(ix, c->qrows.as<float>(), nq, kk, c->out_idx.as<int32_t>(), c->out_score.as<float>(), c->stream));
+  TRY(finish_query_validation(c, c->stream, /*sync=*/false));
   // results are written with stride kk; the caller's rows have stride k
   if ((int64_t)kk == k) {
     CU(cudaMemcpyAsync(out_idx, c->out_idx.p, (size_t)nq * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -1139,6 +1189,7 @@ extern "C" int bbq_search(bbq_index* ix, const float* queries, uint32_t nq, int6
                          (size_t)kk * sizeof(float), nq, cudaMemcpyDeviceToHost, c->stream));
   }
   CU(cudaStreamSynchronize(c->stream));
+  TRY(report_query_validation(c));
   if (out_count) *out_count = kk;
   return BBQ_OK;
 }
@@ -1170,13 +1221,6 @@ extern "C" int bbq_search_rerank(bbq_index* ix, const float* queries, uint32_t n
   if (!out_idx || !out_qscore || !out_true) return fail(BBQ_ERR_NULL, "output buffers must not be null");
   if (factor == 0 || (uint64_t)k * factor > K_MAX) return fail(BBQ_ERR_UNSUPPORTED, "k * oversampleFactor must be in 1..4096");
   bbq_ctx* c = ix->ctx;
-  for (uint32_t q = 0; q < nq; q++) {
-    const int s = validate_rows(queries + (size_t)q * ix->dim, 1, ix->dim, c->cfg.similarity == BBQ_SIM_COSINE);
-    if (s != BBQ_OK) {
-      g_err_vec = q;
-      return s;
-    }
-  }
   const uint32_t m = (uint32_t)std::min<uint64_t>((uint64_t)k * factor, ix->n);  // candidates per query
   const uint32_t kk = std::min(k, m);
   CU(cudaSetDevice(c->device));
@@ -1189,7 +1233,9 @@ extern "C" int bbq_search_rerank(bbq_index* ix, const float* queries, uint32_t n
   TRY(c->rr_q.reserve((size_t)nq * kk * sizeof(float)));
   TRY(c->rr_t.reserve((size_t)nq * kk * sizeof(double)));
   CU(cudaMemcpyAsync(c->qrows.p, queries, (size_t)nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  TRY(enqueue_query_validation(ix, c->qrows.as<float>(), nq, st));
   TRY(bbq_search_device(ix, c->qrows.as<float>(), nq, m, c->out_idx.as<int32_t>(), c->out_score.as<float>(), st));
+  TRY(finish_query_validation(c, st, /*sync=*/false));
   {
     ProfScope prof(c, st, PROF_SELECT);
     const int64_t pairs = (int64_t)nq * m;
@@ -1211,6 +1257,7 @@ extern "C" int bbq_search_rerank(bbq_index* ix, const float* queries, uint32_t n
   TRY(copy_out(out_qscore, c->rr_q.p, sizeof(float)));
   TRY(copy_out(out_true, c->rr_t.p, sizeof(double)));
   CU(cudaStreamSynchronize(st));
+  TRY(report_query_validation(c));
   if (out_count) *out_count = kk;
   return BBQ_OK;
 }
@@ -1246,6 +1293,310 @@ extern "C" int bbq_merge_topk_device(bbq_ctx* c, const int32_t* d_idx, const flo
   CU(cudaMemcpyAsync(la_idx, d_idx, cnt * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   CU(cudaMemcpyAsync(la_score, d_score, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return merge_lists(c, la_idx, la_score, lb_idx, lb_score, lists, (int)nq, k, d_out_idx, d_out_score, st);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// sharded search: row shards on the GPUs of one box, one process / context / communicator per GPU;
+// per-shard top-k lists travel as 64-bit keys in ONE ncclAllGather over NVLink and are merged by k_select.
+// NCCL is dlopen'ed on first use so that a single-GPU host needs no NCCL installation.
+// ------------------------------------------------------------------------------------------------
+struct NcclApi {
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  decltype(&ncclGetVersion) GetVersion = nullptr;
+  std::string error;
+  bool ok = false;
+};
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = nullptr;
+    const char* names[] = {getenv("BBQ_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      if (nm && !h) h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    }
+    if (!h) {
+      api.error = std::string("cannot load NCCL (libnccl.so.2): ") + (dlerror() ? dlerror() : "not found");
+      return &api;
+    }
+#define BBQ_NCCL_SYM(field, name)                                            \
+  api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, name));        \
+  if (!api.field) {                                                          \
+    api.error = std::string("NCCL symbol missing: ") + name;                 \
+    return &api;                                                             \
+  }
+    BBQ_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    BBQ_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    BBQ_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    BBQ_NCCL_SYM(AllGather, "ncclAllGather")
+    BBQ_NCCL_SYM(AllReduce, "ncclAllReduce")
+    BBQ_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+    BBQ_NCCL_SYM(GetVersion, "ncclGetVersion")
+#undef BBQ_NCCL_SYM
+    api.ok = true;
+  }
+  return &api;
+}
+#define NC(expr)                                                                                        \
+  do {                                                                                                  \
+    ncclResult_t _r = (expr);                                                                           \
+    if (_r != ncclSuccess) return fail(BBQ_ERR_COMM, std::string(#expr) + ": " + nccl_api()->GetErrorString(_r)); \
+  } while (0)
+
+static void comm_release(bbq_ctx* c) {
+  if (c->comm) {
+    NcclApi* a = nccl_api();
+    if (a->ok) a->CommDestroy(c->comm);
+    c->comm = nullptr;
+  }
+}
+
+extern "C" int bbq_comm_unique_id(uint8_t* out_id) {
+  if (!out_id) return fail(BBQ_ERR_NULL, "null");
+  static_assert(sizeof(ncclUniqueId) == BBQ_COMM_ID_BYTES, "BBQ_COMM_ID_BYTES must equal sizeof(ncclUniqueId)");
+  NcclApi* a = nccl_api();
+  if (!a->ok) return fail(BBQ_ERR_COMM, a->error);
+  ncclUniqueId id;
+  NC(a->GetUniqueId(&id));
+  memcpy(out_id, &id, sizeof id);
+  return BBQ_OK;
+}
+
+extern "C" int bbq_comm_init(bbq_ctx* c, const uint8_t* id_bytes, int rank, int world) {
+  if (!c || !id_bytes) return fail(BBQ_ERR_NULL, "null");
+  if (world < 1 || rank < 0 || rank >= world) return fail(BBQ_ERR_INVALID_ARG, "rank/world out of range");
+  if (c->comm) return fail(BBQ_ERR_INVALID_ARG, "this context already has a communicator");
+  NcclApi* a = nccl_api();
+  if (!a->ok) return fail(BBQ_ERR_COMM, a->error);
+  CU(cudaSetDevice(c->device));
+  ncclUniqueId id;
+  memcpy(&id, id_bytes, sizeof id);
+  NC(a->CommInitRank(&c->comm, world, id, rank));
+  c->rank = rank;
+  c->world = world;
+  return BBQ_OK;
+}
+
+extern "C" int bbq_comm_destroy(bbq_ctx* c) {
+  if (!c) return fail(BBQ_ERR_NULL, "null");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  comm_release(c);
+  c->rank = 0;
+  c->world = 1;
+  return BBQ_OK;
+}
+
+extern "C" int bbq_comm_info(bbq_ctx* c, int* rank, int* world, int* nccl_version) {
+  if (!c) return fail(BBQ_ERR_NULL, "null");
+  if (rank) *rank = c->rank;
+  if (world) *world = c->comm ? c->world : 1;
+  if (nccl_version) {
+    *nccl_version = 0;
+    NcclApi* a = nccl_api();
+    if (c->comm && a->ok) a->GetVersion(nccl_version);
+  }
+  return BBQ_OK;
+}
+
+// rows over all shards (cached per index; one 8-byte all-reduce when the shard has grown)
+static int global_rows(bbq_index* ix, cudaStream_t st, uint64_t* out) {
+  bbq_ctx* c = ix->ctx;
+  if (!c->comm || c->world == 1) {
+    *out = ix->n;
+    return BBQ_OK;
+  }
+  if (ix->n_global_for != ix->n) {
+    TRY(c->nglob.reserve(2 * sizeof(unsigned long long)));
+    unsigned long long mine = ix->n, all = 0;
+    CU(cudaMemcpyAsync(c->nglob.p, &mine, sizeof mine, cudaMemcpyHostToDevice, st));
+    NC(nccl_api()->AllReduce(c->nglob.p, c->nglob.as<unsigned long long>() + 1, 1, ncclUint64, ncclSum, c->comm, st));
+    CU(cudaMemcpyAsync(&all, c->nglob.as<unsigned long long>() + 1, sizeof all, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ix->n_global = all;
+    ix->n_global_for = ix->n;
+  }
+  *out = ix->n_global;
+  return BBQ_OK;
+}
+
+extern "C" int bbq_search_sharded_device(bbq_index* ix, const float* d_queries, uint32_t nq, uint32_t k,
+                                         int32_t* d_out_idx, float* d_out_score, void* stream) {
+  if (!ix) return fail(BBQ_ERR_NULL, "target vector set must not be null");
+  if (!d_queries || !d_out_idx || !d_out_score) return fail(BBQ_ERR_NULL, "query vector must not be null");
+  if (nq == 0 || k == 0) return BBQ_OK;
+  if (k > K_MAX) return fail(BBQ_ERR_UNSUPPORTED, "k > 4096 is not supported by the device top-k");
+  bbq_ctx* c = ix->ctx;
+  if (!c->comm || c->world == 1) return bbq_search_device(ix, d_queries, nq, k, d_out_idx, d_out_score, stream);
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  const size_t cnt = (size_t)nq * k;
+  TRY(c->loc_idx.reserve(cnt * sizeof(int32_t)));
+  TRY(c->loc_score.reserve(cnt * sizeof(float)));
+  TRY(c->keys_local.reserve(cnt * sizeof(uint64_t)));
+  TRY(c->keys_all.reserve(cnt * sizeof(uint64_t) * (size_t)c->world));
+  TRY(bbq_search_device(ix, d_queries, nq, k, c->loc_idx.as<int32_t>(), c->loc_score.as<float>(), st));
+  {
+    ProfScope prof(c, st, PROF_SELECT);
+    LAUNCH(c, k_pack_keys, (unsigned)((cnt + 255) / 256), 256, 0, st, c->loc_idx.as<int32_t>(), c->loc_score.as<float>(),
+           (int64_t)cnt, c->keys_local.as<uint64_t>());
+  }
+  NC(nccl_api()->AllGather(c->keys_local.p, c->keys_all.p, cnt, ncclUint64, c->comm, st));
+  // merge: every rank selects the k best of world * k keys per query (identical result on every rank)
+  uint32_t lists = (uint32_t)c->world;
+  uint64_t* src = c->keys_all.as<uint64_t>();
+  const uint32_t group = std::max<uint32_t>(2u, (uint32_t)SELECT_MAX / k);
+  while (lists > group) {  // only for k * world > 16384: reduce groups of lists into keys_local-sized partials
+    const uint32_t ngroups = (lists + group - 1) / group;
+    TRY(c->lists_a.reserve((size_t)ngroups * cnt * sizeof(uint64_t)));
+    TRY(c->lists_b.reserve((size_t)ngroups * cnt * sizeof(uint64_t)));
+    uint64_t* dst = (src == c->lists_a.as<uint64_t>()) ? c->lists_b.as<uint64_t>() : c->lists_a.as<uint64_t>();
+    for (uint32_t g = 0; g < ngroups; g++) {
+      SelectParams s{};
+      s.nq = (int)nq;
+      s.k = k;
+      s.keys = src + (size_t)g * group * cnt;
+      s.lists = std::min(group, lists - g * group);
+      s.k_in = k;
+      s.out_keys = dst + (size_t)g * cnt;
+      TRY(launch_select<SEL_KLISTS>(c, s, s.lists * k, st));
+    }
+    src = dst;
+    lists = ngroups;
+  }
+  SelectParams s{};
+  s.nq = (int)nq;
+  s.k = k;
+  s.keys = src;
+  s.lists = lists;
+  s.k_in = k;
+  s.out_idx = d_out_idx;
+  s.out_score = d_out_score;
+  return launch_select<SEL_KLISTS>(c, s, lists * k, st);
+}
+
+extern "C" int bbq_search_sharded(bbq_index* ix, const float* queries, uint32_t nq, int64_t k, int32_t* out_idx,
+                                  float* out_score, uint32_t* out_count) {
+  if (out_count) *out_count = 0;
+  if (!queries) return fail(BBQ_ERR_NULL, "query vector must not be null");
+  if (!ix) return fail(BBQ_ERR_NULL, "target vector set must not be null");
+  if (k < 0) return fail(BBQ_ERR_NEGATIVE_K, "k must not be negative");
+  if (k == 0 || nq == 0) return BBQ_OK;
+  if (!out_idx || !out_score) return fail(BBQ_ERR_NULL, "output buffers must not be null");
+  bbq_ctx* c = ix->ctx;
+  CU(cudaSetDevice(c->device));
+  uint64_t n_all = 0;
+  TRY(global_rows(ix, c->stream, &n_all));
+  const uint32_t kk = (uint32_t)std::min<int64_t>(k, (int64_t)std::min<uint64_t>(n_all, 0x7FFFFFFFull));
+  if (kk > K_MAX) return fail(BBQ_ERR_UNSUPPORTED, "k > 4096 is not supported by the device top-k");
+  TRY(c->qrows.reserve((size_t)nq * ix->dim * sizeof(float)));
+  TRY(c->out_idx.reserve((size_t)nq * kk * sizeof(int32_t)));
+  TRY(c->out_score.reserve((size_t)nq * kk * sizeof(float)));
+  CU(cudaMemcpyAsync(c->qrows.p, queries, (size_t)nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  TRY(enqueue_query_validation(ix, c->qrows.as<float>(), nq, c->stream));
+  TRY(bbq_search_sharded_device(ix, c->qrows.as<float>(), nq, kk, c->out_idx.as<int32_t>(), c->out_score.as<float>(),
+                                c->stream));
+  TRY(finish_query_validation(c, c->stream, /*sync=*/false));
+  if ((int64_t)kk == k) {
+    CU(cudaMemcpyAsync(out_idx, c->out_idx.p, (size_t)nq * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(out_score, c->out_score.p, (size_t)nq * kk * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    CU(cudaMemcpy2DAsync(out_idx, (size_t)k * sizeof(int32_t), c->out_idx.p, (size_t)kk * sizeof(int32_t),
+                         (size_t)kk * sizeof(int32_t), nq, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpy2DAsync(out_score, (size_t)k * sizeof(float), c->out_score.p, (size_t)kk * sizeof(float),
+                         (size_t)kk * sizeof(float), nq, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  TRY(report_query_validation(c));
+  if (out_count) *out_count = kk;
+  return BBQ_OK;
+}
+
+// Page-locked host buffers for hosts that want the H2D / D2H copies of bbq_search* to run at full PCIe speed
+// (a Node host wraps them in external ArrayBuffers; any host pointer works, pageable memory is merely slower).
+extern "C" void* bbq_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    fail(BBQ_ERR_OOM, "cudaMallocHost failed");
+    return nullptr;
+  }
+  return p;
+}
+extern "C" void bbq_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// quantizeQueryVector / computeQuantizationAccuracy (the class members beside the search path)
+// ------------------------------------------------------------------------------------------------
+extern "C" int bbq_quantize_query(bbq_ctx* c, const float* query, const float* centroid, uint32_t dim, uint8_t* codes,
+                                  double* corr4) {
+  if (!c || !query || !centroid) return fail(BBQ_ERR_NULL, "null");
+  if (dim == 0) return fail(BBQ_ERR_INVALID_ARG, "dim must be > 0");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const int row_bytes = row_bytes_for(dim);
+  TRY(c->qrows.reserve((size_t)dim * sizeof(float)));
+  TRY(c->cenv.reserve((size_t)dim * sizeof(float)));
+  TRY(c->bad.reserve(sizeof(unsigned long long)));
+  CU(cudaMemcpyAsync(c->qrows.p, query, (size_t)dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(c->cenv.p, centroid, (size_t)dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  const bool cosine = c->cfg.similarity == BBQ_SIM_COSINE;
+  CU(cudaMemsetAsync(c->bad.p, 0xFF, sizeof(unsigned long long), st));
+  LAUNCH(c, k_validate_queries, 1, 128, 0, st, c->qrows.as<float>(), 1, (int)dim, cosine ? 1 : 0,
+         c->bad.as<unsigned long long>());
+  TRY(quantize_rows(c, c->qrows.as<float>(), 1, (int)dim, row_bytes, c->cenv.as<float>(), cosine ? 1 : 0, st));
+  if (codes) CU(cudaMemcpyAsync(codes, c->qcodes.p, dim, cudaMemcpyDeviceToHost, st));
+  if (corr4) CU(cudaMemcpyAsync(corr4, c->qcorr.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TRY(finish_query_validation(c, st, /*sync=*/true));
+  return report_query_validation(c);
+}
+
+extern "C" int bbq_quantization_accuracy(bbq_ctx* c, const float* rows, const float* queries, uint64_t n, uint32_t dim,
+                                         uint64_t target_ord, double* out5) {
+  if (!c || !out5) return fail(BBQ_ERR_NULL, "null");
+  if (n == 0 || !rows || !queries) return fail(BBQ_ERR_EMPTY, "vector sets must not be empty");
+  if (target_ord >= n) return fail(BBQ_ERR_INVALID_ARG, "target row out of range");
+  const uint32_t qb = c->cfg.query_bits;
+  // computeQuantizedScore, src/binaryQuantizedScorer.ts:78-97: only 1-bit and 4-bit queries
+  if (qb != 1 && qb != 4) return fail(BBQ_ERR_UNSUPPORTED, "unsupported query bits: only 1 and 4 (computeQuantizedScore)");
+  if (n > 0x7FFFFFF0ull) return fail(BBQ_ERR_UNSUPPORTED, "too many vectors");
+  bbq_index* ix = nullptr;
+  TRY(bbq_index_build(c, rows, n, dim, nullptr, &ix));   // 1. quantizeVectors(originalVectors), reference-order centroid
+  cudaStream_t st = c->stream;
+  const bool cosine = c->cfg.similarity == BBQ_SIM_COSINE;
+  int rc = [&]() -> int {
+    TRY(c->qrows.reserve((size_t)n * dim * sizeof(float)));
+    TRY(c->rr_q.reserve((size_t)dim * sizeof(float)));
+    TRY(c->rr_true.reserve((size_t)n * sizeof(double)));
+    TRY(c->rr_t.reserve((size_t)n * sizeof(double)));
+    TRY(c->cacc.reserve(5 * sizeof(double)));
+    CU(cudaMemcpyAsync(c->qrows.p, queries, (size_t)n * dim * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->rr_q.p, rows + target_ord * dim, (size_t)dim * sizeof(float), cudaMemcpyHostToDevice, st));
+    TRY(enqueue_query_validation(ix, c->qrows.as<float>(), (uint32_t)n, st));
+    // 2. quantizeQueryVector(query, centroid): ONE normalisation for COSINE (:271-299)
+    TRY(quantize_rows(c, c->qrows.as<float>(), (int)n, (int)dim, ix->row_bytes, ix->centroid, cosine ? 1 : 0, st));
+    LAUNCH(c, k_accuracy_scores, (unsigned)((n + RERANK_WARPS - 1) / RERANK_WARPS), RERANK_WARPS * 32, 0, st,
+           c->qcodes.as<uint8_t>(), ix->row_bytes * 8, c->qcorr.as<double>(), (int)n, qb == 1 ? 1 : 0,
+           ix->codes + target_ord * ix->row_bytes, ix->lower + target_ord, ix->upper + target_ord, ix->addc + target_ord,
+           ix->compsum + target_ord, c->qrows.as<float>(), c->rr_q.as<float>(), (int)dim, (int)c->cfg.similarity,
+           qb == 1 ? ix->cdp : 0.0, c->rr_true.as<double>(), c->rr_t.as<double>());
+    // 3. statistics (sequential sums, one thread: the reference's order)
+    LAUNCH(c, k_accuracy_stats, 1, 32, 0, st, c->rr_true.as<double>(), c->rr_t.as<double>(), (int64_t)n, c->cacc.as<double>());
+    CU(cudaMemcpyAsync(out5, c->cacc.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TRY(finish_query_validation(c, st, /*sync=*/true));
+    return report_query_validation(c);
+  }();
+  bbq_index_destroy(ix);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1291,4 +1642,40 @@ extern "C" int bbq_debug_qcdist(bbq_index* ix, const float* query, int32_t* out_
 }
 extern "C" int bbq_debug_scores(bbq_index* ix, const float* query, float* out_scores) {
   return debug_dense(ix, query, nullptr, out_scores);
+}
+
+// The tensor-core scan's integers: accumulator >> 3 of every (query, row) pair, through k_scan_mma<SCAN_DUMP>
+// (the popcount kernel is NOT involved) — the tap bbq_debug_qcdist lacks.  out_dots: [nq][n] int32, HOST.
+extern "C" int bbq_debug_qcdist_batch(bbq_index* ix, const float* queries, uint32_t nq, int32_t* out_dots) {
+  if (!ix || !queries || !out_dots) return fail(BBQ_ERR_NULL, "null");
+  if (nq == 0) return BBQ_OK;
+  bbq_ctx* c = ix->ctx;
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const int saved_engine = c->scan_engine;
+  c->scan_engine = 2;  // whatever the batch size: this tap exists to exercise tcgen05
+  MmaPlan pl;
+  const bool ok = mma_plan(ix, (int)nq, &pl);
+  c->scan_engine = saved_engine;
+  if (!ok) return fail(BBQ_ERR_UNSUPPORTED, "the tensor-core scan cannot run this configuration (queryBits > 5, dim > 4096 or > 4096 queries)");
+  TRY(c->qrows.reserve((size_t)nq * ix->dim * sizeof(float)));
+  CU(cudaMemcpyAsync(c->qrows.p, queries, (size_t)nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  TRY(quantize_queries(ix, c->qrows.as<float>(), (int)nq, st));
+  TRY(prepare_mma_operands(ix, (int)nq, pl, st));
+  TRY(ensure_bounds(ix, st));
+  const int64_t n = (int64_t)ix->n, ntiles = (n + TILE_ROWS - 1) / TILE_ROWS;
+  // a bounded scratch: tiles are dumped in groups and copied out row-range by row-range
+  const int64_t group_tiles = std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)(1ll << 28) / ((int64_t)nq * TILE_ROWS)));
+  const int64_t ld = group_tiles * TILE_ROWS;
+  TRY(c->dots.reserve((size_t)nq * ld * sizeof(int32_t)));
+  for (int64_t t0 = 0; t0 < ntiles; t0 += group_tiles) {
+    const int64_t tn = std::min(group_tiles, ntiles - t0);
+    const int64_t rows_here = std::min<int64_t>(tn * TILE_ROWS, n - t0 * TILE_ROWS);
+    TRY(launch_scan_mma(ix, SCAN_DUMP, (int)nq, 1, pl, t0, 1, tn, nullptr, ld, nullptr, nullptr, 0, nullptr, st,
+                        c->dots.as<int32_t>()));
+    CU(cudaMemcpy2DAsync(out_dots + t0 * TILE_ROWS, (size_t)n * sizeof(int32_t), c->dots.p, (size_t)ld * sizeof(int32_t),
+                         (size_t)rows_here * sizeof(int32_t), nq, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return BBQ_OK;
 }

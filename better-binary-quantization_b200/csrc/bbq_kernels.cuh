@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(TILE_ROWS, 4) k_scan_stream(const ScanParams p
 // (ordered f32 score << 32 | ~row id) in shared memory (bitonic, descending) and emits the k best —
 // the canonical form of the MinHeap loop, src/binaryQuantizationFormat.ts:383-411 / src/minHeap.ts.
 // ------------------------------------------------------------------------------------------------
-enum { SEL_DENSE = 0, SEL_KEYS = 1, SEL_PAIRS = 2 };
+enum { SEL_DENSE = 0, SEL_KEYS = 1, SEL_PAIRS = 2, SEL_KLISTS = 3 };
 
 struct SelectParams {
   int nq;
@@ -723,12 +723,14 @@ struct SelectParams {
   const uint64_t* keys;
   const uint32_t* cnt;
   uint32_t cap;
-  // SEL_PAIRS: lists x [nq][k_in] idx/score; idx < 0 = empty slot
+  // SEL_PAIRS: lists x [nq][k_in] idx/score; idx < 0 = empty slot.  SEL_KLISTS: the same lists as 64-bit keys
+  // (`keys` = [lists][nq][k_in], 0 = empty slot) — what the NCCL all-gather of the sharded search delivers
   const int32_t* in_idx;
   const float* in_score;
   uint32_t lists;
   uint32_t k_in;
   // outputs (any may be null)
+  uint64_t* out_keys; // [nq][k] the selected keys themselves (0 = empty slot)
   float* tau_out;     // [nq]: score of the k-th best, -inf if fewer than k keys
   int32_t* out_idx;   // [nq][k]
   float* out_score;   // [nq][k]
@@ -742,7 +744,7 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectParams p,
   uint32_t m;
   if (MODE == SEL_DENSE) m = p.m;
   else if (MODE == SEL_KEYS) m = min(p.cnt[q], p.cap);
-  else m = p.lists * p.k_in;
+  else m = p.lists * p.k_in;  // SEL_PAIRS, SEL_KLISTS
   // sort size: smallest power of two covering the keys and the k outputs (block-uniform)
   uint32_t m2 = 2;
   while (m2 < m || m2 < p.k) m2 <<= 1;
@@ -755,6 +757,9 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectParams p,
         key = bbqn::topk_key(p.scores[(int64_t)q * p.ld + i], id);
       } else if (MODE == SEL_KEYS) {
         key = p.keys[(size_t)q * p.cap + i];
+      } else if (MODE == SEL_KLISTS) {
+        const uint32_t l = i / p.k_in, j = i - l * p.k_in;
+        key = p.keys[((size_t)l * p.nq + q) * p.k_in + j];
       } else {
         const uint32_t l = i / p.k_in, j = i - l * p.k_in;
         const size_t off = ((size_t)l * p.nq + q) * p.k_in + j;
@@ -791,6 +796,8 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectParams p,
     }
     p.tau_out[q] = t;
   }
+  if (p.out_keys != nullptr)
+    for (uint32_t j = tid; j < p.k; j += SELECT_THREADS) p.out_keys[(size_t)q * p.k + j] = j < m2 ? keys_s[j] : 0ull;
   if (p.out_idx != nullptr) {
     for (uint32_t j = tid; j < p.k; j += SELECT_THREADS) {
       const uint64_t key = j < m2 ? keys_s[j] : 0ull;
@@ -874,7 +881,106 @@ __global__ void __launch_bounds__(256) k_rerank_select(const double* __restrict_
   }
 }
 
-// Input screening for the host build path (reference: binaryQuantizationFormat.ts:196-211) is done on
-// the host before upload; device-resident builds are the caller's responsibility.
+// Input screening of a query batch on the device (the reference validates inside scalarQuantize,
+// src/optimizedScalarQuantizer.ts:138-148, after the COSINE normalisation of src/binaryQuantizationFormat.ts:337):
+// one warp per query finds its first NaN / first Infinity.  COSINE: a NaN anywhere makes the normalised vector
+// all-NaN (reported at position 0); an Infinity makes the norm infinite, so the Infinity components become NaN
+// (reported as NaN at the first of them).  Otherwise the first non-finite component is reported as NaN or
+// Infinity.  The lowest offending query wins: bad[0] = min over queries of (query << 34 | status << 32 | position),
+// status 1 = NaN, 2 = Infinity (BBQ_ERR_NAN / BBQ_ERR_INF minus 4).  An offending query is then ZEROED in place so
+// that the search that is already enqueued behind this kernel runs on harmless input; the host reads bad[0] at its
+// one synchronisation point and reports the error instead of the results.
+__global__ void k_validate_queries(float* __restrict__ queries, int nq, int dim, int cosine,
+                                   unsigned long long* __restrict__ bad) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= nq) return;
+  float* v = queries + (int64_t)warp * dim;
+  uint32_t first_nan = 0xFFFFFFFFu, first_inf = 0xFFFFFFFFu;
+  for (int i = lane; i < dim; i += 32) {
+    const float x = v[i];
+    if (x != x) first_nan = min(first_nan, (uint32_t)i);
+    else if (fabsf(x) == INFINITY) first_inf = min(first_inf, (uint32_t)i);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    first_nan = min(first_nan, __shfl_xor_sync(0xffffffffu, first_nan, o));
+    first_inf = min(first_inf, __shfl_xor_sync(0xffffffffu, first_inf, o));
+  }
+  if (first_nan == 0xFFFFFFFFu && first_inf == 0xFFFFFFFFu) return;
+  uint32_t status, pos;
+  if (cosine) {
+    status = 1u;
+    pos = first_nan != 0xFFFFFFFFu ? 0u : first_inf;
+  } else if (first_nan < first_inf) {
+    status = 1u;
+    pos = first_nan;
+  } else {
+    status = 2u;
+    pos = first_inf;
+  }
+  if (lane == 0) atomicMin(bad, ((unsigned long long)warp << 34) | ((unsigned long long)status << 32) | pos);
+  for (int i = lane; i < dim; i += 32) v[i] = 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// computeQuantizationAccuracy on the device: src/binaryQuantizationFormat.ts:420-475 scores every
+// query against ONE target row (the reference uses row 0) twice — through the single-vector quantised scorer
+// (src/binaryQuantizedScorer.ts:69-98) and exactly (computeOriginalScore :430-448 -> src/vectorSimilarity.ts) — and
+// src/binaryQuantizedScorer.ts:524-617 reduces the two score arrays to error statistics.
+// k_accuracy_scores: one warp per query; the exact score's sums are sequential f64 (warp_seq_sums keeps the order).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RERANK_WARPS * 32) k_accuracy_scores(
+    const uint8_t* __restrict__ qcodes, int code_ld, const double* __restrict__ qcorr, int nq, int one_bit_query,
+    const uint8_t* __restrict__ row_codes, const double* __restrict__ lower, const double* __restrict__ upper,
+    const double* __restrict__ addc, const uint32_t* __restrict__ compsum, const float* __restrict__ queries,
+    const float* __restrict__ target_row, int dim, int sim, double cdp, double* __restrict__ orig_out,
+    double* __restrict__ quant_out) {
+  __shared__ double terms_s[RERANK_WARPS][6][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * RERANK_WARPS + warp;
+  if (q >= nq) return;
+  // quantised: qcDist = sum_d code[d] * bit_d(row)  (computeInt4BitDotProduct / computeInt1BitDotProduct on the
+  // unpacked row, src/bitwiseDotProduct.ts:41-55) — an integer, any order
+  const uint8_t* cd = qcodes + (int64_t)q * code_ld;
+  int dot = 0;
+  for (int i = lane; i < dim; i += 32) dot += (int)cd[i] * (int)((row_codes[i >> 3] >> (7 - (i & 7))) & 1);
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  // exact: computeSimilarity(query, originalVectors[target]) on the ORIGINAL (un-normalised) f32 vectors
+  const float* a = queries + (int64_t)q * dim;
+  double r[3];
+  warp_seq_sums<3>(dim, lane, terms_s[warp], [&](int i, double* t) {
+    const double av = (double)a[i], bv = (double)__ldg(target_row + i);
+    if (sim == bbqn::SIM_EUCLIDEAN) {
+      const double d = av - bv;
+      t[0] = d * d;
+      t[1] = t[2] = 0.0;
+    } else {
+      t[0] = av * bv;
+      t[1] = av * av;
+      t[2] = bv * bv;
+    }
+  }, r);
+  if (lane == 0) {
+    const double* c = qcorr + 4 * q;
+    quant_out[q] = bbqn::score_single_f64((double)dot, lower[0], upper[0], addc[0], (double)compsum[0], c[0], c[1], c[2],
+                                          c[3], (double)dim, cdp, sim, one_bit_query != 0);
+    double o;
+    if (sim == bbqn::SIM_EUCLIDEAN) o = 1.0 / (1.0 + sqrt(r[0]));                                  // vectorSimilarity.ts:38-67
+    else if (sim == bbqn::SIM_COSINE) o = (r[1] == 0 || r[2] == 0) ? 0.0 : r[0] / (sqrt(r[1]) * sqrt(r[2]));  // :75-102
+    else o = r[0];                                                                                 // :110-120
+    orig_out[q] = o;
+  }
+}
+__global__ void k_accuracy_stats(const double* __restrict__ orig, const double* __restrict__ quant, int64_t n,
+                                 double* __restrict__ out5) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) bbqn::accuracy_stats(orig, quant, n, out5);
+}
+
+// (idx, score) lists -> 64-bit selection keys (idx < 0 = empty slot = key 0): what a shard contributes to the
+// NCCL all-gather of the sharded search — 8 bytes per entry, one collective instead of two.
+__global__ void k_pack_keys(const int32_t* __restrict__ idx, const float* __restrict__ score, int64_t count,
+                            uint64_t* __restrict__ keys) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) keys[i] = idx[i] < 0 ? 0ull : bbqn::topk_key(score[i], (uint32_t)idx[i]);
+}
 
 }  // namespace bbqk

@@ -12,7 +12,7 @@
 //                  never touch shared memory;
 //   * D          = s32 accumulators in TMEM, double buffered: tcgen05.mma.kind::i8 (M=128, N<=224, K=32)
 //                  issued by one elected thread; exact integers (<= 15*8*dim, far below 2^31);
-//   * epilogue   = 4 warps read D with tcgen05.ld (thread = index row, columns = queries), screen every
+//   * epilogue   = 8 warps read D with tcgen05.ld (thread = index row, columns = queries), screen every
 //                  pair with a 4-FMA fp32 bound against the query's running k-th score, and replay the
 //                  reference's f64 corrective formula (src/batchDotProduct.ts:554-617) only for the pairs
 //                  the screen cannot exclude; survivors are appended to the per-query candidate lists.
@@ -362,6 +362,7 @@ struct MmaParams {
   // SCAN_DUMP: exact score of every pair -> dump[q*dump_ld + i*128 + row]
   float* dump;
   int64_t dump_ld;
+  int32_t* dots;           // optional parity tap: the integer dot (accumulator >> 3) of every pair, same layout as dump
   // SCAN_FILTER
   uint64_t* cand;
   uint32_t* cand_cnt;
@@ -369,8 +370,6 @@ struct MmaParams {
   uint32_t* overflow;
 };
 
-// The exact replay of one (row, query) pair the screen could not exclude — deliberately out of line: it runs
-// for ~0.1% of the pairs and must not bloat (or serialise) the branch-free screen loop.
 // The exact replay of one (row, query) pair the screen could not exclude — deliberately out of line: it runs for
 // ~0.1% of the pairs and must not bloat (or serialise) the branch-free screen loop.  `p` points at the kernel's
 // __grid_constant__ parameter block; the row's f64 correctives are fetched here, only when needed.
@@ -398,7 +397,7 @@ struct HitCtx {
   int nq, one_bit_query;
 };
 
-constexpr uint32_t RETIGHTEN_KMAX = 32;    // k up to which the running threshold is tightened inside the scan
+constexpr uint32_t RETIGHTEN_KMAX = 128;   // k up to which the running threshold is tightened inside the scan (k rounds over a 256-key window)
 constexpr uint32_t RETIGHTEN_EVERY = 16;   // ... once per this many appended candidates of a query
 constexpr uint32_t RETIGHTEN_ZCAP = 4096;  // leading slots of every candidate list that the host zeroes before a scan
 constexpr uint32_t HIT_RING = 512;         // CTA-wide ring of parked hits (8 B each)
@@ -873,10 +872,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
 #pragma unroll
               for (int j = 0; j < 16; j++) {
                 const int c = cc + j;
-                if (c < nv)
-                  p.dump[(int64_t)(q0 + c) * p.dump_ld + i * TILE_ROWS + r] =
-                      bbqn::score_f32((double)(cur[j] >> 3), rt.ax, rt.ux - rt.ax, rt.addx, (double)rt.x1, qt_s[c], p.dim,
-                                      p.cdp, SIM, p.one_bit_query != 0);
+                if (c < nv) {
+                  const int64_t off = (int64_t)(q0 + c) * p.dump_ld + i * TILE_ROWS + r;
+                  if (p.dump != nullptr)
+                    p.dump[off] = bbqn::score_f32((double)(cur[j] >> 3), rt.ax, rt.ux - rt.ax, rt.addx, (double)rt.x1,
+                                                  qt_s[c], p.dim, p.cdp, SIM, p.one_bit_query != 0);
+                  if (p.dots != nullptr) p.dots[off] = cur[j] >> 3;  // D = 8 * dot exactly (file header)
+                }
               }
             }
           } else {
@@ -932,7 +934,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
                 if (g1 >= 0.f) mask |= (1u << (2 * j + 1));
               }
             }
-            if (always) mask = 0xFFFFu;
+            if (always) mask = (nv - cc >= 16) ? 0xFFFFu : ((1u << (nv - cc)) - 1u);  // never a padding column: its query id would alias
             if (p.debug & 2u) mask = 0u;
             if (mask != 0u)  // park the hits for the drainer warp
               mma_park_hits(ring_s, ring_ctl_s + 0, ring_ctl_s + 1, mask, (uint32_t)row, q0 + cc, cur[0], cur[1], cur[2],

@@ -230,6 +230,73 @@ BBQ_HD float score_f32(double dot, double ax, double lx, double addx, double x1,
   return (float)r;
 }
 
+// src/utils.ts:171-176 scaleMaxInnerProductScore
+BBQ_HD double scale_mip(double s) { return (s < 0) ? 1 / (1 - s) : s + 1; }
+
+// One score as the SINGLE-VECTOR scorer computes it (computeQuantizedScore, src/binaryQuantizedScorer.ts:69-98:
+// computeOneBitSimilarityScore :112-160 / computeFourBitSimilarityScore :174-217) — the path
+// computeQuantizationAccuracy (src/binaryQuantizationFormat.ts:420-475) takes.  It is NOT the batch path's formula:
+// the result stays f64, MIP uses the plain scaleMaxInnerProductScore, and the caller passes centroidDP = c.c for
+// 1-bit queries but 0 for 4-bit queries (no originalQueryVector is given, :290).  lower/upper/add/sum as stored.
+BBQ_HD double score_single_f64(double dot, double ax, double ux, double addx, double x1, double ay, double uy,
+                               double addq, double y1, double dim, double cdp, int sim, bool one_bit_query) {
+  const double lx = ux - ax;
+  if (one_bit_query) {
+    const double ly = uy - ay;
+    double score = ax * ay * dim + ay * lx * x1 + ax * ly * y1 + lx * ly * dot;
+    if (sim == SIM_EUCLIDEAN) {
+      score = addq + addx - 2 * score;
+      return js_max(1 / (1 + score), 0.0);
+    }
+    score += addq + addx - cdp;
+    return (sim == SIM_COSINE) ? js_max((1 + score) / 2, 0.0) : scale_mip(score);
+  }
+  const double ly = (uy - ay) * (1.0 / 15.0);
+  const double score = ax * ay * dim + ay * lx * x1 + ax * ly * y1 + lx * ly * dot;
+  if (sim == SIM_EUCLIDEAN) {
+    const double e = addq + addx - 2 * score;
+    return js_max(1 / (1 + e), 0.0);
+  }
+  const double adjusted = score + addq + addx - cdp;
+  return (sim == SIM_MIP) ? scale_mip(adjusted) : js_max((1 + adjusted) / 2, 0.0);
+}
+
+// computeQuantizationAccuracy(originalScores, quantizedScores), src/binaryQuantizedScorer.ts:524-617: strictly
+// sequential f64 sums.  out5 = meanError, maxError, minError, stdError, correlation.
+BBQ_HD void accuracy_stats(const double* orig, const double* quant, int64_t n, double* out5) {
+  double sumError = 0, maxError = 0, minError = (double)INFINITY;
+  for (int64_t i = 0; i < n; i++) {
+    const double e = fabs(orig[i] - quant[i]);
+    sumError += e;
+    maxError = js_max(maxError, e);
+    minError = js_min(minError, e);
+  }
+  const double mean = sumError / (double)n;
+  double ss = 0;
+  for (int64_t i = 0; i < n; i++) {
+    const double d = fabs(orig[i] - quant[i]) - mean;
+    ss += d * d;
+  }
+  const double sd = sqrt(ss / (double)n);
+  double sx = 0, sy = 0, sxy = 0, sx2 = 0, sy2 = 0;
+  for (int64_t i = 0; i < n; i++) {
+    const double x = orig[i], y = quant[i];
+    sx += x;
+    sy += y;
+    sxy += x * y;
+    sx2 += x * x;
+    sy2 += y * y;
+  }
+  const double dn = (double)n;
+  const double num = dn * sxy - sx * sy;
+  const double den = sqrt((dn * sx2 - sx * sx) * (dn * sy2 - sy * sy));
+  out5[0] = mean;
+  out5[1] = maxError;
+  out5[2] = minError;
+  out5[3] = sd;
+  out5[4] = (den == 0) ? 0.0 : num / den;
+}
+
 // Total order used everywhere a top-k is taken: larger key = better.
 // (f32 score descending, row id ascending); NaN ranks below everything; -0 == +0.
 BBQ_HD uint64_t topk_key(float score, uint32_t id) {

@@ -236,18 +236,68 @@ class BinaryQuantizationFormat:
         return BinarizedByteVectorValues(self, h)
 
     # -- query side -------------------------------------------------------------------------------------
-    def quantizeQueryVector(self, queryVector, targetVectors: BinarizedByteVectorValues) -> dict:
-        """The reference signature takes the centroid; here the centroid lives with the device index, so the
-        index handle is passed instead.  NOTE: as in searchNearestNeighbors (:337 + :279) a COSINE query is
-        normalised twice."""
+    def quantizeQueryVector(self, queryVector, centroid) -> dict:
+        """src/binaryQuantizationFormat.ts:271-299.  With a centroid ARRAY (the reference signature) this is the class
+        member as written: a COSINE query is normalised once, then scalarQuantize(queryBits) (bbq_quantize_query).
+        With a device index handle instead of the centroid it is the query quantisation of the SEARCH path
+        (searchNearestNeighbors normalises at :337 and again at :279 — twice), the parity tap the tests compare."""
         q = np.ascontiguousarray(queryVector, np.float32)
         codes = np.empty(q.size, np.uint8)
         corr = np.empty(4, np.float64)
-        _check(_native.load().bbq_debug_quantize_query(targetVectors._h, q.ctypes.data, codes.ctypes.data,
-                                                       corr.ctypes.data), "search")
+        if isinstance(centroid, BinarizedByteVectorValues):
+            _check(_native.load().bbq_debug_quantize_query(centroid._h, q.ctypes.data, codes.ctypes.data,
+                                                           corr.ctypes.data), "search")
+        else:
+            cen = np.ascontiguousarray(centroid, np.float32)
+            if cen.size != q.size:
+                raise BbqError(4, "查询向量维度与目标向量维度不匹配")
+            _check(_native.load().bbq_quantize_query(self._ctx, q.ctypes.data, cen.ctypes.data, q.size,
+                                                     codes.ctypes.data, corr.ctypes.data), "search")
         return {"quantizedQuery": codes,
                 "queryCorrections": {"lowerInterval": corr[0], "upperInterval": corr[1],
                                      "additionalCorrection": corr[2], "quantizedComponentSum": corr[3]}}
+
+    def computeQuantizationAccuracy(self, originalVectors, queryVectors, targetOrd: int = 0) -> dict:
+        """src/binaryQuantizationFormat.ts:420-475 + src/binaryQuantizedScorer.ts:524-617 on the device
+        (bbq_quantization_accuracy): every query scored against row `targetOrd` (the reference: 0) through the
+        single-vector quantised scorer and exactly; -> {meanError, maxError, minError, stdError, correlation}."""
+        if originalVectors is None or len(originalVectors) == 0:
+            raise BbqError(3, "原始向量集合不能为空")
+        if queryVectors is None or len(queryVectors) == 0:
+            raise BbqError(3, "查询向量集合不能为空")
+        if len(originalVectors) != len(queryVectors):
+            raise BbqError(10, "原始向量集合和查询向量集合长度不匹配")
+        if self.config["queryBits"] not in (1, 4):   # computeQuantizedScore, src/binaryQuantizedScorer.ts:96
+            raise BbqError(9, f"不支持的查询位数: {self.config['queryBits']}，只支持1位和4位")
+        m, q = _as_matrix(originalVectors), _as_matrix(queryVectors)
+        if q.shape[1] != m.shape[1]:
+            raise BbqError(4, "向量维度不匹配")
+        out = np.empty(5, np.float64)
+        _check(_native.load().bbq_quantization_accuracy(self._ctx, m.ctypes.data, q.ctypes.data, m.shape[0], m.shape[1],
+                                                        targetOrd, out.ctypes.data), "build")
+        return dict(zip(("meanError", "maxError", "minError", "stdError", "correlation"), out.tolist()))
+
+    def serializeVectorData(self, vectors) -> dict:
+        """src/binaryQuantizationFormat.ts:483-525: quantise (on the device) and return the reference's
+        {vectorData: [VectorDataFormat], metadata: MetadataFormat} objects (src/types.ts:78-113).  binaryValues is
+        the packed MSB-first row (the reference re-packs an already packed row here, which yields ceil(P/8) bytes of
+        no use: the working form is kept).  For indexes that should reach a disk use saveIndex."""
+        qv = self.quantizeVectors(vectors)["quantizedVectors"]
+        packed, corr = qv.exportAll()
+        cen = qv.getCentroid()
+        data = [{"binaryValues": packed[i], "lowerInterval": corr[i, 0], "upperInterval": corr[i, 1],
+                 "additionalCorrection": corr[i, 2], "quantizedComponentSum": corr[i, 3]} for i in range(qv.size())]
+        meta = {"fieldNumber": 0, "vectorEncodingOrdinal": 0, "vectorSimilarityOrdinal": 0, "dimensions": int(cen.size),
+                "vectorDataOffset": 0, "vectorDataLength": 0, "vectorCount": qv.size(), "centroid": cen,
+                "centroidSquareMagnitude": qv.getCentroidDP()}
+        return {"vectorData": data, "metadata": meta}
+
+    def deserializeVectorData(self, vectorData, metadata) -> BinarizedByteVectorValues:
+        """src/binaryQuantizationFormat.ts:533-560: back to a (device-resident) BinarizedByteVectorValues."""
+        packed = np.stack([np.asarray(d["binaryValues"], np.uint8) for d in vectorData])
+        corr = np.array([[d["lowerInterval"], d["upperInterval"], d["additionalCorrection"],
+                          d["quantizedComponentSum"]] for d in vectorData], np.float64)
+        return self.adoptQuantized(packed, corr, metadata["centroid"])
 
     # -- search -----------------------------------------------------------------------------------------
     def searchNearestNeighbors(self, queryVector, targetVectors: BinarizedByteVectorValues, k: int) -> List[dict]:
@@ -315,6 +365,14 @@ class BinaryQuantizationFormat:
         _check(_native.load().bbq_debug_qcdist(targetVectors._h, q.ctypes.data, out.ctypes.data), "search")
         return out
 
+    def debugQcDistBatch(self, queries, targetVectors: BinarizedByteVectorValues) -> np.ndarray:
+        """The integer dots of the TENSOR-CORE scan (tcgen05 accumulators) for a query batch: int32 [nq, n]."""
+        qs = np.ascontiguousarray(queries, np.float32)
+        out = np.empty((qs.shape[0], targetVectors.size()), np.int32)
+        _check(_native.load().bbq_debug_qcdist_batch(targetVectors._h, qs.ctypes.data, qs.shape[0], out.ctypes.data),
+               "search")
+        return out
+
     def debugScores(self, queryVector, targetVectors: BinarizedByteVectorValues) -> np.ndarray:
         q = np.ascontiguousarray(queryVector, np.float32)
         out = np.empty(targetVectors.size(), np.float32)
@@ -341,6 +399,38 @@ class BinaryQuantizationFormat:
                      d_out_idx_ptr: int, d_out_score_ptr: int, stream: int = 0):
         _check(_native.load().bbq_search_device(targetVectors._h, d_queries_ptr, nq, k, d_out_idx_ptr,
                                                 d_out_score_ptr, stream or None), "search")
+
+    # -- sharded search: the exchange lives in the library (bbq_comm_*, one NCCL all-gather of 64-bit keys) -----
+    @staticmethod
+    def commUniqueId() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        _check(_native.load().bbq_comm_unique_id(buf))
+        return bytes(buf)
+
+    def commInit(self, comm_id: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(comm_id)
+        _check(_native.load().bbq_comm_init(self._ctx, buf, rank, world))
+
+    def commDestroy(self):
+        _check(_native.load().bbq_comm_destroy(self._ctx))
+
+    def commInfo(self) -> dict:
+        r, w, v = C.c_int(), C.c_int(), C.c_int()
+        _check(_native.load().bbq_comm_info(self._ctx, C.byref(r), C.byref(w), C.byref(v)))
+        return {"rank": r.value, "world": w.value, "nccl_version": v.value}
+
+    def searchShardedHost(self, h_queries_ptr: int, nq: int, targetVectors: BinarizedByteVectorValues, k: int,
+                          h_out_idx_ptr: int, h_out_score_ptr: int) -> int:
+        """bbq_search_sharded on raw HOST pointers (pinned or pageable); returns the per-query result count."""
+        cnt = C.c_uint32(0)
+        _check(_native.load().bbq_search_sharded(targetVectors._h, h_queries_ptr, nq, k, h_out_idx_ptr,
+                                                 h_out_score_ptr, C.byref(cnt)), "search")
+        return cnt.value
+
+    def searchShardedDevice(self, d_queries_ptr: int, nq: int, targetVectors: BinarizedByteVectorValues, k: int,
+                            d_out_idx_ptr: int, d_out_score_ptr: int, stream: int = 0):
+        _check(_native.load().bbq_search_sharded_device(targetVectors._h, d_queries_ptr, nq, k, d_out_idx_ptr,
+                                                        d_out_score_ptr, stream or None), "search")
 
     def mergeTopKDevice(self, d_idx_ptr: int, d_score_ptr: int, lists: int, nq: int, k: int, d_out_idx_ptr: int,
                         d_out_score_ptr: int, stream: int = 0):

@@ -1,9 +1,12 @@
 """Row-wise sharded search over the GPUs of one box: one process per GPU, each rank owns a
-contiguous row shard (global id = shard base + local row); a query batch is searched on every shard, the
-per-shard top-k lists are exchanged with ONE NCCL all_gather over NVLink (torch.distributed is plumbing
-only) and merged by the deterministic device merge (bbq_merge_topk_device), so the result is independent
-of the number of shards.  The reference has no counterpart (it is single-process); the merge rule is its
-MinHeap contract made canonical (src/binaryQuantizationFormat.ts:383-411)."""
+contiguous row shard (global id = shard base + local row).  The exchange lives IN THE LIBRARY: every rank calls
+bbq_search_sharded with the same query batch; the per-shard top-k lists travel as 64-bit (score, id) keys in ONE
+ncclAllGather over NVLink (the library dlopens NCCL and owns the communicator) and are merged by the device
+selection kernel, so the result is independent of the number of shards.  This file only bootstraps: rank 0 makes
+the communicator id (bbq_comm_unique_id) and it is broadcast over whatever the host already has — here
+torch.distributed (gloo or nccl), in a Node host a pipe or an environment variable.
+The reference has no counterpart (it is single-process); the merge rule is its MinHeap contract made canonical
+(src/binaryQuantizationFormat.ts:383-411)."""
 from __future__ import annotations
 
 import numpy as np
@@ -17,16 +20,26 @@ def shard_bounds(n_total: int, world: int, rank: int):
     return min(n_total, rank * per), min(n_total, (rank + 1) * per)
 
 
+def broadcast_comm_id(make_id, rank: int, world: int, group=None) -> bytes:
+    """Bootstrap only: rank 0's 128-byte communicator id to every rank through torch.distributed."""
+    import torch.distributed as dist
+    box = [make_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    return box[0]
+
+
 class ShardedSearcher:
     def __init__(self, fmt: BinaryQuantizationFormat, shard: BinarizedByteVectorValues, base: int, rank: int = 0,
                  world: int = 1, group=None):
         import torch
         from .. import _native
         self.torch = torch
-        self.fmt, self.shard, self.rank, self.world, self.group = fmt, shard, rank, world, group
+        self.fmt, self.shard, self.rank, self.world = fmt, shard, rank, world
         st = _native.load().bbq_index_set_base(shard._h, int(base))
         if st != 0:
             raise RuntimeError(_native.load().bbq_last_error().decode())
+        if world > 1:
+            fmt.commInit(broadcast_comm_id(fmt.commUniqueId, rank, world, group), rank, world)
         self.stream = torch.cuda.Stream()
         self._bufs = {}
 
@@ -35,11 +48,6 @@ class ShardedSearcher:
         if key not in self._bufs:
             t, dev = self.torch, "cuda"
             self._bufs = {key: dict(
-                dq=t.empty((nq, dim), dtype=t.float32, device=dev),
-                loc_idx=t.empty((nq, k), dtype=t.int32, device=dev),
-                loc_sc=t.empty((nq, k), dtype=t.float32, device=dev),
-                all_idx=t.empty((self.world, nq, k), dtype=t.int32, device=dev),
-                all_sc=t.empty((self.world, nq, k), dtype=t.float32, device=dev),
                 out_idx=t.empty((nq, k), dtype=t.int32, device=dev),
                 out_sc=t.empty((nq, k), dtype=t.float32, device=dev),
                 h_idx=t.empty((nq, k), dtype=t.int32, pin_memory=True),
@@ -48,35 +56,23 @@ class ShardedSearcher:
 
     def search_device(self, dq, k):
         """dq: [nq, dim] f32 CUDA tensor (replicated on every rank).  Returns (idx, score) CUDA tensors [nq, k];
-        enqueued on self.stream (the caller synchronises)."""
-        t = self.torch
+        enqueued on self.stream (the caller synchronises).  bbq_search_sharded_device: local scan, key pack,
+        ncclAllGather, merge — all inside the library."""
         nq, dim = dq.shape
         b = self._buffers(nq, k, dim)
-        s = self.stream.cuda_stream
-        with t.cuda.stream(self.stream):
-            if self.world == 1:
-                self.fmt.searchDevice(dq.data_ptr(), nq, self.shard, k, b["out_idx"].data_ptr(), b["out_sc"].data_ptr(), s)
-            else:
-                self.fmt.searchDevice(dq.data_ptr(), nq, self.shard, k, b["loc_idx"].data_ptr(), b["loc_sc"].data_ptr(), s)
-                t.distributed.all_gather_into_tensor(b["all_idx"], b["loc_idx"], group=self.group)
-                t.distributed.all_gather_into_tensor(b["all_sc"], b["loc_sc"], group=self.group)
-                self.fmt.mergeTopKDevice(b["all_idx"].data_ptr(), b["all_sc"].data_ptr(), self.world, nq, k,
-                                         b["out_idx"].data_ptr(), b["out_sc"].data_ptr(), s)
+        self.fmt.searchShardedDevice(dq.data_ptr(), nq, self.shard, k, b["out_idx"].data_ptr(), b["out_sc"].data_ptr(),
+                                     self.stream.cuda_stream)
         return b["out_idx"], b["out_sc"]
 
     def search(self, h_queries, k):
-        """End-to-end: pinned host queries -> device, sharded search + merge, results back to pinned host."""
-        t = self.torch
+        """End-to-end through the entry a host binds: bbq_search_sharded on HOST buffers (h_queries: a CPU tensor,
+        pinned for full-speed DMA; pageable works too).  The H2D copy of the queries, the search, the exchange and the
+        D2H copy of the results all happen inside the call."""
         nq, dim = h_queries.shape
         b = self._buffers(nq, k, dim)
-        with t.cuda.stream(self.stream):
-            b["dq"].copy_(h_queries, non_blocking=True)
-        oi, os_ = self.search_device(b["dq"], k)
-        with t.cuda.stream(self.stream):
-            b["h_idx"].copy_(oi, non_blocking=True)
-            b["h_sc"].copy_(os_, non_blocking=True)
-        self.stream.synchronize()
-        return b["h_idx"], b["h_sc"]
+        cnt = self.fmt.searchShardedHost(h_queries.data_ptr(), nq, self.shard, k, b["h_idx"].data_ptr(),
+                                         b["h_sc"].data_ptr())
+        return b["h_idx"][:, :cnt], b["h_sc"][:, :cnt]
 
 
 def merge_host(idx_lists, score_lists, k):

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BBQ_B200_ABI_VERSION 1
+#define BBQ_B200_ABI_VERSION 2
 
 typedef struct bbq_ctx bbq_ctx;     /* one GPU: stream, scratch, config          */
 typedef struct bbq_index bbq_index; /* device-resident index shard (a2 in SURVEY) */
@@ -56,7 +56,8 @@ typedef enum {
   /* runtime errors: never a silent fallback */
   BBQ_ERR_NO_DEVICE = 100,
   BBQ_ERR_CUDA = 101,
-  BBQ_ERR_OOM = 102
+  BBQ_ERR_OOM = 102,
+  BBQ_ERR_COMM = 103         /* NCCL could not be loaded / a collective failed (sharded search only)      */
 } bbq_status;
 
 /* src/types.ts:54-73 BinaryQuantizationConfig + QuantizerConfig; defaults src/index.ts:47-55,
@@ -151,6 +152,55 @@ int bbq_search(bbq_index* index, const float* queries, uint32_t nq, int64_t k, i
 int bbq_search_device(bbq_index* index, const float* d_queries, uint32_t nq, uint32_t k,
                       int32_t* d_out_idx, float* d_out_score, void* stream);
 
+/* -------- the class members beside the search path ------------------------------------------------------- */
+
+/* format.quantizeQueryVector(queryVector, centroid) — src/binaryQuantizationFormat.ts:271-299: COSINE normalises
+ * ONCE (the search path normalises a second time, :337), then scalarQuantize(queryBits) against `centroid`.
+ * codes: dim bytes; corr4: {lowerInterval, upperInterval, additionalCorrection, quantizedComponentSum}.  HOST. */
+int bbq_quantize_query(bbq_ctx* ctx, const float* query, const float* centroid, uint32_t dim, uint8_t* codes,
+                       double* corr4);
+
+/* format.computeQuantizationAccuracy(originalVectors, queryVectors) — src/binaryQuantizationFormat.ts:420-475 with
+ * the statistics of src/binaryQuantizedScorer.ts:524-617: quantises `rows` (n x dim, reference-order centroid), then
+ * for every query i scores it against row `target_ord` (the reference: 0) through the single-vector quantised scorer
+ * (src/binaryQuantizedScorer.ts:69-98; queryBits 1 or 4 only, else BBQ_ERR_UNSUPPORTED = its throw) and exactly
+ * (computeOriginalScore :430-448), and reduces |orig - quant| to out5 = {meanError, maxError, minError, stdError,
+ * correlation}.  rows and queries: n x dim each (the reference requires equal lengths).  HOST pointers. */
+int bbq_quantization_accuracy(bbq_ctx* ctx, const float* rows, const float* queries, uint64_t n, uint32_t dim,
+                              uint64_t target_ord, double* out5);
+
+/* -------- sharded search over the GPUs of one box ------------------------------------------ */
+
+/* The reference is single-process and has no counterpart; the model is its wasm surface, where ONE object owns build
+ * and search (rust-wasm/src/wasm_interface.rs:455-516).  One process / bbq_ctx / communicator per GPU: every rank
+ * builds (or loads) its contiguous row shard, sets its base (bbq_index_set_base), and calls bbq_search_sharded with
+ * the SAME query batch; the per-shard top-k lists travel as 64-bit (score, id) keys in one ncclAllGather over NVLink
+ * and every rank merges them with the canonical MinHeap rule of src/binaryQuantizationFormat.ts:383-411, so every
+ * rank returns the same lists, identical to a single-shard search of the whole corpus.
+ * Bootstrap: rank 0 calls bbq_comm_unique_id and ships the BBQ_COMM_ID_BYTES bytes to the other ranks by any means
+ * (pipe, file, env var, torch.distributed store ...); then every rank calls bbq_comm_init(ctx, id, rank, world).
+ * NCCL is loaded with dlopen("libnccl.so.2") on first use (override: env BBQ_NCCL_LIB); without it these entries
+ * return BBQ_ERR_COMM and everything else keeps working. */
+#define BBQ_COMM_ID_BYTES 128
+int bbq_comm_unique_id(uint8_t* out_id /* BBQ_COMM_ID_BYTES */);
+int bbq_comm_init(bbq_ctx* ctx, const uint8_t* id /* BBQ_COMM_ID_BYTES */, int rank, int world);
+int bbq_comm_destroy(bbq_ctx* ctx);
+int bbq_comm_info(bbq_ctx* ctx, int* rank, int* world, int* nccl_version);
+
+/* searchNearestNeighbors over ALL shards (same contract as bbq_search; *out_count = min(k, rows over all ranks)).
+ * HOST pointers; collective: every rank of the communicator must call it with the same queries, nq and k.
+ * Without a communicator (or world == 1) it is bbq_search. */
+int bbq_search_sharded(bbq_index* index, const float* queries, uint32_t nq, int64_t k, int32_t* out_idx,
+                       float* out_score, uint32_t* out_count);
+/* Device-resident variant (collective), like bbq_search_device. */
+int bbq_search_sharded_device(bbq_index* index, const float* d_queries, uint32_t nq, uint32_t k,
+                              int32_t* d_out_idx, float* d_out_score, void* stream);
+
+/* Page-locked host memory for query / result buffers (optional: any host pointer is accepted by bbq_search*, pinned
+ * ones make the copies asynchronous DMA).  A Node host wraps these in external ArrayBuffers. */
+void* bbq_host_alloc(size_t bytes);
+void bbq_host_free(void* p);
+
 /* -------- oversampled search + exact re-rank ---------------------------------------- */
 
 /* Keeps a copy of the ORIGINAL f32 rows next to the index (device memory, n*dim*4 bytes) for the exact re-rank.
@@ -181,6 +231,9 @@ int bbq_debug_quantize_query(bbq_index* index, const float* query, uint8_t* code
 /* computeBatchFourBitDotProductDirectPacked / computeBatchDotProductDirectPacked over the whole index:
  * out_dots n int32 — src/utils/computeBatchFourBitDotProductDirectPacked.ts:10-53, src/batchDotProduct.ts:22-49 */
 int bbq_debug_qcdist(bbq_index* index, const float* query, int32_t* out_dots);
+/* The same integers from the TENSOR-CORE scan (tcgen05 accumulators >> 3, k_scan_mma<SCAN_DUMP>) for a batch:
+ * out_dots [nq][n] int32, HOST.  BBQ_ERR_UNSUPPORTED where that engine cannot run (queryBits > 5, dim > 4096). */
+int bbq_debug_qcdist_batch(bbq_index* index, const float* queries, uint32_t nq, int32_t* out_dots);
 /* computeBatch{FourBit,OneBit}SimilarityScores + Float32Array store: out_scores n floats —
  * src/batchDotProduct.ts:478-541,554-617, src/binaryQuantizationFormat.ts:353,378 */
 int bbq_debug_scores(bbq_index* index, const float* query, float* out_scores);

@@ -505,4 +505,124 @@ void bbqo_qcdist_packed_planes(const uint8_t* qcodes, int query_bits, const uint
   }
 }
 
+// src/binaryQuantizationFormat.ts:271-299 ALONE (quantizeQueryVector called directly, e.g. by
+// computeQuantizationAccuracy :448): COSINE normalises ONCE, then scalarQuantize(queryBits).
+void bbqo_quantize_query_once(const float* q, const float* c, int d, int sim, int query_bits, double lambda,
+                              int iters, uint8_t* codes, double* corr4) {
+  std::vector<float> a(q, q + d), b(d);
+  if (sim == SIM_COSINE) {
+    normalize(a.data(), d, b.data());
+    a = b;
+  }
+  osq_quantize(a.data(), c, d, query_bits, sim, lambda, iters, codes, corr4);
+}
+
+// The single-vector scorer: computeQuantizedScore, src/binaryQuantizedScorer.ts:69-98 ->
+// computeOneBitSimilarityScore :112-160 (queryBits == 1) / computeFourBitSimilarityScore :174-217 (queryBits == 4).
+// Unlike the batch path: f64 result, plain scaleMaxInnerProductScore for MIP, centroidDP supplied by the caller
+// (getCentroidDP() = c.c for 1-bit :245; 0 for 4-bit when no original query is passed :290).
+double bbqo_score_single(double dot, const double xc[4], const double qc[4], int d, double cdp, int sim,
+                         int query_bits) {
+  const double x1 = xc[3], ax = xc[0], lx = xc[1] - ax, ay = qc[0], y1 = qc[3];
+  if (query_bits == 1) {
+    const double ly = qc[1] - ay;
+    double score = ax * ay * d + ay * lx * x1 + ax * ly * y1 + lx * ly * dot;
+    if (sim == SIM_EUCLIDEAN) {
+      score = qc[2] + xc[2] - 2 * score;
+      return js_max(1 / (1 + score), 0.0);
+    }
+    score += qc[2] + xc[2] - cdp;
+    return sim == SIM_COSINE ? js_max((1 + score) / 2, 0.0) : bbqo_scale_mip(score);
+  }
+  const double ly = (qc[1] - ay) * (1.0 / 15.0);
+  const double score = ax * ay * d + ay * lx * x1 + ax * ly * y1 + lx * ly * dot;
+  if (sim == SIM_EUCLIDEAN) {
+    const double e = qc[2] + xc[2] - 2 * score;
+    return js_max(1 / (1 + e), 0.0);
+  }
+  const double adjusted = score + qc[2] + xc[2] - cdp;
+  return sim == SIM_MIP ? bbqo_scale_mip(adjusted) : js_max((1 + adjusted) / 2, 0.0);
+}
+
+// computeSimilarity, src/vectorSimilarity.ts:15-31 -> :38-67 (1/(1+sqrt(sum (a-b)^2))), :75-102, :110-120
+double bbqo_similarity(const float* a, const float* b, int d, int sim) {
+  if (sim == SIM_COSINE) return bbqo_cosine(a, b, d);
+  double s = 0;
+  if (sim == SIM_EUCLIDEAN) {
+    for (int i = 0; i < d; i++) {
+      const double diff = (double)a[i] - (double)b[i];
+      s += diff * diff;
+    }
+    return 1.0 / (1.0 + std::sqrt(s));
+  }
+  for (int i = 0; i < d; i++) s += (double)a[i] * (double)b[i];
+  return s;
+}
+
+// BinaryQuantizedScorer.computeQuantizationAccuracy, src/binaryQuantizedScorer.ts:524-617 (+ computeStandardDeviation,
+// computePearsonCorrelation): out5 = meanError, maxError, minError, stdError, correlation.
+void bbqo_accuracy_stats(const double* orig, const double* quant, int64_t n, double* out5) {
+  std::vector<double> errors;
+  double sumError = 0, maxError = 0, minError = std::numeric_limits<double>::infinity();
+  for (int64_t i = 0; i < n; i++) {
+    const double e = std::fabs(orig[i] - quant[i]);
+    errors.push_back(e);
+    sumError += e;
+    maxError = js_max(maxError, e);
+    minError = js_min(minError, e);
+  }
+  const double mean = sumError / (double)errors.size();
+  double ss = 0;
+  for (double v : errors) {
+    const double diff = v - mean;
+    ss += diff * diff;
+  }
+  const double sd = std::sqrt(ss / (double)errors.size());
+  double sx = 0, sy = 0, sxy = 0, sx2 = 0, sy2 = 0;
+  for (int64_t i = 0; i < n; i++) {
+    sx += orig[i];
+    sy += quant[i];
+    sxy += orig[i] * quant[i];
+    sx2 += orig[i] * orig[i];
+    sy2 += quant[i] * quant[i];
+  }
+  const double dn = (double)n;
+  const double num = dn * sxy - sx * sy;
+  const double den = std::sqrt((dn * sx2 - sx * sx) * (dn * sy2 - sy * sy));
+  out5[0] = mean;
+  out5[1] = maxError;
+  out5[2] = minError;
+  out5[3] = sd;
+  out5[4] = den == 0 ? 0.0 : num / den;
+}
+
+// BinaryQuantizationFormat.computeQuantizationAccuracy, src/binaryQuantizationFormat.ts:420-475: quantise the rows,
+// then score EVERY query against row `target` (the reference: 0) through the single-vector scorer and exactly.
+// Returns 0, or -1 for a query width the single-vector scorer rejects (:96).  orig/quant (n each) may be null.
+int bbqo_quantization_accuracy(const float* rows, const float* queries, int64_t n, int d, int sim, int query_bits,
+                               double lambda, int iters, int64_t target, double* out5, double* orig_out,
+                               double* quant_out) {
+  if (query_bits != 1 && query_bits != 4) return -1;
+  std::vector<float> centroid(d);
+  std::vector<uint8_t> packed((size_t)n * ((d + 7) / 8)), unpacked((size_t)n * d);
+  std::vector<double> corr((size_t)n * 4);
+  bbqo_build_index(rows, n, d, sim, 1, lambda, iters, nullptr, centroid.data(), packed.data(), unpacked.data(),
+                   corr.data());
+  const double cdp = query_bits == 1 ? bbqo_centroid_dp(centroid.data(), d) : 0.0;
+  std::vector<double> orig(n), quant(n);
+  std::vector<uint8_t> qcodes(d);
+  double qc[4];
+  for (int64_t i = 0; i < n; i++) {
+    const float* q = queries + i * (int64_t)d;
+    bbqo_quantize_query_once(q, centroid.data(), d, sim, query_bits, lambda, iters, qcodes.data(), qc);
+    const int32_t dot = bbqo_dot_unpacked(qcodes.data(), unpacked.data() + target * (int64_t)d, d);
+    quant[i] = bbqo_score_single((double)dot, corr.data() + 4 * target, qc, d, cdp, sim, query_bits);
+    orig[i] = bbqo_similarity(q, rows + target * (int64_t)d, d, sim);
+  }
+  bbqo_accuracy_stats(orig.data(), quant.data(), n, out5);
+  if (orig_out) std::memcpy(orig_out, orig.data(), sizeof(double) * n);
+  if (quant_out) std::memcpy(quant_out, quant.data(), sizeof(double) * n);
+  return 0;
+}
+
 }  // extern "C"

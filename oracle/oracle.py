@@ -27,6 +27,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libbbq_oracle.so")
+_LIB_OVERRIDE = os.environ.get("BBQ_ORACLE_LIB")  # tools/sanitize.sh host: an ASan/UBSan build of the same source
 
 SIM = {"EUCLIDEAN": 0, "COSINE": 1, "MAXIMUM_INNER_PRODUCT": 2}
 
@@ -44,8 +45,9 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        build()
-        L = C.CDLL(_LIB_PATH)
+        if not _LIB_OVERRIDE:
+            build()
+        L = C.CDLL(os.path.abspath(_LIB_OVERRIDE) if _LIB_OVERRIDE else _LIB_PATH)
         f32p, u8p, f64p, i32p = (C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_double),
                                  C.POINTER(C.c_int32))
         L.bbqo_normalize.argtypes = [f32p, C.c_int, f32p]
@@ -76,6 +78,15 @@ def lib():
         L.bbqo_search.argtypes = [f32p, f32p, u8p, f64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double,
                                   C.c_int, C.c_int64, C.c_int, i32p, f32p, f32p, i32p]
         L.bbqo_search.restype = C.c_int64
+        L.bbqo_quantize_query_once.argtypes = [f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, u8p, f64p]
+        L.bbqo_score_single.argtypes = [C.c_double, f64p, f64p, C.c_int, C.c_double, C.c_int, C.c_int]
+        L.bbqo_score_single.restype = C.c_double
+        L.bbqo_similarity.argtypes = [f32p, f32p, C.c_int, C.c_int]
+        L.bbqo_similarity.restype = C.c_double
+        L.bbqo_accuracy_stats.argtypes = [f64p, f64p, C.c_int64, f64p]
+        L.bbqo_quantization_accuracy.argtypes = [f32p, f32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                                                 C.c_int64, f64p, f64p, f64p]
+        L.bbqo_quantization_accuracy.restype = C.c_int
         _lib = L
     return _lib
 
@@ -162,6 +173,43 @@ def quantize_query_vector(q, centroid, sim="COSINE", query_bits=4, lam=0.1, iter
     return codes, corr
 
 
+def quantize_query_vector_once(q, centroid, sim="COSINE", query_bits=4, lam=0.1, iters=5):
+    """format.quantizeQueryVector called directly (src/binaryQuantizationFormat.ts:271-299): ONE normalisation."""
+    q, centroid = _f32(q), _f32(centroid)
+    d = q.size
+    codes = np.empty(d, np.uint8)
+    corr = np.empty(4, np.float64)
+    lib().bbqo_quantize_query_once(_p(q, C.c_float), _p(centroid, C.c_float), d, SIM[sim], query_bits, lam, iters,
+                                   _p(codes, C.c_uint8), _p(corr, C.c_double))
+    return codes, corr
+
+
+def accuracy_stats(orig, quant):
+    """BinaryQuantizedScorer.computeQuantizationAccuracy, src/binaryQuantizedScorer.ts:524-617"""
+    orig = np.ascontiguousarray(orig, np.float64)
+    quant = np.ascontiguousarray(quant, np.float64)
+    out = np.empty(5, np.float64)
+    lib().bbqo_accuracy_stats(_p(orig, C.c_double), _p(quant, C.c_double), orig.size, _p(out, C.c_double))
+    return dict(zip(("meanError", "maxError", "minError", "stdError", "correlation"), out.tolist()))
+
+
+def compute_quantization_accuracy(rows, queries, sim="COSINE", query_bits=4, lam=0.1, iters=5, target=0,
+                                  want_scores=False):
+    """BinaryQuantizationFormat.computeQuantizationAccuracy, src/binaryQuantizationFormat.ts:420-475."""
+    rows, queries = _f32(rows), _f32(queries)
+    n, d = rows.shape
+    assert queries.shape == rows.shape
+    out = np.empty(5, np.float64)
+    orig, quant = np.empty(n, np.float64), np.empty(n, np.float64)
+    rc = lib().bbqo_quantization_accuracy(_p(rows, C.c_float), _p(queries, C.c_float), n, d, SIM[sim], query_bits,
+                                          lam, iters, target, _p(out, C.c_double), _p(orig, C.c_double),
+                                          _p(quant, C.c_double))
+    if rc != 0:
+        raise ValueError(f"不支持的查询位数: {query_bits}，只支持1位和4位")
+    stats = dict(zip(("meanError", "maxError", "minError", "stdError", "correlation"), out.tolist()))
+    return (stats, orig, quant) if want_scores else stats
+
+
 def qcdist_packed(qcodes, packed, d, planes=None):
     qcodes = np.ascontiguousarray(qcodes, np.uint8)
     packed = np.ascontiguousarray(packed, np.uint8)
@@ -172,6 +220,23 @@ def qcdist_packed(qcodes, packed, d, planes=None):
     else:
         lib().bbqo_qcdist_packed_planes(_p(qcodes, C.c_uint8), planes, _p(packed, C.c_uint8), n, d,
                                         _p(out, C.c_int32))
+    return out
+
+
+def qcdist_matrix(qcodes, packed, d, chunk=65536):
+    """qcDist for MANY queries at once, in numpy: out[q][v] = sum_d qcodes[q][d] * bit_d(x_v) — the same integer as
+    computeBatchFourBitDotProductDirectPacked (src/utils/computeBatchFourBitDotProductDirectPacked.ts:10-53: bit d of
+    row v is (byte[d>>3] >> (7-(d&7))) & 1).  A float32 matrix product is exact here: every partial sum is an
+    integer below 255 * d <= 2^24 for d <= 65793.  qcodes u8[nq, d], packed u8[n, ceil(d/8)] -> int32[nq, n]."""
+    qcodes = np.ascontiguousarray(qcodes, np.uint8)
+    packed = np.ascontiguousarray(packed, np.uint8)
+    assert 255 * d <= (1 << 24)
+    qf = qcodes[:, :d].astype(np.float32).T.copy()            # [d, nq]
+    n = packed.shape[0]
+    out = np.empty((qcodes.shape[0], n), np.int32)
+    for r0 in range(0, n, chunk):
+        bits = np.unpackbits(packed[r0:r0 + chunk], axis=1, bitorder="big")[:, :d].astype(np.float32)
+        out[:, r0:r0 + chunk] = (bits @ qf).T.astype(np.int32)
     return out
 
 

@@ -24,7 +24,9 @@ def test_shim_calls_only_declared_entry_points():
     assert called and called <= declared, called - declared
     # the path's entry points are all reachable from JavaScript
     for fn in ("bbq_create", "bbq_index_build", "bbq_search", "bbq_index_export", "bbq_index_attach_rows",
-               "bbq_search_rerank", "bbq_index_save", "bbq_index_load", "bbq_destroy", "bbq_index_destroy"):
+               "bbq_search_rerank", "bbq_index_save", "bbq_index_load", "bbq_destroy", "bbq_index_destroy",
+               "bbq_quantize_query", "bbq_quantization_accuracy", "bbq_index_from_quantized", "bbq_search_sharded",
+               "bbq_comm_unique_id", "bbq_comm_init", "bbq_index_set_base"):
         assert fn in called, fn
 
 
@@ -34,9 +36,41 @@ def test_typescript_class_uses_registered_addon_functions():
     ts = open(os.path.join(TS, "binaryQuantizationFormat.gpu.ts")).read()
     used = set(re.findall(r"\baddon\.([A-Za-z]+)\(", ts))
     assert used and used <= registered, used - registered
-    # the reference's public methods are all there (src/binaryQuantizationFormat.ts:165,308,583; src/types.ts:32-49)
-    for name in ("quantizeVectors", "searchNearestNeighbors", "getConfig", "dimension()", "size()", "getCentroid"):
-        assert name in ts, name
+    for name in ("dimension()", "size()", "getCentroid", "vectorValue", "getUnpackedVector", "getCorrectiveTerms"):
+        assert name in ts, name      # src/types.ts:32-49
+
+
+REFERENCE_CLASS = "/root/reference/src/binaryQuantizationFormat.ts"
+# the ten public members of the reference class, src/binaryQuantizationFormat.ts:141-601
+PUBLIC_MEMBERS = ["constructor", "quantizeVectors", "quantizeQueryVector", "searchNearestNeighbors",
+                  "computeQuantizationAccuracy", "serializeVectorData", "deserializeVectorData", "getConfig",
+                  "getQuantizer", "getScorer"]
+
+
+def test_typescript_class_keeps_every_public_member_of_the_reference():
+    """The replacement class must type-check wherever the reference class did (src/index.ts:133 calls
+    computeQuantizationAccuracy): it EXTENDS the reference class, overrides the members on the path with the
+    reference's exact signatures, and inherits the three accessors."""
+    ts = open(os.path.join(TS, "binaryQuantizationFormat.gpu.ts")).read()
+    assert re.search(r"export class BinaryQuantizationFormat extends ReferenceBinaryQuantizationFormat", ts)
+    assert "from './binaryQuantizationFormat.cpu'" in ts
+    overridden = set(re.findall(r"public override (\w+)\(", ts))
+    assert overridden == {"quantizeVectors", "quantizeQueryVector", "searchNearestNeighbors",
+                          "computeQuantizationAccuracy", "serializeVectorData", "deserializeVectorData"}
+    assert "constructor(config: BinaryQuantizationConfig)" in ts and "super(config)" in ts
+    inherited = set(PUBLIC_MEMBERS) - overridden - {"constructor"}
+    assert inherited == {"getConfig", "getQuantizer", "getScorer"}
+    if os.path.exists(REFERENCE_CLASS):   # (this container only; the GPU box has no /root/reference)
+        ref = open(REFERENCE_CLASS, encoding="utf-8").read()
+        body = ref[ref.index("export class BinaryQuantizationFormat"):]
+        ref_public = set(re.findall(r"^  public (\w+)\(", body, flags=re.M)) | {"constructor"}
+        assert ref_public == set(PUBLIC_MEMBERS), ref_public ^ set(PUBLIC_MEMBERS)
+        # same parameter lists as the reference for every overridden member
+        for name in overridden:
+            want = re.search(rf"public {name}\(([^)]*)\)", body, flags=re.S).group(1)
+            got = re.search(rf"public override {name}\(([^)]*)\)", ts, flags=re.S).group(1)
+            norm = lambda t: re.sub(r"\s+", "", t)
+            assert norm(got) == norm(want), (name, got, want)
 
 
 def test_error_table_covers_every_reference_status():

@@ -163,7 +163,7 @@ def test_c4_full_size_shard_invariance(bbq):
     assert np.array_equal(wi, wi2) and bits_equal(ws, ws2)           # determinism at full size
 
     # popcount engine over the same 100M rows for a few queries (a different kernel, same answer)
-    # (fewer than 64 queries take the popcount path in the same context)
+    # (fewer than 5 queries take the streaming popcount scan in the same context: mma_plan, csrc/bbq_api.cu)
     pi, ps = fm.searchBatch(qs[:4], whole, k)
     assert fm.stats()["last_engine"] == 1
     assert np.array_equal(pi, wi[:4]) and bits_equal(ps, ws[:4])

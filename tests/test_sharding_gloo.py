@@ -85,3 +85,35 @@ def test_merge_host_tie_rule():
     i2, s2 = np.array([[2, 7, 8]], np.int32), np.array([[5.0, 5.0, 1.0]], np.float32)
     mi, ms = bbq_b200.merge_host([i1, i2], [s1, s2], 4)
     assert mi.tolist() == [[2, 4, 7, 9]] and ms.tolist() == [[5.0, 5.0, 5.0, 3.0]]
+
+
+def _id_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        calls = []
+
+        def make_id():          # stands in for bbq_comm_unique_id (needs NCCL + a GPU): rank 0 only may call it
+            calls.append(rank)
+            return bytes(range(128))
+
+        cid = bbq_b200.broadcast_comm_id(make_id, rank, world)
+        out.put((rank, cid == bytes(range(128)), calls))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_comm_id_bootstrap_reaches_every_rank():
+    """The only thing torch.distributed does for the sharded search: ship rank 0's 128-byte communicator id."""
+    world = 3
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_id_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(out.get(timeout=5) for _ in range(world))
+    assert got == [(0, True, [0]), (1, True, []), (2, True, [])]

@@ -6,6 +6,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mma_issue_probe mma_issue_probe.cu && ./mma_issue_probe
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <cuda_runtime.h>
 
@@ -289,9 +290,24 @@ static void run_contention(long long* d) {
   }
 }
 
-int main() {
+int main(int argc, char** argv) {
   long long* d;
   CK(cudaMalloc(&d, (NMMA + 2) * sizeof(long long)));
+  if (argc > 1 && !strcmp(argv[1], "peak")) {
+    // bench.py's roofline denominator: the tcgen05.mma.kind::i8 rate of an otherwise idle SM (M=128, N=208, K=32,
+    // A in tensor memory — the shape k_scan_mma issues), 512 back-to-back MMAs per SM on all 148 SMs, in SM cycles
+    const int smem = 208 * 32 + 1024;
+    long long h[8] = {0};
+    for (int rep = 0; rep < 3; rep++) {
+      k_probe_contention<<<148, 512, smem>>>(208, 0, 0, 0, 0, d);
+      CK(cudaDeviceSynchronize());
+    }
+    CK(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    const double cyc = (double)h[1] / (double)h[2];
+    printf("{\"cycles_per_mma\": %.3f, \"m\": 128, \"n\": 208, \"k\": 32, \"int8_ops_per_cycle_per_sm\": %.1f, \"sms\": 148}\n",
+           cyc, 2.0 * 128 * 208 * 32 / cyc);
+    return 0;
+  }
   const int smem = 256 * 32 + 128 * 32 + 1024;
   CK(cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int ns[] = {112, 208, 256};
