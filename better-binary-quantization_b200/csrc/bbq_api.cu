@@ -81,7 +81,7 @@ struct bbq_ctx {
   DevBuf T, stage, cacc;
   // query scratch
   DevBuf qrows, qT, qcodes, qcorr, planes, qterms, tau, dump, cand, cand_cnt, flag, lists_a, lists_b,
-      out_idx, out_score, dots, images, qscreen, tau_bits, trace, rr_true, rr_idx, rr_q, rr_t, cenv;
+      out_idx, out_score, dots, images, qscreen, tau_bits, trace, rr_true, rr_idx, rr_q, rr_t, cenv, qoff, qenv;
   int64_t sample_tiles_dyn = 128;  // BBQ_SAMPLE_TILES: sample size when the running threshold is on
   int k1s_ctas = 4;         // BBQ_K1S_CTAS: persistent CTAs per SM of the streaming scan (huge = one tile per CTA)
   int csa = 1;              // BBQ_CSA=0: plain popcount accumulation in the streaming scan (A/B, tests)
@@ -220,7 +220,7 @@ static void ctx_release(bbq_ctx* c) {
   for (DevBuf* b : {&c->T, &c->stage, &c->cacc, &c->qrows, &c->qT, &c->qcodes, &c->qcorr, &c->planes, &c->qterms,
                     &c->tau, &c->dump, &c->cand, &c->cand_cnt, &c->flag, &c->lists_a, &c->lists_b, &c->out_idx,
                     &c->out_score, &c->dots, &c->images, &c->qscreen, &c->tau_bits, &c->trace, &c->rr_true, &c->rr_idx,
-                    &c->rr_q, &c->rr_t, &c->cenv, &c->keys_local, &c->keys_all, &c->loc_idx, &c->loc_score, &c->bad,
+                    &c->rr_q, &c->rr_t, &c->cenv, &c->qoff, &c->qenv, &c->keys_local, &c->keys_all, &c->loc_idx, &c->loc_score, &c->bad,
                     &c->nglob})
     b->release();
   comm_release(c);
@@ -806,6 +806,8 @@ static int prepare_mma_operands(bbq_index* ix, int nq, const MmaPlan& pl, cudaSt
   TRY(c->images.reserve(bytes));
   TRY(c->qscreen.reserve((size_t)pl.passes * pl.n_tile * sizeof(QScreen)));
   TRY(c->tau_bits.reserve((size_t)pl.passes * pl.n_tile * sizeof(uint32_t)));
+  TRY(c->qoff.reserve((size_t)pl.passes * pl.n_tile * sizeof(int32_t)));
+  TRY(c->qenv.reserve((size_t)pl.passes * sizeof(QEnv)));
   ProfScope prof(c, st, PROF_QUANT);
   const int64_t threads = (int64_t)pl.passes * pl.n_tile * (pl.kbytes / 16);
   LAUNCH(c, k_query_tiles, (unsigned)((threads + 255) / 256), 256, 0, st, c->qcodes.as<uint8_t>(), ix->row_bytes * 8, nq,
@@ -847,13 +849,17 @@ static int launch_scan_mma(bbq_index* ix, int mode, int nq, uint32_t k, const Mm
   p.images = c->images.as<uint8_t>();
   p.qscreen = c->qscreen.as<QScreen>();
   p.rscreen = ix->rscreen;
+  p.qoff = mode == SCAN_FILTER ? c->qoff.as<int32_t>() : nullptr;  // the dump (sample, taps) reads plain accumulators
+  p.qenv = mode == SCAN_FILTER ? c->qenv.as<QEnv>() : nullptr;
   p.tau_bits = c->tau_bits.as<uint32_t>();
   p.bounds = ix->bounds;
   p.k = c->dynamic_tau ? k : 0xFFFFFFFFu;
   p.debug = c->mma_debug;
   p.trace = nullptr;
-  if (c->mma_debug & 32u) {
+  if (c->mma_debug & (32u | 256u)) {
+    const bool fresh = c->trace.p == nullptr;
     TRY(c->trace.reserve(4 * 4096 * sizeof(long long)));
+    if (fresh) CU(cudaMemsetAsync(c->trace.p, 0, 4 * 4096 * sizeof(long long), st));
     p.trace = c->trace.as<long long>();
   }
   p.qterms = c->qterms.as<bbqn::QueryTerms>();
@@ -1062,10 +1068,9 @@ static int search_filtered(bbq_index* ix, int nq, uint32_t k, int32_t* d_out_idx
     if (use_mma) {
       {
         ProfScope prof(c, st, PROF_QUANT);
-        const int nq_pad = pl.passes * pl.n_tile;
-        LAUNCH(c, k_query_screen, (nq_pad + 127) / 128, 128, 0, st, c->qterms.as<bbqn::QueryTerms>(), c->tau.as<float>(),
-               nq, nq_pad, (double)ix->dim, ix->cdp, (int)c->cfg.similarity, c->cfg.query_bits == 1 ? 1 : 0, ix->bounds,
-               c->qscreen.as<QScreen>(), c->tau_bits.as<uint32_t>());
+        LAUNCH(c, k_query_screen, pl.passes, 256, 0, st, c->qterms.as<bbqn::QueryTerms>(), c->tau.as<float>(), nq,
+               pl.n_tile, (double)ix->dim, ix->cdp, (int)c->cfg.similarity, c->cfg.query_bits == 1 ? 1 : 0, ix->bounds,
+               c->qscreen.as<QScreen>(), c->tau_bits.as<uint32_t>(), c->qoff.as<int32_t>(), c->qenv.as<QEnv>());
       }
       // the running threshold reads candidate slots that may be reserved but not yet written: they must read as 0
       CU(cudaMemset2DAsync(p.cand, (size_t)CAND_CAP * sizeof(uint64_t), 0, (size_t)RETIGHTEN_ZCAP * sizeof(uint64_t), nq, st));

@@ -22,13 +22,30 @@
 // this lets one shift serve eight masks.  Requires code * 8 <= 255, i.e. queryBits <= 5.
 #pragma once
 #include <cuda_runtime.h>
+#include <climits>
 #include <cstdint>
 #include "bbq_kernels.cuh"
 
 namespace bbqk {
 
-constexpr int MMA_EPI_WARPS = 8;      // epilogue warps: two per TMEM lane quarter, alternating 16-column chunks
-constexpr int MMA_THREADS = (8 + MMA_EPI_WARPS) * 32;  // warp 0 B loader, 1-2 MMA issuers (2 also allocates TMEM), 3 drainer, 4-7 expansion, 8.. epilogue
+#ifndef BBQ_MMA_EPI_WARPS
+#define BBQ_MMA_EPI_WARPS 8
+#endif
+#ifndef BBQ_MMA_EXP_GROUPS
+#define BBQ_MMA_EXP_GROUPS 1
+#endif
+#ifndef BBQ_MMA_LDW
+#define BBQ_MMA_LDW 16
+#endif
+constexpr int MMA_LDW = BBQ_MMA_LDW;                // accumulator columns per epilogue TMEM load (16 or 32)
+static_assert(MMA_LDW == 16 || MMA_LDW == 32, "tcgen05.ld .x16 or .x32");
+constexpr int MMA_EPI_WARPS = BBQ_MMA_EPI_WARPS;    // epilogue warps: one or two per TMEM lane quarter, alternating 16-column chunks
+constexpr int MMA_EXP_GROUPS = BBQ_MMA_EXP_GROUPS;  // expansion groups of 4 warps (one warp per TMEM lane quarter), alternating hand-offs
+constexpr int MMA_EPI_WARP0 = 4 + 4 * MMA_EXP_GROUPS;
+// warp 0 B loader, 1-2 MMA issuers (2 also allocates TMEM), 3 drainer, 4.. expansion groups, then the epilogue
+constexpr int MMA_THREADS = (MMA_EPI_WARP0 + MMA_EPI_WARPS) * 32;
+static_assert(MMA_EPI_WARPS == 4 || MMA_EPI_WARPS == 8, "one or two epilogue warps per TMEM lane quarter");
+static_assert(MMA_EXP_GROUPS == 1 || MMA_EXP_GROUPS == 2, "one or two expansion groups");
 constexpr int MMA_N_MAX = 224;        // 2 accumulators + >= 2 A stages must fit the 512 TMEM columns
 constexpr int MMA_CHUNK_DIMS = 128;   // dims per A stage (32 TMEM columns)
 
@@ -40,11 +57,24 @@ struct __align__(16) QScreen {
   float negl;   // -(L - margin)
   float wadj;   // EUCLIDEAN: upper bound U + margin of (s - addx/2) — the pole 1+e = 0 — INDEPENDENT of tau; +inf otherwise
   float tau;
-  float pad0, pad1;
+  float negl0;  // negl at the sampled threshold — what the first-level offset qoff0 and the block envelope were made from
+  int qoff0;    // first-level offset at the sampled threshold (k_query_screen); the running one lives in MmaParams::qoff
 };
 
-struct IndexBounds {  // maxima over the shard's correctives, for the screen's error margin
+struct IndexBounds {  // maxima over the shard's correctives, for the screen's error margin ...
   float lx, ax, mv, wv;
+  // ... and the sums of the per-row screen constants (rv, x1, gv, iv) over the rows that have them, from which the
+  // "typical row" rho0 of the first-level screen is taken (any rho0 is valid; a central one is tight)
+  double sum[4];
+  unsigned long long cnt, pad;
+};
+
+// First-level screen, per resident query block (pass): see k_query_screen.
+struct __align__(16) QEnv {
+  float rho0[4];   // typical row constants (rv, x1, gv, iv)
+  float cbar[4];   // centre of the queries' threshold gradients
+  float hdev[4];   // max deviation of a query's gradient from cbar, rounded up
+  float pad[4];
 };
 
 // ---- small PTX wrappers ------------------------------------------------------------------------
@@ -136,6 +166,14 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32])
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&r)[16]) {
   asm volatile(
@@ -146,6 +184,19 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, int (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ldw(uint32_t taddr, int (&r)[16]) { tc_ld16(taddr, r); }
+__device__ __forceinline__ void tc_ldw(uint32_t taddr, int (&r)[32]) { tc_ld32(taddr, r); }
 __device__ __forceinline__ int tc_ld1(uint32_t taddr) {
   int r;
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
@@ -233,6 +284,8 @@ __global__ void k_index_bounds(const double* __restrict__ lower, const double* _
                                const double* __restrict__ addc, const uint32_t* __restrict__ compsum, int64_t n,
                                int sim, uint32_t* __restrict__ out4, float4* __restrict__ rscreen) {
   float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  unsigned long long cnt = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double ax = lower[i], lx = upper[i] - ax, ad = addc[i];
     float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -244,8 +297,14 @@ __global__ void k_index_bounds(const double* __restrict__ lower, const double* _
       const double inv = 1.0 / lx;
       const float rv = (float)(ax * inv), gv = (float)((sim == bbqn::SIM_EUCLIDEAN ? -0.5 * ad : ad) * inv),
                   iv = (float)inv;
-      if (bbqn::js_isfinite((double)rv) && bbqn::js_isfinite((double)gv) && bbqn::js_isfinite((double)iv) && iv > 0.f)
+      if (bbqn::js_isfinite((double)rv) && bbqn::js_isfinite((double)gv) && bbqn::js_isfinite((double)iv) && iv > 0.f) {
         rs = make_float4(rv, (float)compsum[i], gv, iv);
+        s0 += (double)rs.x;
+        s1 += (double)rs.y;
+        s2 += (double)rs.z;
+        s3 += (double)rs.w;
+        cnt++;
+      }
     }
     rscreen[i] = rs;
   }
@@ -255,11 +314,24 @@ __global__ void k_index_bounds(const double* __restrict__ lower, const double* _
     m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
     m3 = fmaxf(m3, __shfl_xor_sync(0xffffffffu, m3, o));
   }
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
   if ((threadIdx.x & 31) == 0) {  // non-negative floats order like their bit patterns
     atomicMax(out4 + 0, __float_as_uint(m0));
     atomicMax(out4 + 1, __float_as_uint(m1));
     atomicMax(out4 + 2, __float_as_uint(m2));
     atomicMax(out4 + 3, __float_as_uint(m3));
+    IndexBounds* b = reinterpret_cast<IndexBounds*>(out4);  // (the order of these additions only moves rho0: harmless)
+    atomicAdd(&b->sum[0], s0);
+    atomicAdd(&b->sum[1], s1);
+    atomicAdd(&b->sum[2], s2);
+    atomicAdd(&b->sum[3], s3);
+    atomicAdd(&b->cnt, cnt);
   }
 }
 
@@ -278,7 +350,8 @@ __device__ __forceinline__ QScreen make_qscreen(const bbqn::QueryTerms& t, float
   s.negl = INFINITY;  // admit everything unless a finite lower bound can be derived
   s.wadj = INFINITY;
   s.tau = tau;
-  s.pad0 = s.pad1 = 0.f;
+  s.negl0 = s.negl;
+  s.qoff0 = 0;
   const double tq = (double)tau;
   const double aq = t.ay * dim + t.ly * t.y1;
   double L = 0, W = INFINITY;
@@ -311,27 +384,125 @@ __device__ __forceinline__ QScreen make_qscreen(const bbqn::QueryTerms& t, float
       s.wadj = (W == INFINITY) ? INFINITY : __double2float_ru(U + margin_u);
     }
   }
+  s.negl0 = s.negl;
   return s;
 }
 
-__global__ void k_query_screen(const bbqn::QueryTerms* __restrict__ qterms, const float* __restrict__ tau, int nq,
-                               int nq_pad, double dim, double cdp, int sim, int one_bit_query,
-                               const IndexBounds* __restrict__ bounds, QScreen* __restrict__ out,
-                               uint32_t* __restrict__ tau_bits) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nq_pad) return;
-  if (q < nq) {
-    out[q] = make_qscreen(qterms[q], tau[q], dim, cdp, sim, one_bit_query, *bounds);
-    tau_bits[q] = (uint32_t)(bbqn::topk_key(tau[q], 0u) >> 32);
-  } else {  // padding column of the last query block: admits nothing
-    QScreen s;
-    s.ly8 = s.aq = s.ay = 0.f;
-    s.negl = -INFINITY;
-    s.wadj = INFINITY;
-    s.tau = INFINITY;
-    s.pad0 = s.pad1 = 0.f;
+// Per resident query block (= pass; one CTA each): the fp32 screen constants of every query (QScreen, second-level
+// screen) and the FIRST-LEVEL screen, an integer test on the accumulators themselves.
+//
+// In exact arithmetic on the fp32 constants the second-level test  g = negl*iv + ly8*D + rv*aq + x1*ay + gv >= 0
+// is  D >= theta_q(rho) = c_q . rho  with the row vector rho = (rv, x1, gv, iv) and the query's gradient
+// c_q = -(aq, ay, 1, negl) / ly8.  Around a typical row rho0 (the shard mean):  theta_q(rho) = b_q + c_q . (rho - rho0),
+// b_q = c_q . rho0, and for every query of the block  c_q . d >= cbar . d - sum_i hdev_i |d_i|.  So a pair can only
+// pass if   D + qoff[q]  >=  S(row) = cbar . d - hdev . |d|   (d = rho - rho0),  qoff[q] = -(floor(b_q) - 1),
+// an INTEGER test: the epilogue adds the (warp-uniform) offsets to the 16 accumulators of a chunk, takes the maximum
+// and compares it with the row's integer T = floor(S - guard) — 16 IADD + 8 VIMNMX3 + 1 ISETP for 16 pairs.
+// (Pre-loading the accumulators with qoff through tcgen05.st instead — so that the tensor core delivers D + qoff —
+// was built and measured: correct, but 2.2x slower; tensor-memory stores are the scarce resource while MMAs run.)
+// Only chunks that pass go on to the per-pair fp32 screen (about 1-2 % of them: the thresholds here are the SAMPLED
+// ones, constant during the scan; the running threshold acts at the second level).
+// qoff = +2^30: no usable bound for this query (always second level); -2^30: padding column (never passes).
+// COSINE and MAXIMUM_INNER_PRODUCT only: the EUCLIDEAN window is two-sided and too narrow for any block envelope.
+constexpr int QOFF_ALWAYS = 1 << 30;
+__global__ void __launch_bounds__(256) k_query_screen(const bbqn::QueryTerms* __restrict__ qterms,
+                                                      const float* __restrict__ tau, int nq, int n_tile, double dim,
+                                                      double cdp, int sim, int one_bit_query,
+                                                      const IndexBounds* __restrict__ bounds, QScreen* __restrict__ out,
+                                                      uint32_t* __restrict__ tau_bits, int32_t* __restrict__ qoff,
+                                                      QEnv* __restrict__ qenv) {
+  __shared__ double red_lo[4][8], red_hi[4][8];
+  __shared__ float cbar_s[4];
+  const int pass = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int q = pass * n_tile + t;
+  const bool live = t < n_tile;
+  QScreen s;
+  s.ly8 = s.aq = s.ay = 0.f;
+  s.negl = -INFINITY;  // padding column of the last query block: admits nothing
+  s.wadj = INFINITY;
+  s.tau = INFINITY;
+  s.negl0 = s.negl;
+  s.qoff0 = 0;
+  if (live) {
+    if (q < nq) {
+      s = make_qscreen(qterms[q], tau[q], dim, cdp, sim, one_bit_query, *bounds);
+      tau_bits[q] = (uint32_t)(bbqn::topk_key(tau[q], 0u) >> 32);
+    } else {
+      tau_bits[q] = 0xFFFFFFFFu;
+    }
+  }
+  float rho0[4] = {0.f, 0.f, 0.f, 1.f};
+  if (bounds->cnt > 0) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) rho0[i] = (float)(bounds->sum[i] / (double)bounds->cnt);
+  }
+  const bool has = live && q < nq && s.ly8 > 0.f && bbqn::js_isfinite((double)s.negl) &&
+                   bbqn::js_isfinite((double)s.aq) && bbqn::js_isfinite((double)s.ay);
+  double c[4] = {0, 0, 0, 0};
+  if (has) {
+    const double inv = 1.0 / (double)s.ly8;
+    c[0] = -(double)s.aq * inv;
+    c[1] = -(double)s.ay * inv;
+    c[2] = -inv;
+    c[3] = -(double)s.negl * inv;
+  }
+  // block-wide min / max of every gradient component over the queries that have one
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    double lo = has ? c[i] : INFINITY, hi = has ? c[i] : -INFINITY;
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) {
+      red_lo[i][warp] = lo;
+      red_hi[i][warp] = hi;
+    }
+  }
+  __syncthreads();
+  if (t < 4) {
+    double lo = INFINITY, hi = -INFINITY;
+    for (int w = 0; w < 8; w++) {
+      lo = fmin(lo, red_lo[t][w]);
+      hi = fmax(hi, red_hi[t][w]);
+    }
+    const float cb = (lo <= hi) ? (float)((lo + hi) / 2) : 0.f;
+    cbar_s[t] = bbqn::js_isfinite((double)cb) ? cb : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    double dev = has ? fabs(c[i] - (double)cbar_s[i]) : 0.0;
+    for (int o = 16; o > 0; o >>= 1) dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+    if (lane == 0) red_hi[i][warp] = dev;
+  }
+  __syncthreads();
+  if (t == 0) {
+    QEnv e;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      double dev = 0;
+      for (int w = 0; w < 8; w++) dev = fmax(dev, red_hi[i][w]);
+      e.rho0[i] = rho0[i];
+      e.cbar[i] = cbar_s[i];
+      e.hdev[i] = __double2float_ru(dev * (1.0 + 1e-6));
+      e.pad[i] = 0.f;
+    }
+    qenv[pass] = e;
+  }
+  if (live) {
+    int off = QOFF_ALWAYS;
+    if (q >= nq) {
+      off = -QOFF_ALWAYS;
+    } else if (has) {
+      const double b = c[0] * (double)rho0[0] + c[1] * (double)rho0[1] + c[2] * (double)rho0[2] + c[3] * (double)rho0[3];
+      const double fl = floor(b) - 1.0;  // one unit of slack for the f64 rounding of b itself
+      if (fabs(fl) < 1.0e9) off = -(int)fl;
+    }
+    qoff[q] = off;
+    s.negl0 = s.negl;
+    s.qoff0 = off;
     out[q] = s;
-    tau_bits[q] = 0xFFFFFFFFu;
   }
 }
 
@@ -353,6 +524,8 @@ struct MmaParams {
   long long* trace;        // BBQ_MMA_DEBUG bit 32: clock64 stamps of CTA 0's hand-offs (tools/mma_trace.py)
   uint32_t debug;          // profiling knobs (BBQ_MMA_DEBUG): 1 = epilogue skips the screen, 2 = hits are ignored, 4 = no TMEM loads, 32 = record the hand-off timeline
   const float4* rscreen;   // [n] per-row screen constants (k_index_bounds)
+  const int32_t* qoff;     // [passes * n_tile] per-query offsets of the first-level screen (nullptr in SCAN_DUMP)
+  const QEnv* qenv;        // [passes] first-level envelope of each resident query block
   const bbqn::QueryTerms* qterms;
   int nq, n_tile, passes, nstage;
   double dim, cdp;
@@ -395,6 +568,7 @@ struct HitCtx {
   const uint32_t* compsum;
   uint32_t cap, k, base;
   int nq, one_bit_query;
+  int32_t* qoff;   // running first-level offsets (nullptr: no first level)
 };
 
 constexpr uint32_t RETIGHTEN_KMAX = 128;   // k up to which the running threshold is tightened inside the scan (k rounds over a 256-key window)
@@ -473,6 +647,15 @@ __device__ void mma_retighten_warp(const HitCtx* cx, int q, int lane) {  // whol
       if (s.ly8 == dst->ly8 && s.aq == dst->aq && s.ay == dst->ay) {  // same query terms: only the bounds move
         dst->negl = fminf(dst->negl, s.negl);
         dst->tau = fmaxf(dst->tau, tnew);
+        // The first level follows: theta_q(rho) grows by delta * iv(row), delta = (negl0 - negl) / ly8 >= 0, and
+        // iv(row) >= 1 / max lx over the shard — so the integer offset may drop by floor(delta / lx_max), whatever
+        // the row (k_query_screen's envelope was built from negl0 and stays as it is).  One 32-bit atomicMin.
+        const int q0off = dst->qoff0;
+        if (cx->qoff != nullptr && q0off > -QOFF_ALWAYS && q0off < QOFF_ALWAYS && s.ly8 > 0.f && cx->bounds->lx > 0.f) {
+          const double delta = ((double)dst->negl0 - (double)s.negl) / (double)s.ly8;
+          const double drop = floor(delta / (double)cx->bounds->lx * (1.0 - 1.0e-6));
+          if (drop >= 1.0 && drop < 1.0e9) atomicMin(cx->qoff + q, q0off - (int)drop);
+        }
       }
     }
   }
@@ -541,7 +724,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
   float4* qpb_s = qpa_s + p.n_tile / 2;
   float2* qw_s = reinterpret_cast<float2*>(qpb_s + p.n_tile / 2);
   bbqn::QueryTerms* qt_s = reinterpret_cast<bbqn::QueryTerms*>(qw_s + p.n_tile / 2);  // DUMP mode only
-  uint64_t* bars = reinterpret_cast<uint64_t*>(qt_s + p.n_tile);
+  int32_t* qoff_s = reinterpret_cast<int32_t*>(qt_s + p.n_tile);   // [n_tile] this pass's first-level offsets (16 B aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(qoff_s + p.n_tile + 16);  // (+16: a 32-column load may straddle the end)
   uint64_t* a_full = bars;            // [8]
   uint64_t* a_empty = bars + 8;       // [8]
   uint64_t* acc_full = bars + 16;     // [2]
@@ -589,6 +773,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
     hit_s->base = p.base;
     hit_s->nq = p.nq;
     hit_s->one_bit_query = p.one_bit_query;
+    hit_s->qoff = const_cast<int32_t*>(p.qoff);
     ring_ctl_s[0] = ring_ctl_s[1] = ring_ctl_s[2] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -680,38 +865,61 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
   } else if (warp == 3) {
     // ===== drainer: exact replay of the parked hits, candidate append, threshold tightening =====
     if (MODE == SCAN_FILTER) mma_drain_ring<SIM>(hit_s, ring_s, ring_ctl_s + 0, ring_ctl_s + 1, ring_ctl_s + 2, lane);
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < MMA_EPI_WARP0) {
     // ===== expansion: packed 1-bit row -> weighted u8 A operand, straight into TMEM =====
-    // The (tile, chunk) sequence of a pass is walked as one flat stream so that the 16-byte packed chunks can
-    // be prefetched PF deep across tile boundaries (the loads come from HBM: ~1 us each if not in flight early).
-    const int r = (warp - 4) * 32 + lane;  // row within the tile == TMEM lane
+    // The (tile, chunk) sequence of a pass is one flat stream of chunks f = 0 .. total-1, handed over in PAIRS
+    // (both tcgen05.st in flight before the single wait::st); with two groups, pair h belongs to group h % 2.  Every
+    // group prefetches its own chunks PF deep across tile boundaries, and group 0 asks L2 for each row four tiles
+    // ahead (the 16-byte loads themselves come too late to hide an HBM round trip under a busy SM).
+    constexpr int G = MMA_EXP_GROUPS;
+    constexpr int CH = G == 1 ? 2 : 1;  // chunks per hand-off: a single group pairs them, two groups alternate single chunks
+    const int grp = (warp - 4) >> 2;
+    const int r = ((warp - 4) & 3) * 32 + lane;  // row within the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     constexpr int PF = 4;
+    constexpr int L2_AHEAD = 4;
     const int64_t my_tiles = (p.ntiles > blockIdx.x) ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t total = my_tiles * nchunks;
-    // cursor of the NEXT chunk to prefetch: tile ordinal + a row pointer that is recomputed once per tile
+    const int64_t hands = (total + CH - 1) / CH;  // hand-offs of the pass; hand-off h belongs to group h % G
+    // cursor of the NEXT chunk of this group to load: tile ordinal + chunk in tile + a row pointer per tile
     int64_t pf_tile = 0;
     int pf_kc = 0;
+    int pf_in = 0;                  // position of the cursor inside its hand-off (0 .. CH-1)
     const uint4* pf_ptr = nullptr;  // nullptr: the row lies past the end of the shard (zero chunks)
+    auto row_ptr = [&](int64_t t) -> const uint8_t* {
+      if (t >= my_tiles) return nullptr;
+      const int64_t row = (p.tile_first + (blockIdx.x + t * gridDim.x) * p.tile_stride) * TILE_ROWS + r;
+      return row < p.n ? p.codes + row * (int64_t)p.row_bytes : nullptr;
+    };
     auto pf_set_tile = [&]() {
-      pf_ptr = nullptr;
-      if (pf_tile < my_tiles) {
-        const int64_t row = (p.tile_first + (blockIdx.x + pf_tile * gridDim.x) * p.tile_stride) * TILE_ROWS + r;
-        if (row < p.n) pf_ptr = reinterpret_cast<const uint4*>(p.codes + row * (int64_t)p.row_bytes);
+      pf_ptr = reinterpret_cast<const uint4*>(row_ptr(pf_tile));
+      if (grp == 0 && !(p.debug & 128u)) {
+        const uint8_t* far = row_ptr(pf_tile + L2_AHEAD);
+        if (far != nullptr)
+          for (int b = 0; b < p.row_bytes; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(far + b));
       }
     };
-    auto load_next = [&]() -> uint4 {
+    auto pf_advance = [&](int k) {
+      pf_kc += k;
+      bool moved = false;
+      while (pf_kc >= nchunks) {
+        pf_kc -= nchunks;
+        pf_tile++;
+        moved = true;
+      }
+      if (moved) pf_set_tile();
+    };
+    auto load_next = [&]() -> uint4 {  // the chunk under the cursor; then on to this group's next chunk
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if (pf_ptr != nullptr) v = __ldg(pf_ptr + pf_kc);
-      if (++pf_kc == nchunks) {
-        pf_kc = 0;
-        pf_tile++;
-        pf_set_tile();
+      if (++pf_in == CH) {
+        pf_in = 0;
+        pf_advance((G - 1) * CH + 1);
+      } else {
+        pf_advance(1);
       }
       return v;
     };
-    // Two chunks per hand-off: both tcgen05.st are in flight before the single wait::st, and the second chunk
-    // is expanded while the first store travels — the store latency, not the ALU work, bounds this loop.
     auto expand = [&](const uint4& x, uint32_t (&e)[32]) {
       const uint32_t ws[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
@@ -728,46 +936,51 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
       mbar_wait_relaxed(a_empty + st_, ph_ ^ 1u);
       tc_fence_after();
     };
+    // (stage, phase) of the first chunk of this group's current hand-off; chunks are numbered through all passes
     uint32_t stage = 0, sphase = 0;
+    auto stage_inc = [&](uint32_t& st_, uint32_t& ph_) {
+      if (++st_ == (uint32_t)nstage) {
+        st_ = 0;
+        ph_ ^= 1u;
+      }
+    };
+    for (int k = 0; k < CH * grp; k++) stage_inc(stage, sphase);
     int exp_ev = 0;
     for (int pass = 0; pass < p.passes; pass++) {
       uint4 q[PF];
       pf_tile = 0;
       pf_kc = 0;
+      pf_in = 0;
       pf_set_tile();
+      pf_advance(CH * grp);
 #pragma unroll
       for (int i = 0; i < PF; i++) q[i] = load_next();
-      for (int64_t f0 = 0; f0 < total; f0 += PF) {
+      for (int64_t h0 = grp; h0 < hands; h0 += (PF / CH) * G) {
 #pragma unroll
-        for (int i = 0; i < PF; i += 2) {
-          if (f0 + i < total) {
-            const bool two = f0 + i + 1 < total;
+        for (int i = 0; i < PF; i += CH) {
+          const int64_t h = h0 + (i / CH) * G;  // this group's hand-off
+          if (h < hands) {
+            const bool two = CH == 2 && CH * h + 1 < total;
             const bool tr = (p.debug & 32u) && blockIdx.x == 0 && warp == 4 && lane == 0 && pass == 0 && exp_ev < 1000;
             long long x0 = tr ? clock64() : 0;
-            uint32_t e0[32], e1[32];
+            uint32_t e0[32];
             expand(q[i], e0);
             q[i] = load_next();
             const uint32_t s0 = stage, p0 = sphase;
-            if (++stage == (uint32_t)nstage) {
-              stage = 0;
-              sphase ^= 1u;
-            }
+            uint32_t s1 = stage, p1 = sphase;
+            stage_inc(s1, p1);
             long long x1 = tr ? clock64() : 0;
             wait_stage(s0, p0);
             long long x2 = tr ? clock64() : 0;
             tc_st32(lane_addr + a_col + s0 * 32u, e0);
-            uint32_t s1 = 0;
-            if (two) {
-              expand(q[i + 1], e1);
-              q[i + 1] = load_next();
-              s1 = stage;
-              const uint32_t p1 = sphase;
-              if (++stage == (uint32_t)nstage) {
-                stage = 0;
-                sphase ^= 1u;
+            if (CH == 2) {
+              uint32_t e1[32];
+              expand(q[(i + 1) % PF], e1);  // (a zero chunk when the stream ends on an odd count: loaded, never stored)
+              q[(i + 1) % PF] = load_next();
+              if (two) {
+                wait_stage(s1, p1);
+                tc_st32(lane_addr + a_col + s1 * 32u, e1);
               }
-              wait_stage(s1, p1);
-              tc_st32(lane_addr + a_col + s1 * 32u, e1);
             }
             long long x3 = tr ? clock64() : 0;
             tc_wait_st();
@@ -783,20 +996,38 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
               d[0] = x0; d[1] = x1; d[2] = x2; d[3] = x3; d[4] = x4; d[5] = clock64();
               exp_ev++;
             }
+            for (int k = 0; k < CH * G; k++) stage_inc(stage, sphase);  // on to this group's next hand-off
+          }
+        }
+      }
+      // chunk numbers run on through the passes: re-base this group's (stage, phase) for the next pass.  The loop
+      // above advanced it in steps of CH * G from CH * grp; the next pass starts at total + CH * grp.
+      {
+        const int64_t mine = hands > grp ? (hands - grp + G - 1) / G : 0;  // hand-offs this group handled
+        const int64_t at = CH * grp + mine * CH * G;                        // where the stepping left off
+        const int64_t want = total + CH * grp;                              // first chunk of the next pass
+        for (int64_t k = at; k < want; k++) stage_inc(stage, sphase);
+        for (int64_t k = want; k < at; k++) {  // (a few positions at most)
+          if (stage == 0u) {
+            stage = (uint32_t)nstage - 1u;
+            sphase ^= 1u;
+          } else {
+            stage--;
           }
         }
       }
     }
-  } else if (warp >= 8) {
-    // ===== epilogue: screen (fp32, branch-free over 16 queries) + exact replay (f64) + candidate append =====
-    const int ew = warp - 8;                       // 0 .. MMA_EPI_WARPS-1
+  } else if (warp >= MMA_EPI_WARP0) {
+    // ===== epilogue: first-level integer screen on the accumulators, second level + parking for what passes =====
+    const int ew = warp - MMA_EPI_WARP0;           // 0 .. MMA_EPI_WARPS-1
     const int quarter = ew & 3;                    // TMEM lane quarter this warp may touch (== warp % 4)
     const int sub = ew >> 2;                       // which of the quarter's warps: takes chunks sub, sub+NSUB, ...
     constexpr int NSUB = MMA_EPI_WARPS / 4;
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const int et = threadIdx.x - 256;              // 0 .. MMA_EPI_WARPS*32-1 within the epilogue group
+    const int et = threadIdx.x - MMA_EPI_WARP0 * 32;  // 0 .. MMA_EPI_WARPS*32-1 within the epilogue group
     uint32_t tcount = 0;
+    unsigned long long dbg_tested = 0ull, dbg_passed = 0ull, dbg_warps = 0ull;  // BBQ_MMA_DEBUG bit 256: first-level statistics
     for (int pass = 0; pass < p.passes; pass++) {
       // per-pass query constants -> shared memory (epilogue warps only: named barrier 1)
       asm volatile("bar.sync 1, %0;" ::"n"(MMA_EPI_WARPS * 32) : "memory");
@@ -814,7 +1045,20 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
           pb[2 + (c & 1)] = qs.negl;
           pw[c & 1] = qs.wadj;
         }
+        qoff_s[c] = p.qoff != nullptr ? p.qoff[q0 + c] : 0;
+        if (c < 16) qoff_s[p.n_tile + c] = -QOFF_ALWAYS;  // columns past the block: never pass
         if (MODE == SCAN_DUMP && c < nv) qt_s[c] = p.qterms[q0 + c];
+      }
+      // first-level envelope of this query block (registers; warp-uniform)
+      float e_r0 = 0.f, e_r1 = 0.f, e_r2 = 0.f, e_r3 = 1.f, e_c0 = 0.f, e_c1 = 0.f, e_c2 = 0.f, e_c3 = 0.f, e_h0 = 0.f,
+            e_h1 = 0.f, e_h2 = 0.f, e_h3 = 0.f;
+      if (MODE == SCAN_FILTER && p.qenv != nullptr) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.qenv + pass));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.qenv + pass) + 1);
+        const float4 h = __ldg(reinterpret_cast<const float4*>(p.qenv + pass) + 2);
+        e_r0 = a.x; e_r1 = a.y; e_r2 = a.z; e_r3 = a.w;
+        e_c0 = b.x; e_c1 = b.y; e_c2 = b.z; e_c3 = b.w;
+        e_h0 = h.x; e_h1 = h.y; e_h2 = h.z; e_h3 = h.w;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(MMA_EPI_WARPS * 32) : "memory");
       auto row_of = [&](int64_t ti) { return (p.tile_first + ti * p.tile_stride) * TILE_ROWS + r; };
@@ -833,9 +1077,24 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
         rs_next = load_rs(i + gridDim.x);
         const float rv = rs.x, x1f = rs.y, gv = rs.z, iv = rs.w;
         const bool always = valid && !(iv > 0.f);  // degenerate correctives: every pair goes to the exact replay
+        // first level: T = floor(cbar . d - hdev . |d| - guard), d = rho(row) - rho0; a pair can only pass the second
+        // level if its pre-loaded accumulator reaches T (see k_query_screen).  The guard covers the fp32 rounding of
+        // this very expression (a few ulp of each product; 2^-19 of their absolute sum is ample) plus one unit.
+        int T;
+        {
+          const float d0 = rv - e_r0, d1 = x1f - e_r1, d2 = gv - e_r2, d3 = iv - e_r3;
+          const float a0 = fabsf(d0), a1 = fabsf(d1), a2 = fabsf(d2), a3 = fabsf(d3);
+          const float S = fmaf(e_c0, d0, fmaf(e_c1, d1, fmaf(e_c2, d2, e_c3 * d3)));
+          const float H = fmaf(e_h0, a0, fmaf(e_h1, a1, fmaf(e_h2, a2, e_h3 * a3)));
+          const float A = fmaf(fabsf(e_c0), a0, fmaf(fabsf(e_c1), a1, fmaf(fabsf(e_c2), a2, fabsf(e_c3) * a3))) + H;
+          const float Sl = S - H - fmaf(A, 1.9073486328125e-06f, 1.0f);
+          T = (Sl > -1.0e9f && Sl < 1.0e9f) ? (int)floorf(Sl) : INT_MIN;  // NaN / out of range: everything passes on
+          if (!valid) T = INT_MAX;
+          if (always || MODE != SCAN_FILTER || p.qenv == nullptr || (p.debug & 64u)) T = INT_MIN;
+        }
+        const uint32_t l2flags = (always ? 1u : 0u) | ((p.debug & 1u) ? 2u : 0u) | ((p.debug & 2u) ? 4u : 0u);
         const uint64_t rv2 = f2_pack(rv, rv), x1f2 = f2_pack(x1f, x1f), gv2 = f2_pack(gv, gv), iv2 = f2_pack(iv, iv);
-        const uint64_t neg2 = f2_pack(-1.f, -1.f);
-        // f64 correctives: issued now, consumed only by the (rare) exact replays, so their latency stays hidden
+        // f64 correctives: issued now, consumed only by the dump
         RowTerms rt{0.0, 0.0, 0.0, 0u};
         if (MODE == SCAN_DUMP && valid) {
           rt.ax = __ldg(p.lower + row);
@@ -847,30 +1106,33 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
         mbar_wait(acc_full + buf, bphase);
         tc_fence_after();
         const uint32_t d_addr = lane_addr + buf * (uint32_t)p.n_tile;
-        // this tile's refresh of the (possibly tightened) screen constants: loads issued now, stored after the tile
+        // this tile's refresh of the (possibly tightened) second-level constants: loads issued now, stored after the tile
+        constexpr int ET = MMA_EPI_WARPS * 32;  // 128 or 256 threads refresh up to 224 queries: one or two each
         const bool refresh = MODE == SCAN_FILTER && p.k <= RETIGHTEN_KMAX && et < nv;
-        float4 fr0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool refresh2 = MODE == SCAN_FILTER && p.k <= RETIGHTEN_KMAX && ET < MMA_N_MAX && et + ET < nv;
+        float4 fr0 = make_float4(0.f, 0.f, 0.f, 0.f), fr1 = fr0;
+        int fo0 = 0, fo1 = 0;
         if (refresh) fr0 = __ldcg(reinterpret_cast<const float4*>(p.qscreen + q0 + et));
+        if (refresh2) fr1 = __ldcg(reinterpret_cast<const float4*>(p.qscreen + q0 + et + ET));
+        if (refresh && p.qoff != nullptr) fo0 = __ldcg(p.qoff + q0 + et);
+        if (refresh2 && p.qoff != nullptr) fo1 = __ldcg(p.qoff + q0 + et + ET);
         // software pipeline over this warp's 16-column chunks: the next chunk's TMEM load is in flight while the
-        // current one is screened
-        int acc[16], nxt[16];
-        int c0 = sub * 16;
+        // current one is reduced; the chunk just read is re-armed for the tile two positions ahead
+        constexpr int W = MMA_LDW;
+        int acc[W], nxt[W];
+        int c0 = sub * W;
         if (c0 < nv) {
-          tc_ld16(d_addr + (uint32_t)c0, acc);
+          tc_ldw(d_addr + (uint32_t)c0, acc);
           tc_wait_ld();
         }
         if (p.debug & 4u) c0 = nv;
-        // One 16-query chunk: prefetch the next chunk into `nx`, screen `cur`.  The fast path only asks whether ANY of
-        // the 16 pairs may reach the top-k — a max reduction (one 3-input FMNMX per query pair) instead of a compare,
-        // a select and an add per query; the 16-bit mask is built only when something passes (about 5 % of the
-        // chunks).  A NaN (e.g. a row past the end of the shard) loses every max and so compares false, as before.
-        auto chunk = [&](int (&cur)[16], int (&nx)[16], int cc) -> bool {
-          const int c1 = cc + NSUB * 16;
-          if (c1 < nv) tc_ld16(d_addr + (uint32_t)c1, nx);
+        auto chunk = [&](int (&cur)[W], int (&nx)[W], int cc) -> bool {
+          const int c1 = cc + NSUB * W;
+          if (c1 < nv) tc_ldw(d_addr + (uint32_t)c1, nx);
           if (MODE == SCAN_DUMP) {
             if (valid) {
 #pragma unroll
-              for (int j = 0; j < 16; j++) {
+              for (int j = 0; j < W; j++) {
                 const int c = cc + j;
                 if (c < nv) {
                   const int64_t off = (int64_t)(q0 + c) * p.dump_ld + i * TILE_ROWS + r;
@@ -882,51 +1144,49 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
               }
             }
           } else {
-            // EUCLIDEAN keeps the direct mask: its two-sided window passes often enough that the second evaluation
-            // costs more than the compares it saves (same-box A/B: C3 0.981 vs 0.996 ms); COSINE / MIP: C4 88.4 -> 84.9 ms
-            constexpr bool ANYHIT = SIM != bbqn::SIM_EUCLIDEAN;
-            float any = -INFINITY;
-            uint32_t mask = 0u;
-            if (!(p.debug & 1u)) {
+            // Second level (EUCLIDEAN: the only level): the packed fp32 screen of every pair of the chunk against the
+            // query's CURRENT threshold — 4 FFMA2 (+ 1 FMUL2 + 1 FADD2 for the EUCLIDEAN window) per two pairs.
+            // EUCLIDEAN has no first level: its admission window is TWO-sided (the pole 1 + e = 0) and, on the corpora
+            // this path meets, only a few accumulator units wide in the dense part of the distribution — no envelope
+            // over a block of queries is that sharp (measured: a one-sided first level passes 88 % of the chunks).
+            bool go = true;
+            if (SIM != bbqn::SIM_EUCLIDEAN) {
+              // first level: max_j (8*dot_j + qoff_j) against the row's T; the 16 offsets are warp-uniform (4 broadcast
+              // LDS.128).  A warp goes on if ANY of its 32 rows passes, so the per-row rate has to be well below 1/32:
+              // the offsets follow the running threshold (mma_retighten_warp), not just the sampled one.
+              const int4* o4 = reinterpret_cast<const int4*>(qoff_s + cc);
+              int mm[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};  // four independent VIMNMX3 chains
 #pragma unroll
-              for (int j = 0; j < 8; j++) {  // two queries per step
-                const int pj = (cc >> 1) + j;
-                const float4 qa = qpa_s[pj], qb = qpb_s[pj];
-                // f0 = (s + c*addx) / lx for the two queries; lower test: f0 + negl/lx >= 0; EUCLIDEAN upper: f0 <= wadj/lx
-                uint64_t t = f2_fma(x1f2, f2_pack(qb.x, qb.y), gv2);
-                t = f2_fma(rv2, f2_pack(qa.z, qa.w), t);
-                const uint64_t f0 = f2_fma(f2_pack(qa.x, qa.y), f2_pack((float)cur[2 * j], (float)cur[2 * j + 1]), t);
-                float g0, g1;
-                f2_unpack(f2_fma(f2_pack(qb.z, qb.w), iv2, f0), g0, g1);
-                if (SIM == bbqn::SIM_EUCLIDEAN) {
-                  const float2 w = qw_s[pj];
-                  float d0, d1;
-                  f2_unpack(f2_sub(f2_mul(f2_pack(w.x, w.y), iv2), f0), d0, d1);  // wadj * iv - f0
-                  g0 = fminf(g0, d0);
-                  g1 = fminf(g1, d1);
-                }
-                if (ANYHIT) {
-                  any = f_max3(any, g0, g1);
-                } else {
-                  if (g0 >= 0.f) mask |= (1u << (2 * j));
-                  if (g1 >= 0.f) mask |= (1u << (2 * j + 1));
-                }
+              for (int g = 0; g < W / 4; g++) {
+                const int4 o = o4[g];
+                mm[g & 3] = max(max(mm[g & 3], cur[4 * g] + o.x), cur[4 * g + 1] + o.y);
+                mm[(g + 2) & 3] = max(max(mm[(g + 2) & 3], cur[4 * g + 2] + o.z), cur[4 * g + 3] + o.w);
+              }
+              const int m = max(max(mm[0], mm[1]), max(mm[2], mm[3]));
+              go = m >= T;
+              if (p.debug & 256u) {
+                dbg_tested++;
+                dbg_passed += go ? 1ull : 0ull;
+                const bool any_go = __any_sync(0xffffffffu, go);  // (every lane votes: no short-circuit around it)
+                dbg_warps += (lane == 0 && any_go) ? 1ull : 0ull;
               }
             }
-            if (ANYHIT && any >= 0.f) {  // rare: which of the 16?
+            uint32_t mask = 0u;
+            if (go && !(p.debug & 1u)) {
 #pragma unroll
-              for (int j = 0; j < 8; j++) {
+              for (int j = 0; j < W / 2; j++) {  // two queries per step
                 const int pj = (cc >> 1) + j;
                 const float4 qa = qpa_s[pj], qb = qpb_s[pj];
+                // f0 = (s + c*addx) / lx for the two queries; lower test: f0 + negl/lx >= 0; upper: f0 <= wadj/lx
                 uint64_t t = f2_fma(x1f2, f2_pack(qb.x, qb.y), gv2);
                 t = f2_fma(rv2, f2_pack(qa.z, qa.w), t);
                 const uint64_t f0 = f2_fma(f2_pack(qa.x, qa.y), f2_pack((float)cur[2 * j], (float)cur[2 * j + 1]), t);
                 float g0, g1;
                 f2_unpack(f2_fma(f2_pack(qb.z, qb.w), iv2, f0), g0, g1);
                 if (SIM == bbqn::SIM_EUCLIDEAN) {
-                  const float2 w = qw_s[pj];
                   float d0, d1;
-                  f2_unpack(f2_sub(f2_mul(f2_pack(w.x, w.y), iv2), f0), d0, d1);
+                  const float2 w = qw_s[pj];
+                  f2_unpack(f2_sub(f2_mul(f2_pack(w.x, w.y), iv2), f0), d0, d1);  // wadj * iv - f0
                   g0 = fminf(g0, d0);
                   g1 = fminf(g1, d1);
                 }
@@ -934,39 +1194,48 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
                 if (g1 >= 0.f) mask |= (1u << (2 * j + 1));
               }
             }
-            if (always) mask = (nv - cc >= 16) ? 0xFFFFu : ((1u << (nv - cc)) - 1u);  // never a padding column: its query id would alias
+            const uint32_t vmask = (nv - cc >= 32) ? 0xFFFFFFFFu : ((1u << (nv - cc)) - 1u);  // never a padding column: its query id would alias
+            if (always) mask = 0xFFFFFFFFu;
+            mask &= vmask;
             if (p.debug & 2u) mask = 0u;
-            if (mask != 0u)  // park the hits for the drainer warp
-              mma_park_hits(ring_s, ring_ctl_s + 0, ring_ctl_s + 1, mask, (uint32_t)row, q0 + cc, cur[0], cur[1], cur[2],
-                            cur[3], cur[4], cur[5], cur[6], cur[7], cur[8], cur[9], cur[10], cur[11], cur[12], cur[13],
-                            cur[14], cur[15]);
+            if ((mask & 0xFFFFu) != 0u)  // park the hits for the drainer warp
+              mma_park_hits(ring_s, ring_ctl_s + 0, ring_ctl_s + 1, mask & 0xFFFFu, (uint32_t)row, q0 + cc, cur[0], cur[1],
+                            cur[2], cur[3], cur[4], cur[5], cur[6], cur[7], cur[8], cur[9], cur[10], cur[11], cur[12],
+                            cur[13], cur[14], cur[15]);
+            if (W == 32 && (mask >> 16) != 0u)
+              mma_park_hits(ring_s, ring_ctl_s + 0, ring_ctl_s + 1, mask >> 16, (uint32_t)row, q0 + cc + 16, cur[W - 16],
+                            cur[W - 15], cur[W - 14], cur[W - 13], cur[W - 12], cur[W - 11], cur[W - 10], cur[W - 9],
+                            cur[W - 8], cur[W - 7], cur[W - 6], cur[W - 5], cur[W - 4], cur[W - 3], cur[W - 2], cur[W - 1]);
           }
           if (c1 >= nv) return false;
           tc_wait_ld();
           return true;
         };
-        // COSINE / MIP ping-pong between the two register sets (no copies); for EUCLIDEAN the doubled loop body
-        // measured slower than 16 moves (same-box A/B), so it copies
-        constexpr bool PINGPONG = SIM != bbqn::SIM_EUCLIDEAN;
-        while (c0 < nv) {
+        while (c0 < nv) {  // ping-pong between the two register sets (no copies)
           if (!chunk(acc, nxt, c0)) break;
-          c0 += NSUB * 16;
-          if (PINGPONG) {
-            if (!chunk(nxt, acc, c0)) break;
-            c0 += NSUB * 16;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; j++) acc[j] = nxt[j];
-          }
+          c0 += NSUB * W;
+          if (!chunk(nxt, acc, c0)) break;
+          c0 += NSUB * W;
         }
         if (refresh) {  // fr0 = (ly8, aq, ay, negl) of query et: only the lower offset moves with the threshold
           float* pb = reinterpret_cast<float*>(qpb_s + (et >> 1));
           pb[2 + (et & 1)] = fr0.w;
+          if (p.qoff != nullptr) qoff_s[et] = fo0;
+        }
+        if (refresh2) {
+          float* pb = reinterpret_cast<float*>(qpb_s + ((et + ET) >> 1));
+          pb[2 + ((et + ET) & 1)] = fr1.w;
+          if (p.qoff != nullptr) qoff_s[et + ET] = fo1;
         }
         tc_fence_before();
         mbar_arrive(acc_empty + buf);
         tcount++;
       }
+    }
+    if (p.debug & 256u) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.trace) + 3 * 4096 + 0, dbg_tested);
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.trace) + 3 * 4096 + 1, dbg_passed);
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.trace) + 3 * 4096 + 2, dbg_warps);
     }
     __syncwarp();
     if (lane == 0) atomicAdd(ring_ctl_s + 2, 1u);  // this epilogue warp will park nothing more
