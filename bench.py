@@ -48,7 +48,7 @@ WORKLOADS = {
                  name="1M x 1024 EUCLIDEAN k=10 single query (the HBM-bound regime of BASELINE configs[2])"),
     "c4": dict(n=100_000_000, dim=1024, sim="COSINE", k=10, nq=4096, qb=4, ib=1,
                name="100M x 1024 COSINE k=10 batch of 4096 queries, row-sharded (BASELINE configs[3])"),
-    "c5": dict(n=10_000_000, dim=1536, sim="COSINE", k=100, nq=1024, qb=8, ib=2,
+    "c5": dict(n=10_000_000, dim=1536, sim="COSINE", k=100, nq=1024, qb=8, ib=2, cpu_rows=200_000,
                name="10M x 1536 COSINE k=100 batch of 1024 queries, queryBits=8/indexBits=2 (BASELINE configs[4]; "
                     "EXTENSION: the reference throws for this config, parity unpinned by construction)"),
 }
@@ -478,7 +478,7 @@ def run_gpu(args, w, rank, world, local_rank):
     # timed configuration's own lists -------------------------------------------------------------------------
     cpu = parity = None
     if not args.no_cpu and (world == 1 or args.parity_multi):
-        sample_rows = min(m["rows_local"], args.cpu_rows)          # bounded sample: the first rows of THIS index
+        sample_rows = min(m["rows_local"], w.get("cpu_rows", args.cpu_rows))   # bounded sample: the first rows of THIS index
         packed, corr = m["shard"]._export(0, sample_rows)
         oidx = oracle_index_from_arrays(packed, corr, m["shard"].getCentroid(), dim, sim, w["ib"])
         qs = gen_queries(nq, dim)

@@ -136,6 +136,7 @@ struct bbq_index {
   bbq_ctx* ctx = nullptr;
   uint64_t n = 0;
   uint32_t dim = 0;
+  int ib = 1;             // index bits (planes per 128-dim chunk of a row)
   int row_bytes = 0;
   uint8_t* codes = nullptr;
   double *lower = nullptr, *upper = nullptr, *addc = nullptr;
@@ -159,7 +160,9 @@ static constexpr int64_t SAMPLE_TILES_MAX = 2048;  // ... grown with k*n up to 2
 static constexpr uint32_t CAND_CAP = SELECT_MAX;
 static constexpr uint32_t K_MAX = 4096;
 
-static inline int row_bytes_for(uint32_t dim) { return (int)((((dim + 7) / 8) + 15) / 16 * 16); }
+// device row: 16-byte chunks, index_bits planes per 128-dim chunk (k_osq_index); index_bits == 1: the packed row padded to 16 B
+static inline int row_bytes_for(uint32_t dim, uint32_t index_bits = 1) { return (int)(((dim + 127) / 128) * 16 * index_bits); }
+static constexpr uint32_t INDEX_BITS_MAX = 2;  // 1 = the reference's searchable layout, 2 = this build's extension
 
 // ------------------------------------------------------------------------------------------------
 // lifecycle
@@ -301,7 +304,8 @@ static int index_alloc(bbq_ctx* c, uint64_t n, uint32_t dim, bbq_index** out) {
   c->refs++;
   ix->n = n;
   ix->dim = dim;
-  ix->row_bytes = row_bytes_for(dim);
+  ix->ib = (int)c->cfg.index_bits;
+  ix->row_bytes = row_bytes_for(dim, c->cfg.index_bits);
   ix->capacity = n;
   *out = ix;
   CU(cudaMalloc(&ix->codes, (size_t)n * ix->row_bytes));
@@ -351,10 +355,10 @@ static int build_impl(bbq_ctx* c, const float* rows, bool is_host, uint64_t n, u
   if (n == 0) return fail(BBQ_ERR_EMPTY, "vector set must not be empty");
   if (dim == 0) return fail(BBQ_ERR_INVALID_ARG, "dim must be > 0");
   if (n > 0x7FFFFFF0ull) return fail(BBQ_ERR_UNSUPPORTED, "more than 2^31 rows per shard (result ids are int32)");
-  if (c->cfg.index_bits != 1)
+  if (c->cfg.index_bits > INDEX_BITS_MAX)
     return fail(BBQ_ERR_UNSUPPORTED,
-                "indexBits != 1: the reference's batch search path cannot run it (createDirectPackedBuffer throws); "
-                "only the 1-bit index is built on device");
+                "indexBits > 2: the reference's search cannot run any indexBits != 1 (createDirectPackedBuffer throws); "
+                "this build searches 1-bit indexes (reference behaviour) and 2-bit ones (extension)");
   CU(cudaSetDevice(c->device));
   bbq_index* ix = nullptr;
   int st = index_alloc(c, n, dim, &ix);
@@ -416,9 +420,14 @@ static int build_impl(bbq_ctx* c, const float* rows, bool is_host, uint64_t n, u
     st = stage_chunk(off, rows_here);
     if (st != BBQ_OK) return bail(st);
     st = [&]() -> int {
-      LAUNCH(c, k_osq_index, (unsigned)((rows_here + 127) / 128), 128, 0, c->stream, T, R, rows_here, (int)dim,
-             ix->centroid, sim, c->cfg.lambda, (int)c->cfg.iters, ix->codes, ix->row_bytes, off, ix->lower, ix->upper,
-             ix->addc, ix->compsum);
+      if (ix->ib == 1)
+        LAUNCH(c, k_osq_index<1>, (unsigned)((rows_here + 127) / 128), 128, 0, c->stream, T, R, rows_here, (int)dim,
+               ix->centroid, sim, c->cfg.lambda, (int)c->cfg.iters, ix->codes, ix->row_bytes, off, ix->lower, ix->upper,
+               ix->addc, ix->compsum);
+      else
+        LAUNCH(c, k_osq_index<2>, (unsigned)((rows_here + 127) / 128), 128, 0, c->stream, T, R, rows_here, (int)dim,
+               ix->centroid, sim, c->cfg.lambda, (int)c->cfg.iters, ix->codes, ix->row_bytes, off, ix->lower, ix->upper,
+               ix->addc, ix->compsum);
       return BBQ_OK;
     }();
     if (st != BBQ_OK) return bail(st);
@@ -496,9 +505,14 @@ static int append_impl(bbq_index* ix, const float* rows, bool is_host, uint64_t 
     LAUNCH(c, k_transpose, grid, block, 0, c->stream, src, rows_here, (int)dim, T, R);
     if (sim == BBQ_SIM_COSINE)
       LAUNCH(c, k_normalize_T, (unsigned)((rows_here + 127) / 128), 128, 0, c->stream, T, R, rows_here, (int)dim, 1);
-    LAUNCH(c, k_osq_index, (unsigned)((rows_here + 127) / 128), 128, 0, c->stream, T, R, rows_here, (int)dim,
-           ix->centroid, sim, c->cfg.lambda, (int)c->cfg.iters, ix->codes, ix->row_bytes, (int64_t)ix->n + off,
-           ix->lower, ix->upper, ix->addc, ix->compsum);
+    if (ix->ib == 1)
+      LAUNCH(c, k_osq_index<1>, (unsigned)((rows_here + 127) / 128), 128, 0, c->stream, T, R, rows_here, (int)dim,
+             ix->centroid, sim, c->cfg.lambda, (int)c->cfg.iters, ix->codes, ix->row_bytes, (int64_t)ix->n + off,
+             ix->lower, ix->upper, ix->addc, ix->compsum);
+    else
+      LAUNCH(c, k_osq_index<2>, (unsigned)((rows_here + 127) / 128), 128, 0, c->stream, T, R, rows_here, (int)dim,
+             ix->centroid, sim, c->cfg.lambda, (int)c->cfg.iters, ix->codes, ix->row_bytes, (int64_t)ix->n + off,
+             ix->lower, ix->upper, ix->addc, ix->compsum);
     if (is_host) CU(cudaStreamSynchronize(c->stream));  // the staging buffer is reused by the next chunk
   }
   CU(cudaStreamSynchronize(c->stream));
@@ -514,7 +528,7 @@ extern "C" int bbq_index_reserve(bbq_ctx* c, uint64_t capacity, uint32_t dim, co
   if (capacity == 0) return fail(BBQ_ERR_EMPTY, "vector set must not be empty");
   if (dim == 0) return fail(BBQ_ERR_INVALID_ARG, "dim must be > 0");
   if (capacity > 0x7FFFFFF0ull) return fail(BBQ_ERR_UNSUPPORTED, "more than 2^31 rows per shard");
-  if (c->cfg.index_bits != 1) return fail(BBQ_ERR_UNSUPPORTED, "only the 1-bit index is built on device");
+  if (c->cfg.index_bits > INDEX_BITS_MAX) return fail(BBQ_ERR_UNSUPPORTED, "indexBits > 2 is not built on device");
   CU(cudaSetDevice(c->device));
   bbq_index* ix = nullptr;
   int st = index_alloc(c, capacity, dim, &ix);
@@ -544,6 +558,38 @@ extern "C" int bbq_index_append_device(bbq_index* ix, const float* d_rows, uint6
   return append_impl(ix, d_rows, false, n);
 }
 
+// Host-side conversion between the caller's row form and the device row (cold paths: adopt / export).
+// index_bits == 1: the caller's row is the packed MSB-first row (ceil(dim/8) bytes) and the device row is that row
+// zero-padded.  index_bits >= 2: the caller's row is what BinarizedByteVectorValuesImpl holds for such an index —
+// dim UNPACKED codes (src/binaryQuantizationFormat.ts:221-249) — and the device row is plane-interleaved.
+static void row_to_device(const uint8_t* src, uint32_t dim, int ib, uint8_t* dst, int row_bytes) {
+  memset(dst, 0, (size_t)row_bytes);
+  if (ib == 1) {
+    const int P = (int)((dim + 7) / 8);
+    memcpy(dst, src, P);
+    if (dim & 7) dst[P - 1] &= (uint8_t)(0xFF << (8 - (dim & 7)));  // tail bits are zero by contract
+    return;
+  }
+  for (uint32_t i = 0; i < dim; i++) {
+    const uint32_t rc = i >> 7, j = (i & 127) >> 3, t = i & 7;
+    for (int p = 0; p < ib; p++)
+      if ((src[i] >> p) & 1) dst[(rc * ib + p) * 16 + j] |= (uint8_t)(1u << (7 - t));
+  }
+}
+static void row_from_device(const uint8_t* src, uint32_t dim, int ib, uint8_t* dst) {
+  if (ib == 1) {
+    memcpy(dst, src, (dim + 7) / 8);
+    return;
+  }
+  for (uint32_t i = 0; i < dim; i++) {
+    const uint32_t rc = i >> 7, j = (i & 127) >> 3, t = i & 7;
+    uint8_t v = 0;
+    for (int p = 0; p < ib; p++) v |= (uint8_t)(((src[(rc * ib + p) * 16 + j] >> (7 - t)) & 1) << p);
+    dst[i] = v;
+  }
+}
+static inline size_t caller_row_bytes(uint32_t dim, int ib) { return ib == 1 ? (dim + 7) / 8 : dim; }
+
 extern "C" int bbq_index_from_quantized(bbq_ctx* c, const uint8_t* packed, const double* corr4, const float* centroid,
                                         uint64_t n, uint32_t dim, bbq_index** out_index) {
   if (!c || !out_index) return fail(BBQ_ERR_NULL, "null ctx/out_index");
@@ -551,7 +597,7 @@ extern "C" int bbq_index_from_quantized(bbq_ctx* c, const uint8_t* packed, const
   if (!packed || !corr4 || !centroid) return fail(BBQ_ERR_NULL, "null input");
   if (n == 0) return fail(BBQ_ERR_EMPTY, "vector set must not be empty");
   if (dim == 0) return fail(BBQ_ERR_INVALID_ARG, "dim must be > 0");
-  if (c->cfg.index_bits != 1) return fail(BBQ_ERR_UNSUPPORTED, "only 1-bit packed indexes can be adopted");
+  if (c->cfg.index_bits > INDEX_BITS_MAX) return fail(BBQ_ERR_UNSUPPORTED, "only 1- and 2-bit indexes can be adopted");
   CU(cudaSetDevice(c->device));
   bbq_index* ix = nullptr;
   int st = index_alloc(c, n, dim, &ix);
@@ -559,13 +605,13 @@ extern "C" int bbq_index_from_quantized(bbq_ctx* c, const uint8_t* packed, const
     bbq_index_destroy(ix);
     return st;
   }
-  const int P = (int)((dim + 7) / 8), RB = ix->row_bytes;
+  const size_t P = caller_row_bytes(dim, ix->ib);
+  const int RB = ix->row_bytes;
   std::vector<uint8_t> codes((size_t)n * RB, 0);
   std::vector<double> lo(n), up(n), ad(n);
   std::vector<uint32_t> cs(n);
   for (uint64_t i = 0; i < n; i++) {
-    memcpy(codes.data() + i * RB, packed + i * P, P);
-    if (dim & 7) codes[i * RB + P - 1] &= (uint8_t)(0xFF << (8 - (dim & 7)));  // tail bits are zero by contract
+    row_to_device(packed + i * P, dim, ix->ib, codes.data() + i * RB, RB);
     lo[i] = corr4[4 * i];
     up[i] = corr4[4 * i + 1];
     ad[i] = corr4[4 * i + 2];
@@ -609,11 +655,12 @@ extern "C" int bbq_index_export(const bbq_index* ix, uint64_t first, uint64_t co
   if (count == 0) return BBQ_OK;
   CU(cudaSetDevice(ix->ctx->device));
   CU(cudaStreamSynchronize(ix->ctx->stream));
-  const int P = (int)((ix->dim + 7) / 8), RB = ix->row_bytes;
+  const size_t P = caller_row_bytes(ix->dim, ix->ib);
+  const int RB = ix->row_bytes;
   if (packed) {
     std::vector<uint8_t> tmp((size_t)count * RB);
     CU(cudaMemcpy(tmp.data(), ix->codes + first * RB, tmp.size(), cudaMemcpyDeviceToHost));
-    for (uint64_t i = 0; i < count; i++) memcpy(packed + i * P, tmp.data() + i * RB, P);
+    for (uint64_t i = 0; i < count; i++) row_from_device(tmp.data() + i * RB, ix->dim, ix->ib, packed + i * P);
   }
   if (corr4) {
     std::vector<double> lo(count), up(count), ad(count);
@@ -672,6 +719,11 @@ static int launch_scan_nb(bbq_ctx* c, int nb, bool stream_form, dim3 grid, size_
     BBQ_SCAN_CASE(6)
     BBQ_SCAN_CASE(7)
     BBQ_SCAN_CASE(8)
+    case 9:  // 8-bit queries on a 2-bit index: 9 virtual planes, shared-memory tile form only
+      if (stream_form) return fail(BBQ_ERR_UNSUPPORTED, "no streaming scan for 9 planes");
+      if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_scan<9, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      LAUNCH(c, (k_scan<9, MODE>), grid, TILE_ROWS, smem, st, p);
+      break;
     default:
       return fail(BBQ_ERR_QUERY_BITS, "queryBits must be in 1..8");
   }
@@ -683,7 +735,7 @@ static int launch_scan_nb(bbq_ctx* c, int nb, bool stream_form, dim3 grid, size_
 // tiles [tile_first, tile_first + ntiles*tile_stride) step tile_stride, queries [0, nq)
 static int launch_scan(bbq_index* ix, int mode, ScanParams p, int64_t ntiles, cudaStream_t st) {
   bbq_ctx* c = ix->ctx;
-  const int nb = (int)c->cfg.query_bits;
+  const int nb = (int)c->cfg.query_bits + ix->ib - 1;  // (virtual) query bit-planes, k_query_planes
   const int w4 = ix->row_bytes / 16, s4 = w4 | 1;
   int qb = std::min(p.nq, 32);
   auto smem_for = [&](int q) {
@@ -700,7 +752,7 @@ static int launch_scan(bbq_index* ix, int mode, ScanParams p, int64_t ntiles, cu
   p.ntiles = ntiles;
   // one or a few queries: the streaming (register/shuffle, HBM-bound) form; it needs >= 2 rows per 512-byte load
   const bool stream_ok = w4 == 1 || w4 == 2 || w4 == 3 || w4 == 4 || w4 == 6 || w4 == 8 || w4 == 12;  // dims 128..1536
-  const bool stream_form = c->popc_form != 1 && p.nq <= 4 && stream_ok;
+  const bool stream_form = c->popc_form != 1 && p.nq <= 4 && stream_ok && nb <= 8;
   if (mode == SCAN_DUMP) return launch_scan_nb<SCAN_DUMP>(c, nb, stream_form, grid, smem_for(qb), st, p);
   return launch_scan_nb<SCAN_FILTER>(c, nb, stream_form, grid, smem_for(qb), st, p);
 }
@@ -723,11 +775,13 @@ static int launch_select(bbq_ctx* c, const SelectParams& p, uint32_t m_max, cuda
 // :279), 1 for a direct quantizeQueryVector call (:271-299).
 static int quantize_rows(bbq_ctx* c, const float* d_queries, int nq, int dim, int row_bytes, const float* d_centroid,
                          int ntimes, cudaStream_t st) {
-  const int nb = (int)c->cfg.query_bits, words = row_bytes / 4, code_ld = row_bytes * 8;
+  // row_bytes: the DEVICE row of the index the queries are for (planes included); codes are stored per real dim
+  const int ib = (int)c->cfg.index_bits <= (int)INDEX_BITS_MAX ? (int)c->cfg.index_bits : 1;
+  const int nb = (int)c->cfg.query_bits, nbv = nb + ib - 1, words = row_bytes / 4, code_ld = row_bytes * 8 / ib;
   TRY(c->qT.reserve((size_t)nq * dim * sizeof(float)));
   TRY(c->qcodes.reserve((size_t)nq * code_ld));
   TRY(c->qcorr.reserve((size_t)nq * 4 * sizeof(double)));
-  TRY(c->planes.reserve((size_t)nq * nb * words * sizeof(uint32_t)));
+  TRY(c->planes.reserve((size_t)nq * nbv * words * sizeof(uint32_t)));
   TRY(c->qterms.reserve((size_t)nq * sizeof(bbqn::QueryTerms)));
   ProfScope prof(c, st, PROF_QUANT);
   const size_t per_warp = (size_t)((dim + 3) & ~3) * sizeof(float) + 14 * 33 * sizeof(double);
@@ -748,9 +802,9 @@ static int quantize_rows(bbq_ctx* c, const float* d_queries, int nq, int dim, in
     LAUNCH(c, k_osq_query, (nq + 63) / 64, 64, 0, st, T, (int64_t)nq, nq, dim, d_centroid, (int)c->cfg.similarity, nb,
            c->cfg.lambda, (int)c->cfg.iters, c->qcodes.as<uint8_t>(), code_ld, c->qcorr.as<double>());
   }
-  const int64_t total = (int64_t)nq * nb * words;
+  const int64_t total = std::max<int64_t>((int64_t)nq * nbv * words, nq);
   LAUNCH(c, k_query_planes, (unsigned)((total + 127) / 128), 128, 0, st, c->qcodes.as<uint8_t>(), code_ld,
-         c->qcorr.as<double>(), nq, nb, words, c->planes.as<uint32_t>(), c->qterms.as<bbqn::QueryTerms>());
+         c->qcorr.as<double>(), nq, nb, ib, words, c->planes.as<uint32_t>(), c->qterms.as<bbqn::QueryTerms>());
   return BBQ_OK;
 }
 static int quantize_queries(bbq_index* ix, const float* d_queries, int nq, cudaStream_t st) {
@@ -762,13 +816,20 @@ static int quantize_queries(bbq_index* ix, const float* d_queries, int nq, cudaS
 // ---- tensor-core scan (K2) -------------------------------------------------------------------------
 struct MmaPlan {
   int n_tile = 0, passes = 0, nstage = 0, kbytes = 0;
+  int cpq = 1;  // accumulator columns per query: 2 when the code is split into nibbles (k_query_tiles)
   size_t smem = 0;
 };
 static bool mma_plan(const bbq_index* ix, int nq, MmaPlan* out) {
   const bbq_ctx* c = ix->ctx;
-  if (c->scan_engine == 1 || c->cfg.query_bits > 5) return false;
-  if (ix->row_bytes * 8 > 4096 || nq > 4096) return false;  // parked-hit word: 20-bit accumulator, 12-bit query
+  if (c->scan_engine == 1) return false;
+  const int qb_ = (int)c->cfg.query_bits;
+  // B elements are code << plane << (0..3): they fit a byte while (2^qb - 1) * 2^(ib-1) <= 31; wider codes are split
+  // into two nibble columns per query
   MmaPlan pl;
+  pl.cpq = (((1 << qb_) - 1) << (ix->ib - 1)) <= 31 ? 1 : 2;
+  const int64_t max_dot = (int64_t)((1 << qb_) - 1) * ((1 << ix->ib) - 1) * ix->dim;
+  if (max_dot >= (1ll << HIT_DOT_BITS) || nq > 4096) return false;  // parked-hit word: 21-bit dot, 12-bit query
+  if (ix->row_bytes * 8 > 4096) return false;                        // K bytes per row the resident B block is planned for
   pl.kbytes = ix->row_bytes * 8;
   const size_t budget = 227 * 1024 - 1024 - (HIT_RING * sizeof(uint64_t) + 64);
   int n_cap = (int)(budget / ((size_t)pl.kbytes + 64)) / 16 * 16;
@@ -779,8 +840,9 @@ static bool mma_plan(const bbq_index* ix, int nq, MmaPlan* out) {
   // tensor-core scan wins: one pass over 1M x 1024 costs 0.145 ms whatever the block size (operand-feed bound), the
   // popcount tile scan 0.03 ms per query (tools/crossover.sh: 8 queries 0.145 vs 0.257 ms, 48 queries 0.154 vs 1.43 ms)
   if (c->scan_engine != 2 && nq < 5) return false;
-  pl.passes = (nq + n_cap - 1) / n_cap;
-  pl.n_tile = (((nq + pl.passes - 1) / pl.passes) + 15) / 16 * 16;
+  const int ncols = nq * pl.cpq;
+  pl.passes = (ncols + n_cap - 1) / n_cap;
+  pl.n_tile = (((ncols + pl.passes - 1) / pl.passes) + 15) / 16 * 16;
   pl.nstage = std::min(8, (512 - 2 * pl.n_tile) / 32);
   pl.smem = (size_t)pl.n_tile * pl.kbytes + (size_t)pl.n_tile * (sizeof(QScreen) + sizeof(bbqn::QueryTerms)) + 26 * 8 + sizeof(HitCtx) + HIT_RING * sizeof(uint64_t) + 16 + 16;
   *out = pl;
@@ -794,7 +856,7 @@ static int ensure_bounds(bbq_index* ix, cudaStream_t st) {
   if (!ix->rscreen) CU(cudaMalloc(&ix->rscreen, (size_t)ix->capacity * sizeof(float4)));
   CU(cudaMemsetAsync(ix->bounds, 0, sizeof(IndexBounds), st));
   LAUNCH(c, k_index_bounds, 592, 256, 0, st, ix->lower, ix->upper, ix->addc, ix->compsum, (int64_t)ix->n,
-         (int)c->cfg.similarity, reinterpret_cast<uint32_t*>(ix->bounds), ix->rscreen);
+         (int)c->cfg.similarity, bbqn::index_lx_div(ix->ib), reinterpret_cast<uint32_t*>(ix->bounds), ix->rscreen);
   ix->bounds_n = ix->n;
   return BBQ_OK;
 }
@@ -804,23 +866,29 @@ static int prepare_mma_operands(bbq_index* ix, int nq, const MmaPlan& pl, cudaSt
   bbq_ctx* c = ix->ctx;
   const size_t bytes = (size_t)pl.passes * pl.n_tile * pl.kbytes;
   TRY(c->images.reserve(bytes));
+  // per-query tables are indexed by query SLOT: pass * (n_tile / cpq) + position in the pass
   TRY(c->qscreen.reserve((size_t)pl.passes * pl.n_tile * sizeof(QScreen)));
   TRY(c->tau_bits.reserve((size_t)pl.passes * pl.n_tile * sizeof(uint32_t)));
   TRY(c->qoff.reserve((size_t)pl.passes * pl.n_tile * sizeof(int32_t)));
   TRY(c->qenv.reserve((size_t)pl.passes * sizeof(QEnv)));
   ProfScope prof(c, st, PROF_QUANT);
   const int64_t threads = (int64_t)pl.passes * pl.n_tile * (pl.kbytes / 16);
-  LAUNCH(c, k_query_tiles, (unsigned)((threads + 255) / 256), 256, 0, st, c->qcodes.as<uint8_t>(), ix->row_bytes * 8, nq,
-         pl.n_tile, pl.kbytes, c->images.as<uint8_t>());
+  LAUNCH(c, k_query_tiles, (unsigned)((threads + 255) / 256), 256, 0, st, c->qcodes.as<uint8_t>(),
+         ix->row_bytes * 8 / ix->ib, nq, pl.n_tile, pl.kbytes, ix->ib, pl.cpq, c->images.as<uint8_t>());
   return BBQ_OK;
 }
 
 template <int MODE>
-static int launch_mma_sim(bbq_ctx* c, int sim, unsigned grid, size_t smem, cudaStream_t st, const MmaParams& p) {
+static int launch_mma_sim(bbq_ctx* c, int sim, int cpq, unsigned grid, size_t smem, cudaStream_t st, const MmaParams& p) {
 #define BBQ_MMA_CASE(S)                                                                                         \
   case S:                                                                                                       \
-    CU(cudaFuncSetAttribute(k_scan_mma<MODE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-    LAUNCH(c, (k_scan_mma<MODE, S>), grid, MMA_THREADS, smem, st, p);                                           \
+    if (cpq == 1) {                                                                                             \
+      CU(cudaFuncSetAttribute(k_scan_mma<MODE, S, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      LAUNCH(c, (k_scan_mma<MODE, S, 1>), grid, MMA_THREADS, smem, st, p);                                      \
+    } else {                                                                                                    \
+      CU(cudaFuncSetAttribute(k_scan_mma<MODE, S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      LAUNCH(c, (k_scan_mma<MODE, S, 2>), grid, MMA_THREADS, smem, st, p);                                      \
+    }                                                                                                           \
     break;
   switch (sim) {
     BBQ_MMA_CASE(0)
@@ -870,7 +938,8 @@ static int launch_scan_mma(bbq_index* ix, int mode, int nq, uint32_t k, const Mm
   p.dim = (double)ix->dim;
   p.cdp = ix->cdp;
   p.sim = (int)c->cfg.similarity;
-  p.one_bit_query = c->cfg.query_bits == 1 ? 1 : 0;
+  p.one_bit_query = bbqn::score_mode((int)c->cfg.query_bits, ix->ib);
+  p.lx_div = bbqn::index_lx_div(ix->ib);
   p.base = (uint32_t)ix->base;
   p.tile_first = tile_first;
   p.tile_stride = tile_stride;
@@ -887,8 +956,8 @@ static int launch_scan_mma(bbq_index* ix, int mode, int nq, uint32_t k, const Mm
   c->stats.mma_n_tile = (uint32_t)pl.n_tile;
   c->stats.mma_passes = (uint32_t)pl.passes;
   const unsigned grid = (unsigned)std::min<int64_t>(ntiles, c->sm_count);
-  if (mode == SCAN_DUMP) return launch_mma_sim<SCAN_DUMP>(c, p.sim, grid, pl.smem, st, p);
-  return launch_mma_sim<SCAN_FILTER>(c, p.sim, grid, pl.smem, st, p);
+  if (mode == SCAN_DUMP) return launch_mma_sim<SCAN_DUMP>(c, p.sim, pl.cpq, grid, pl.smem, st, p);
+  return launch_mma_sim<SCAN_FILTER>(c, p.sim, pl.cpq, grid, pl.smem, st, p);
 }
 
 static ScanParams base_scan_params(bbq_index* ix, int nq) {
@@ -907,7 +976,8 @@ static ScanParams base_scan_params(bbq_index* ix, int nq) {
   p.dim = (double)ix->dim;
   p.cdp = ix->cdp;
   p.sim = (int)c->cfg.similarity;
-  p.one_bit_query = c->cfg.query_bits == 1 ? 1 : 0;
+  p.one_bit_query = bbqn::score_mode((int)c->cfg.query_bits, ix->ib);
+  p.lx_div = bbqn::index_lx_div(ix->ib);
   p.base = (uint32_t)ix->base;
   p.tile_first = 0;
   p.tile_stride = 1;
@@ -1069,7 +1139,8 @@ static int search_filtered(bbq_index* ix, int nq, uint32_t k, int32_t* d_out_idx
       {
         ProfScope prof(c, st, PROF_QUANT);
         LAUNCH(c, k_query_screen, pl.passes, 256, 0, st, c->qterms.as<bbqn::QueryTerms>(), c->tau.as<float>(), nq,
-               pl.n_tile, (double)ix->dim, ix->cdp, (int)c->cfg.similarity, c->cfg.query_bits == 1 ? 1 : 0, ix->bounds,
+               pl.n_tile / pl.cpq, (double)ix->dim, ix->cdp, (int)c->cfg.similarity,
+               bbqn::score_mode((int)c->cfg.query_bits, ix->ib), ix->bounds,
                c->qscreen.as<QScreen>(), c->tau_bits.as<uint32_t>(), c->qoff.as<int32_t>(), c->qenv.as<QEnv>());
       }
       // the running threshold reads candidate slots that may be reserved but not yet written: they must read as 0
@@ -1548,7 +1619,7 @@ extern "C" int bbq_quantize_query(bbq_ctx* c, const float* query, const float* c
   if (dim == 0) return fail(BBQ_ERR_INVALID_ARG, "dim must be > 0");
   CU(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
-  const int row_bytes = row_bytes_for(dim);
+  const int row_bytes = row_bytes_for(dim, std::min<uint32_t>(c->cfg.index_bits, INDEX_BITS_MAX));
   TRY(c->qrows.reserve((size_t)dim * sizeof(float)));
   TRY(c->cenv.reserve((size_t)dim * sizeof(float)));
   TRY(c->bad.reserve(sizeof(unsigned long long)));
@@ -1573,6 +1644,7 @@ extern "C" int bbq_quantization_accuracy(bbq_ctx* c, const float* rows, const fl
   const uint32_t qb = c->cfg.query_bits;
   // computeQuantizedScore, src/binaryQuantizedScorer.ts:78-97: only 1-bit and 4-bit queries
   if (qb != 1 && qb != 4) return fail(BBQ_ERR_UNSUPPORTED, "unsupported query bits: only 1 and 4 (computeQuantizedScore)");
+  if (c->cfg.index_bits != 1) return fail(BBQ_ERR_UNSUPPORTED, "computeQuantizationAccuracy scores through the single-vector scorer, which knows 1-bit indexes only");
   if (n > 0x7FFFFFF0ull) return fail(BBQ_ERR_UNSUPPORTED, "too many vectors");
   bbq_index* ix = nullptr;
   TRY(bbq_index_build(c, rows, n, dim, nullptr, &ix));   // 1. quantizeVectors(originalVectors), reference-order centroid

@@ -139,6 +139,7 @@ extern "C" int bbq_index_save(const bbq_index* cix, const char* veb_path, const 
   bbq_index* ix = const_cast<bbq_index*>(cix);
   if (!ix || !veb_path || !vemb_path) return fail(BBQ_ERR_NULL, "null index/path");
   if (ix->n == 0) return fail(BBQ_ERR_EMPTY, "vector set must not be empty");
+  if (ix->ib != 1) return fail(BBQ_ERR_UNSUPPORTED, "only 1-bit index images can be saved");
   bbq_ctx* c = ix->ctx;
   CU(cudaSetDevice(c->device));
   bbqio::Section s[5];

@@ -98,9 +98,14 @@ __global__ void k_centroid_dp(const float* __restrict__ c, int dim, double* __re
   }
 }
 
-// K5: scalarQuantize(indexBits = 1) + packAsBinary, src/optimizedScalarQuantizer.ts:108-227,420-446,
-// driven as src/binaryQuantizationFormat.ts:221-249 does.  One thread per vector; the packed row is
-// written MSB-first (dim 8j+t -> bit 7-t of byte j), zero padded to row_bytes (a multiple of 16).
+// K5: scalarQuantize(indexBits) + packAsBinary, src/optimizedScalarQuantizer.ts:108-227,420-446,
+// driven as src/binaryQuantizationFormat.ts:221-249 does.  One thread per vector.
+// Device row layout (north-star item 1, "bit-plane-interleaved, 16-byte aligned"): the row is a sequence of 16-byte
+// chunks; chunk rc * IB + p holds bit-plane p (p = 0: least significant) of the codes of dims [128 rc, 128 rc + 128),
+// MSB-first inside each byte (dim 8j+t -> bit 7-t of byte j) exactly as packAsBinary writes a 1-bit row; zero padded.
+// With IB = 1 this IS the reference's packed row (padded to 16 bytes).  With IB >= 2 (EXTENSION: the reference keeps
+// such rows unpacked and cannot search them) a scan sees a 1-bit row of IB * 128 * chunks "virtual dims".
+template <int IB>
 __global__ void k_osq_index(const float* __restrict__ T, int64_t ld, int64_t nrows, int dim,
                             const float* __restrict__ centroid, int sim, double lambda, int iters,
                             uint8_t* __restrict__ codes, int row_bytes, int64_t row0,
@@ -110,32 +115,52 @@ __global__ void k_osq_index(const float* __restrict__ T, int64_t ld, int64_t nro
   if (t >= nrows) return;
   TAcc v{T + t, ld};
   CAcc c{centroid};
-  const bbqn::OsqResult r = bbqn::osq_interval(v, c, dim, 1, sim, lambda, iters);
+  const bbqn::OsqResult r = bbqn::osq_interval(v, c, dim, IB, sim, lambda, iters);
   uint4* out = reinterpret_cast<uint4*>(codes + (row0 + t) * (int64_t)row_bytes);
-  uint32_t w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u, cur = 0u;
+  uint32_t w[IB][4], cur[IB];
+#pragma unroll
+  for (int p = 0; p < IB; p++) {
+    cur[p] = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; j++) w[p][j] = 0u;
+  }
   int nout = 0;
-  const double qsum = bbqn::osq_codes(v, c, dim, 1, r.lower, r.upper, [&](int i, uint8_t q) {
-    cur |= (uint32_t)q << (8 * ((i >> 3) & 3) + 7 - (i & 7));  // little-endian word of MSB-first bytes
+  auto flush_chunk = [&]() {
+#pragma unroll
+    for (int p = 0; p < IB; p++) {
+      out[nout++] = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) w[p][j] = 0u;
+    }
+  };
+  const double qsum = bbqn::osq_codes(v, c, dim, IB, r.lower, r.upper, [&](int i, uint8_t q) {
+    const int sh = 8 * ((i >> 3) & 3) + 7 - (i & 7);  // little-endian word of MSB-first bytes
+#pragma unroll
+    for (int p = 0; p < IB; p++) cur[p] |= (uint32_t)((q >> p) & 1u) << sh;
     if ((i & 31) == 31) {
-      const int s = (i >> 5) & 3;
-      if (s == 0) w0 = cur;
-      else if (s == 1) w1 = cur;
-      else if (s == 2) w2 = cur;
-      else {
-        out[nout++] = make_uint4(w0, w1, w2, cur);
-        w0 = w1 = w2 = 0u;
+      const int j = (i >> 5) & 3;
+#pragma unroll
+      for (int p = 0; p < IB; p++) {
+        if (j == 0) w[p][0] = cur[p];
+        else if (j == 1) w[p][1] = cur[p];
+        else if (j == 2) w[p][2] = cur[p];
+        else w[p][3] = cur[p];
+        cur[p] = 0u;
       }
-      cur = 0u;
+      if (j == 3) flush_chunk();
     }
   });
   if (dim & 31) {  // partial last word
-    const int s = (dim >> 5) & 3;
-    if (s == 0) w0 = cur;
-    else if (s == 1) w1 = cur;
-    else if (s == 2) w2 = cur;
-    else w3 = cur;
+    const int j = (dim >> 5) & 3;
+#pragma unroll
+    for (int p = 0; p < IB; p++) {
+      if (j == 0) w[p][0] = cur[p];
+      else if (j == 1) w[p][1] = cur[p];
+      else if (j == 2) w[p][2] = cur[p];
+      else w[p][3] = cur[p];
+    }
   }
-  if (dim & 127) out[nout++] = make_uint4(w0, w1, w2, w3);
+  if (dim & 127) flush_chunk();
   for (; nout < row_bytes / 16; nout++) out[nout] = make_uint4(0u, 0u, 0u, 0u);
   lower[row0 + t] = r.lower;
   upper[row0 + t] = r.upper;
@@ -376,28 +401,36 @@ __global__ void __launch_bounds__(TAU_THREADS) k_tau_from_sample(const float* __
 }
 
 // Query bit-planes in the index's bit order: plane b, word w holds bit b of codes[32w .. 32w+31],
-// dim 8j+t at bit 7-t of byte j (so `plane & row` pairs equal dims).  Layout [nq][nb][words].
+// dim 8j+t at bit 7-t of byte j (so `plane & row` pairs equal dims).  Layout [nq][nbv][words].
+// With an IB-bit index (plane-interleaved rows, see k_osq_index) the row is a 1-bit row of virtual dims and the query
+// gets nbv = nb + IB - 1 VIRTUAL planes of weight 2^b': at a position of index plane p, virtual plane b' holds bit
+// b' - p of the code, so that  sum_b' 2^b' popc(vplane_b' & row) = sum_d code[d] * x[d]  (x = sum_p 2^p bit_p).
 // Also hoists the per-query score terms (src/batchDotProduct.ts:497-502,573-578).
 __global__ void k_query_planes(const uint8_t* __restrict__ qcodes, int code_ld, const double* __restrict__ qcorr,
-                               int nq, int nb, int words, uint32_t* __restrict__ planes,
+                               int nq, int nb, int ib, int words, uint32_t* __restrict__ planes,
                                bbqn::QueryTerms* __restrict__ qterms) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)nq * nb * words;
+  const int nbv = nb + ib - 1;
+  const int64_t total = (int64_t)nq * nbv * words;
   if (g < total) {
     const int w = (int)(g % words);
-    const int b = (int)((g / words) % nb);
-    const int q = (int)(g / ((int64_t)words * nb));
-    const uint8_t* cd = qcodes + (int64_t)q * code_ld + 32 * w;
+    const int b = (int)((g / words) % nbv);
+    const int q = (int)(g / ((int64_t)words * nbv));
+    const int chunk = w >> 2, rc = chunk / ib, p = chunk - rc * ib;  // virtual chunk -> (real 128-dim chunk, index plane)
+    const int bit = b - p;
     uint32_t word = 0;
+    if (bit >= 0 && bit < nb) {
+      const uint8_t* cd = qcodes + (int64_t)q * code_ld + 128 * rc + 32 * (w & 3);
 #pragma unroll
-    for (int j = 0; j < 4; j++)
+      for (int j = 0; j < 4; j++)
 #pragma unroll
-      for (int t = 0; t < 8; t++) word |= (uint32_t)((cd[8 * j + t] >> b) & 1) << (8 * j + 7 - t);
+        for (int t = 0; t < 8; t++) word |= (uint32_t)((cd[8 * j + t] >> bit) & 1) << (8 * j + 7 - t);
+    }
     planes[g] = word;
   }
   if (g < nq) {
     const double* c = qcorr + 4 * g;
-    qterms[g] = bbqn::make_query_terms(c[0], c[1], c[2], c[3], nb);
+    qterms[g] = bbqn::make_query_terms(c[0], c[1], c[2], c[3], nb, ib);
   }
 }
 
@@ -429,7 +462,8 @@ struct ScanParams {
   double dim;
   double cdp;
   int sim;
-  int one_bit_query;
+  int one_bit_query;      // bbqn::SCORE_REF_MULTIBIT / SCORE_REF_ONEBIT / SCORE_EXT
+  double lx_div;          // 2^indexBits - 1: lx = (upper - lower) / lx_div
   int64_t ntiles;         // k_scan_stream (persistent): number of tiles to cover
   uint32_t base;          // global id of row 0
   // tile mapping: CTA x handles tile (tile_first + blockIdx.x * tile_stride)
@@ -485,7 +519,7 @@ __global__ void __launch_bounds__(TILE_ROWS) k_scan(const ScanParams p) {
   double ax = 0, lx = 0, addx = 0, x1 = 0;
   if (valid) {
     ax = p.lower[row];
-    lx = p.upper[row] - ax;  // `indexCorrections.upperInterval - ax`, src/batchDotProduct.ts:499,575
+    lx = (p.upper[row] - ax) / p.lx_div;  // `indexCorrections.upperInterval - ax`, src/batchDotProduct.ts:499,575 (/1 there)
     addx = p.addc[row];
     x1 = (double)p.compsum[row];
   }
@@ -510,7 +544,7 @@ __global__ void __launch_bounds__(TILE_ROWS) k_scan(const ScanParams p) {
 #pragma unroll
     for (int b = 0; b < NB; b++) dot += acc[b] << b;
     const float score = bbqn::score_f32((double)dot, ax, lx, addx, x1, qt_s[ql], p.dim, p.cdp, p.sim,
-                                        p.one_bit_query != 0);
+                                        p.one_bit_query);
     const int q = q0 + ql;
     if (MODE == SCAN_DUMP) {
       if (valid) {
@@ -628,7 +662,7 @@ __global__ void __launch_bounds__(TILE_ROWS, 4) k_scan_stream(const ScanParams p
   for (; u < nunits; u += ustride) {
 #pragma unroll
     for (int it = 0; it < iters; it++) x[it] = xn[it];
-    const double ax = lo_n, lx = up_n - lo_n, addx = add_n, x1 = (double)cs_n;
+    const double ax = lo_n, lx = (up_n - lo_n) / p.lx_div, addx = add_n, x1 = (double)cs_n;
     const int64_t my_row = unit_row0(u) + out_rl;
     const bool valid = my_row < p.n;
     if (u + ustride < nunits) fetch(u + ustride);  // next unit in flight while this one is reduced
@@ -687,7 +721,7 @@ __global__ void __launch_bounds__(TILE_ROWS, 4) k_scan_stream(const ScanParams p
           if (lane / R == it) mydot = got;  // row (it*R + lane%R) == lane
         }
       }
-      const float score = bbqn::score_f32((double)mydot, ax, lx, addx, x1, qt_s[q], p.dim, p.cdp, p.sim, p.one_bit_query != 0);
+      const float score = bbqn::score_f32((double)mydot, ax, lx, addx, x1, qt_s[q], p.dim, p.cdp, p.sim, p.one_bit_query);
       if (MODE == SCAN_DUMP) {
         if (valid) {
           p.dump[(int64_t)q * p.dump_ld + (u >> 2) * TILE_ROWS + (u & 3) * 32 + out_rl] = score;

@@ -249,25 +249,35 @@ __host__ __device__ inline uint32_t make_idesc_i8(int m, int n) {
 
 // ---- operand / constant preparation ------------------------------------------------------------
 // B image of pass p: element (n, kpos) at (kpos/16)*(n_tile*16) + (n/8)*128 + (n%8)*16 + kpos%16, where
-// kpos = 32g + 4u + j  <->  dim 32g + 8j + 7 - u, weight 2^(3 - u%4)  (see file header).  Queries beyond nq: 0.
-__global__ void k_query_tiles(const uint8_t* __restrict__ qcodes, int code_ld, int nq, int n_tile, int kbytes,
-                              uint8_t* __restrict__ images) {
+// kpos = 32g + 4u + j  <->  virtual dim 32g + 8j + 7 - u, weight 2^(3 - u%4)  (see file header).
+// Virtual dims: with an IB-bit index the row is plane-interleaved (k_osq_index): 16-byte chunk c of the row is index
+// plane p = c % IB of real dims [128 (c / IB), +128), and the B element there is code << p.
+// Columns: one per query while (2^queryBits - 1) * 2^(IB-1) * 8 <= 255, otherwise TWO per query (cpq = 2): column 2q
+// carries the high nibble of the code, column 2q+1 the low one, and the epilogue recombines 16 * D_hi + D_lo — that is
+// how 6..8-bit queries (and the 8b x 2b extension) run on kind::i8.  Columns beyond the batch: 0.
+__global__ void k_query_tiles(const uint8_t* __restrict__ qcodes, int code_ld, int nq, int n_tile, int kbytes, int ib,
+                              int cpq, uint8_t* __restrict__ images) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (pass, n, 16-byte k group)
   const int k16s = kbytes / 16;
-  const int passes = (nq + n_tile - 1) / n_tile;
+  const int ncols = nq * cpq;
+  const int passes = (ncols + n_tile - 1) / n_tile;
   if (g >= (int64_t)passes * n_tile * k16s) return;
   const int n = (int)(g % n_tile);
   const int k16 = (int)((g / n_tile) % k16s);
   const int p = (int)(g / ((int64_t)n_tile * k16s));
-  const int q = p * n_tile + n;
+  const int col = p * n_tile + n;
   uint32_t w[4] = {0u, 0u, 0u, 0u};
-  if (q < nq) {
+  if (col < ncols) {
+    const int q = col / cpq, half = col - q * cpq;
     const uint8_t* cd = qcodes + (int64_t)q * code_ld;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
       const int kpos = k16 * 16 + i;
       const int grp = kpos >> 5, u = (kpos >> 2) & 7, j = kpos & 3;
-      const uint32_t v = (uint32_t)cd[32 * grp + 8 * j + 7 - u] << (3 - (u & 3));
+      const int chunk = grp >> 2, rc = chunk / ib, plane = chunk - rc * ib;
+      uint32_t code = cd[128 * rc + 32 * (grp & 3) + 8 * j + 7 - u];
+      if (cpq == 2) code = half == 0 ? (code >> 4) : (code & 15u);
+      const uint32_t v = (code << plane) << (3 - (u & 3));
       w[i >> 2] |= (v & 0xFFu) << (8 * (i & 3));
     }
   }
@@ -282,12 +292,12 @@ __global__ void k_query_tiles(const uint8_t* __restrict__ qcodes, int code_ld, i
 // reads as "send every pair of this row to the exact replay".
 __global__ void k_index_bounds(const double* __restrict__ lower, const double* __restrict__ upper,
                                const double* __restrict__ addc, const uint32_t* __restrict__ compsum, int64_t n,
-                               int sim, uint32_t* __restrict__ out4, float4* __restrict__ rscreen) {
+                               int sim, double lx_div, uint32_t* __restrict__ out4, float4* __restrict__ rscreen) {
   float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
   double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
   unsigned long long cnt = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const double ax = lower[i], lx = upper[i] - ax, ad = addc[i];
+    const double ax = lower[i], lx = (upper[i] - ax) / lx_div, ad = addc[i];
     float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lx > 0 && bbqn::js_isfinite(lx) && bbqn::js_isfinite(ax) && bbqn::js_isfinite(ad)) {
       m0 = fmaxf(m0, __double2float_ru(lx));
@@ -529,7 +539,8 @@ struct MmaParams {
   const bbqn::QueryTerms* qterms;
   int nq, n_tile, passes, nstage;
   double dim, cdp;
-  int sim, one_bit_query;
+  int sim, one_bit_query;  // one_bit_query: bbqn::SCORE_* mode
+  double lx_div;           // 2^indexBits - 1
   uint32_t base;
   int64_t tile_first, tile_stride, ntiles;  // tiles handled: tile_first + i*tile_stride, i < ntiles
   // SCAN_DUMP: exact score of every pair -> dump[q*dump_ld + i*128 + row]
@@ -568,6 +579,7 @@ struct HitCtx {
   const uint32_t* compsum;
   uint32_t cap, k, base;
   int nq, one_bit_query;
+  double lx_div;
   int32_t* qoff;   // running first-level offsets (nullptr: no first level)
 };
 
@@ -579,11 +591,13 @@ constexpr uint32_t HIT_RING = 512;         // CTA-wide ring of parked hits (8 B 
 // ---- hits: parked by the epilogue warps, replayed by a dedicated "drainer" warp -------------------------------
 // A lane that replayed its own hit would serialise its whole warp behind a ~100-instruction f64 routine plus two
 // dependent global round trips (measured: 1.0 ms of a 2.2 ms scan).  Instead the epilogue lanes only PARK a hit —
-// one 64-bit word (row+1 | query | accumulator) into a CTA-wide shared-memory ring — and warp 3 drains the ring,
+// one 64-bit word (row+1 | query | dot) into a CTA-wide shared-memory ring — and warp 3 drains the ring,
 // one lane per hit: exact f64 replay, comparison with the query's CURRENT threshold, candidate append, and the
 // threshold tightening below.  A ring word is published by a single 64-bit store and consumed in order.
-__device__ __forceinline__ uint64_t hit_pack(uint32_t row, uint32_t q, uint32_t acc) {
-  return ((uint64_t)(row + 1u) << 32) | ((uint64_t)(q & 0xFFFu) << 20) | (uint64_t)(acc & 0xFFFFFu);
+// ring word: row + 1 (31 bits: a shard holds < 2^31 - 16 rows) | query (12 bits) | integer dot (21 bits)
+constexpr int HIT_DOT_BITS = 21;
+__device__ __forceinline__ uint64_t hit_pack(uint32_t row, uint32_t q, uint32_t dot) {
+  return ((uint64_t)(row + 1u) << 33) | ((uint64_t)(q & 0xFFFu) << HIT_DOT_BITS) | (uint64_t)(dot & 0x1FFFFFu);
 }
 
 __device__ __noinline__ void mma_park_hits(uint64_t* ring, uint32_t* tail_s, const uint32_t* head_s, uint32_t mask,
@@ -595,7 +609,7 @@ __device__ __noinline__ void mma_park_hits(uint64_t* ring, uint32_t* tail_s, con
     mask &= mask - 1;
     const uint32_t slot = atomicAdd(tail_s, 1u);
     while (slot - *((volatile const uint32_t*)head_s) >= HIT_RING) __nanosleep(100);  // ring full: wait for the drainer
-    *((volatile uint64_t*)(ring + (slot % HIT_RING))) = hit_pack(row, (uint32_t)(q0c0 + j), (uint32_t)acc[j]);
+    *((volatile uint64_t*)(ring + (slot % HIT_RING))) = hit_pack(row, (uint32_t)(q0c0 + j), (uint32_t)acc[j] >> 3);
   }
 }
 
@@ -676,16 +690,17 @@ __device__ void mma_drain_ring(const HitCtx* cx, uint64_t* ring, const uint32_t*
     }
     int tighten_q = -1;
     if ((uint32_t)lane < n) {
-      const int64_t row = (int64_t)((uint32_t)(e >> 32) - 1u);
-      const int q = (int)((e >> 20) & 0xFFFu);
-      const int acc = (int)(e & 0xFFFFFu);
+      const int64_t row = (int64_t)((uint32_t)(e >> 33) - 1u);
+      const int q = (int)((e >> HIT_DOT_BITS) & 0xFFFu);
+      const int dot = (int)(e & 0x1FFFFFu);
       float score = 0.f, tau = INFINITY;
       if (q < cx->nq) {  // (a degenerate row parks the padding columns of the last query block too)
         const double ax = __ldg(cx->lower + row), ux = __ldg(cx->upper + row), addx = __ldg(cx->addc + row);
         const double x1 = (double)__ldg(cx->compsum + row);
         const bbqn::QueryTerms qt = cx->qterms[q];
         tau = __ldcg(&cx->qscreen[q].tau);
-        score = bbqn::score_f32((double)(acc >> 3), ax, ux - ax, addx, x1, qt, cx->dim, cx->cdp, SIM, cx->one_bit_query != 0);
+        score = bbqn::score_f32((double)dot, ax, (ux - ax) / cx->lx_div, addx, x1, qt, cx->dim, cx->cdp, SIM,
+                                cx->one_bit_query);
       }
       if (q < cx->nq && score >= tau) {
         const uint32_t pos = atomicAdd(cx->cand_cnt + q, 1u);
@@ -713,7 +728,9 @@ __device__ void mma_drain_ring(const HitCtx* cx, uint64_t* ring, const uint32_t*
   }
 }
 
-template <int MODE, int SIM>
+// CPQ = accumulator columns per query: 1, or 2 when the query code is split into nibbles (k_query_tiles); then the
+// epilogue works on val = 16 * D_hi + D_lo = 8 * dot and every per-query table is indexed by column / 2.
+template <int MODE, int SIM, int CPQ>
 __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_constant__ MmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // layout: [B image n_tile*kbytes][QScreen n_tile][QueryTerms n_tile][barriers][tmem ptr]
@@ -773,6 +790,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
     hit_s->base = p.base;
     hit_s->nq = p.nq;
     hit_s->one_bit_query = p.one_bit_query;
+    hit_s->lx_div = p.lx_div;
     hit_s->qoff = const_cast<int32_t*>(p.qoff);
     ring_ctl_s[0] = ring_ctl_s[1] = ring_ctl_s[2] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1031,11 +1049,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
     for (int pass = 0; pass < p.passes; pass++) {
       // per-pass query constants -> shared memory (epilogue warps only: named barrier 1)
       asm volatile("bar.sync 1, %0;" ::"n"(MMA_EPI_WARPS * 32) : "memory");
-      const int q0 = pass * p.n_tile;
-      const int nv = min(p.n_tile, p.nq - q0);
-      for (int c = et; c < p.n_tile; c += MMA_EPI_WARPS * 32) {
+      const int q0 = pass * p.n_tile;                     // first accumulator COLUMN of the pass (all passes)
+      const int nv = min(p.n_tile, p.nq * CPQ - q0);      // valid columns of this pass
+      const int nq_pass = p.n_tile / CPQ;                 // query slots per pass: every per-query table is indexed by slot
+      const int q0q = pass * nq_pass, nvq = nv / CPQ;     // first query slot of the pass / valid queries in it
+      for (int c = et; c < nq_pass; c += MMA_EPI_WARPS * 32) {
         if (MODE == SCAN_FILTER) {
-          const QScreen qs = p.qscreen[q0 + c];
+          const QScreen qs = p.qscreen[q0q + c];
           float* pa = reinterpret_cast<float*>(qpa_s + (c >> 1));
           float* pb = reinterpret_cast<float*>(qpb_s + (c >> 1));
           float* pw = reinterpret_cast<float*>(qw_s + (c >> 1));
@@ -1045,9 +1065,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
           pb[2 + (c & 1)] = qs.negl;
           pw[c & 1] = qs.wadj;
         }
-        qoff_s[c] = p.qoff != nullptr ? p.qoff[q0 + c] : 0;
-        if (c < 16) qoff_s[p.n_tile + c] = -QOFF_ALWAYS;  // columns past the block: never pass
-        if (MODE == SCAN_DUMP && c < nv) qt_s[c] = p.qterms[q0 + c];
+        qoff_s[c] = p.qoff != nullptr ? p.qoff[q0q + c] : 0;
+        if (c < 16) qoff_s[nq_pass + c] = -QOFF_ALWAYS;  // slots past the block: never pass
+        if (MODE == SCAN_DUMP && c < nvq) qt_s[c] = p.qterms[q0q + c];
       }
       // first-level envelope of this query block (registers; warp-uniform)
       float e_r0 = 0.f, e_r1 = 0.f, e_r2 = 0.f, e_r3 = 1.f, e_c0 = 0.f, e_c1 = 0.f, e_c2 = 0.f, e_c3 = 0.f, e_h0 = 0.f,
@@ -1108,14 +1128,14 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
         const uint32_t d_addr = lane_addr + buf * (uint32_t)p.n_tile;
         // this tile's refresh of the (possibly tightened) second-level constants: loads issued now, stored after the tile
         constexpr int ET = MMA_EPI_WARPS * 32;  // 128 or 256 threads refresh up to 224 queries: one or two each
-        const bool refresh = MODE == SCAN_FILTER && p.k <= RETIGHTEN_KMAX && et < nv;
-        const bool refresh2 = MODE == SCAN_FILTER && p.k <= RETIGHTEN_KMAX && ET < MMA_N_MAX && et + ET < nv;
+        const bool refresh = MODE == SCAN_FILTER && p.k <= RETIGHTEN_KMAX && et < nvq;
+        const bool refresh2 = MODE == SCAN_FILTER && p.k <= RETIGHTEN_KMAX && ET < MMA_N_MAX && et + ET < nvq;
         float4 fr0 = make_float4(0.f, 0.f, 0.f, 0.f), fr1 = fr0;
         int fo0 = 0, fo1 = 0;
-        if (refresh) fr0 = __ldcg(reinterpret_cast<const float4*>(p.qscreen + q0 + et));
-        if (refresh2) fr1 = __ldcg(reinterpret_cast<const float4*>(p.qscreen + q0 + et + ET));
-        if (refresh && p.qoff != nullptr) fo0 = __ldcg(p.qoff + q0 + et);
-        if (refresh2 && p.qoff != nullptr) fo1 = __ldcg(p.qoff + q0 + et + ET);
+        if (refresh) fr0 = __ldcg(reinterpret_cast<const float4*>(p.qscreen + q0q + et));
+        if (refresh2) fr1 = __ldcg(reinterpret_cast<const float4*>(p.qscreen + q0q + et + ET));
+        if (refresh && p.qoff != nullptr) fo0 = __ldcg(p.qoff + q0q + et);
+        if (refresh2 && p.qoff != nullptr) fo1 = __ldcg(p.qoff + q0q + et + ET);
         // software pipeline over this warp's 16-column chunks: the next chunk's TMEM load is in flight while the
         // current one is reduced; the chunk just read is re-armed for the tile two positions ahead
         constexpr int W = MMA_LDW;
@@ -1129,17 +1149,23 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
         auto chunk = [&](int (&cur)[W], int (&nx)[W], int cc) -> bool {
           const int c1 = cc + NSUB * W;
           if (c1 < nv) tc_ldw(d_addr + (uint32_t)c1, nx);
+          // per QUERY from here on: val = 8 * dot (split codes: 16 * D_hi + D_lo), qc = the chunk's first query slot
+          constexpr int NVC = W / CPQ;
+          int val[NVC];
+#pragma unroll
+          for (int j = 0; j < NVC; j++) val[j] = CPQ == 1 ? cur[j] : cur[2 * j] * 16 + cur[2 * j + 1];
+          const int qc = cc / CPQ;
           if (MODE == SCAN_DUMP) {
             if (valid) {
 #pragma unroll
-              for (int j = 0; j < W; j++) {
-                const int c = cc + j;
-                if (c < nv) {
-                  const int64_t off = (int64_t)(q0 + c) * p.dump_ld + i * TILE_ROWS + r;
+              for (int j = 0; j < NVC; j++) {
+                const int c = qc + j;
+                if (c < nvq) {
+                  const int64_t off = (int64_t)(q0q + c) * p.dump_ld + i * TILE_ROWS + r;
                   if (p.dump != nullptr)
-                    p.dump[off] = bbqn::score_f32((double)(cur[j] >> 3), rt.ax, rt.ux - rt.ax, rt.addx, (double)rt.x1,
-                                                  qt_s[c], p.dim, p.cdp, SIM, p.one_bit_query != 0);
-                  if (p.dots != nullptr) p.dots[off] = cur[j] >> 3;  // D = 8 * dot exactly (file header)
+                    p.dump[off] = bbqn::score_f32((double)(val[j] >> 3), rt.ax, (rt.ux - rt.ax) / p.lx_div, rt.addx, (double)rt.x1,
+                                                  qt_s[c], p.dim, p.cdp, SIM, p.one_bit_query);
+                  if (p.dots != nullptr) p.dots[off] = val[j] >> 3;  // D = 8 * dot exactly (file header)
                 }
               }
             }
@@ -1154,13 +1180,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
               // first level: max_j (8*dot_j + qoff_j) against the row's T; the 16 offsets are warp-uniform (4 broadcast
               // LDS.128).  A warp goes on if ANY of its 32 rows passes, so the per-row rate has to be well below 1/32:
               // the offsets follow the running threshold (mma_retighten_warp), not just the sampled one.
-              const int4* o4 = reinterpret_cast<const int4*>(qoff_s + cc);
+              const int4* o4 = reinterpret_cast<const int4*>(qoff_s + qc);
               int mm[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN};  // four independent VIMNMX3 chains
 #pragma unroll
-              for (int g = 0; g < W / 4; g++) {
+              for (int g = 0; g < NVC / 4; g++) {
                 const int4 o = o4[g];
-                mm[g & 3] = max(max(mm[g & 3], cur[4 * g] + o.x), cur[4 * g + 1] + o.y);
-                mm[(g + 2) & 3] = max(max(mm[(g + 2) & 3], cur[4 * g + 2] + o.z), cur[4 * g + 3] + o.w);
+                mm[g & 3] = max(max(mm[g & 3], val[4 * g] + o.x), val[4 * g + 1] + o.y);
+                mm[(g + 2) & 3] = max(max(mm[(g + 2) & 3], val[4 * g + 2] + o.z), val[4 * g + 3] + o.w);
               }
               const int m = max(max(mm[0], mm[1]), max(mm[2], mm[3]));
               go = m >= T;
@@ -1174,13 +1200,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
             uint32_t mask = 0u;
             if (go && !(p.debug & 1u)) {
 #pragma unroll
-              for (int j = 0; j < W / 2; j++) {  // two queries per step
-                const int pj = (cc >> 1) + j;
+              for (int j = 0; j < NVC / 2; j++) {  // two queries per step
+                const int pj = (qc >> 1) + j;
                 const float4 qa = qpa_s[pj], qb = qpb_s[pj];
                 // f0 = (s + c*addx) / lx for the two queries; lower test: f0 + negl/lx >= 0; upper: f0 <= wadj/lx
                 uint64_t t = f2_fma(x1f2, f2_pack(qb.x, qb.y), gv2);
                 t = f2_fma(rv2, f2_pack(qa.z, qa.w), t);
-                const uint64_t f0 = f2_fma(f2_pack(qa.x, qa.y), f2_pack((float)cur[2 * j], (float)cur[2 * j + 1]), t);
+                const uint64_t f0 = f2_fma(f2_pack(qa.x, qa.y), f2_pack((float)val[2 * j], (float)val[2 * j + 1]), t);
                 float g0, g1;
                 f2_unpack(f2_fma(f2_pack(qb.z, qb.w), iv2, f0), g0, g1);
                 if (SIM == bbqn::SIM_EUCLIDEAN) {
@@ -1194,18 +1220,19 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
                 if (g1 >= 0.f) mask |= (1u << (2 * j + 1));
               }
             }
-            const uint32_t vmask = (nv - cc >= 32) ? 0xFFFFFFFFu : ((1u << (nv - cc)) - 1u);  // never a padding column: its query id would alias
+            const uint32_t vmask = (nvq - qc >= 32) ? 0xFFFFFFFFu : ((1u << (nvq - qc)) - 1u);  // never a padding slot: its query id would alias
             if (always) mask = 0xFFFFFFFFu;
             mask &= vmask;
             if (p.debug & 2u) mask = 0u;
+            auto v_at = [&](int j) { return j < NVC ? val[j < NVC ? j : 0] : 0; };
             if ((mask & 0xFFFFu) != 0u)  // park the hits for the drainer warp
-              mma_park_hits(ring_s, ring_ctl_s + 0, ring_ctl_s + 1, mask & 0xFFFFu, (uint32_t)row, q0 + cc, cur[0], cur[1],
-                            cur[2], cur[3], cur[4], cur[5], cur[6], cur[7], cur[8], cur[9], cur[10], cur[11], cur[12],
-                            cur[13], cur[14], cur[15]);
-            if (W == 32 && (mask >> 16) != 0u)
-              mma_park_hits(ring_s, ring_ctl_s + 0, ring_ctl_s + 1, mask >> 16, (uint32_t)row, q0 + cc + 16, cur[W - 16],
-                            cur[W - 15], cur[W - 14], cur[W - 13], cur[W - 12], cur[W - 11], cur[W - 10], cur[W - 9],
-                            cur[W - 8], cur[W - 7], cur[W - 6], cur[W - 5], cur[W - 4], cur[W - 3], cur[W - 2], cur[W - 1]);
+              mma_park_hits(ring_s, ring_ctl_s + 0, ring_ctl_s + 1, mask & 0xFFFFu, (uint32_t)row, q0q + qc, v_at(0), v_at(1),
+                            v_at(2), v_at(3), v_at(4), v_at(5), v_at(6), v_at(7), v_at(8), v_at(9), v_at(10), v_at(11),
+                            v_at(12), v_at(13), v_at(14), v_at(15));
+            if (NVC == 32 && (mask >> 16) != 0u)
+              mma_park_hits(ring_s, ring_ctl_s + 0, ring_ctl_s + 1, mask >> 16, (uint32_t)row, q0q + qc + 16, v_at(16),
+                            v_at(17), v_at(18), v_at(19), v_at(20), v_at(21), v_at(22), v_at(23), v_at(24), v_at(25),
+                            v_at(26), v_at(27), v_at(28), v_at(29), v_at(30), v_at(31));
           }
           if (c1 >= nv) return false;
           tc_wait_ld();

@@ -198,10 +198,23 @@ struct QueryTerms {
   double addq;  // additionalCorrection
 };
 
+// Which score formula: the reference's 4-bit path (every queryBits != 1 with a 1-bit index: FOUR_BIT_SCALE = 1/15 and
+// the batch-path MIP quirk), its 1-bit path, or this build's EXTENSION for indexBits >= 2 (the reference throws there;
+// natural generalisation, SURVEY §8c: ly = (u_q - l_q)/(2^queryBits - 1), lx = (u_i - l_i)/(2^indexBits - 1), plain
+// scaleMaxInnerProductScore).
+enum { SCORE_REF_MULTIBIT = 0, SCORE_REF_ONEBIT = 1, SCORE_EXT = 2 };
+BBQ_HD int score_mode(int query_bits, int index_bits) {
+  return index_bits >= 2 ? SCORE_EXT : (query_bits == 1 ? SCORE_REF_ONEBIT : SCORE_REF_MULTIBIT);
+}
+// divisor of the index interval: lx = (upper_i - lower_i) / lx_div (1 for the reference's 1-bit index: x / 1.0 == x)
+BBQ_HD double index_lx_div(int index_bits) { return (double)((1 << index_bits) - 1); }
+
 BBQ_HD QueryTerms make_query_terms(double lower, double upper, double additional, double compsum,
-                                   int query_bits) {
+                                   int query_bits, int index_bits = 1) {
   QueryTerms t;
   t.ay = lower;
+  if (index_bits >= 2) t.ly = (upper - lower) / (double)((1 << query_bits) - 1);  // EXTENSION
+  else
   t.ly = (query_bits == 1) ? (upper - lower) : (upper - lower) * (1.0 / 15.0);  // src/constants.ts:20
   t.y1 = compsum;
   t.addq = additional;
@@ -211,14 +224,19 @@ BBQ_HD QueryTerms make_query_terms(double lower, double upper, double additional
 // One corrected score as the reference's batch path computes it, INCLUDING the Float32Array store
 // (src/binaryQuantizationFormat.ts:353,378).  ax = lower_i, lx = upper_i - lower_i, x1 = componentSum_i.
 // queryBits != 1: src/batchDotProduct.ts:554-617;  queryBits == 1: :478-541 (different association).
+// `mode`: SCORE_REF_MULTIBIT / SCORE_REF_ONEBIT / SCORE_EXT; lx = (upper_i - lower_i) / index_lx_div(indexBits).
 BBQ_HD float score_f32(double dot, double ax, double lx, double addx, double x1, const QueryTerms& q,
-                       double dim, double cdp, int sim, bool one_bit_query) {
+                       double dim, double cdp, int sim, int mode) {
   double s = ax * q.ay * dim + q.ay * lx * x1 + ax * q.ly * q.y1 + lx * q.ly * dot;
   double r;
   if (sim == SIM_EUCLIDEAN) {
     const double e = q.addq + addx - 2 * s;
     r = js_max(1 / (1 + e), 0.0);
-  } else if (one_bit_query) {
+  } else if (mode == SCORE_EXT) {
+    const double adj = s + q.addq + addx - cdp;
+    if (sim == SIM_COSINE) r = js_max((1 + adj) / 2, 0.0);
+    else r = (adj < 0) ? 1 / (1 - adj) : adj + 1;
+  } else if (mode == SCORE_REF_ONEBIT) {
     s = s + (q.addq + addx - cdp);
     if (sim == SIM_COSINE) r = js_max((1 + s) / 2, 0.0);
     else r = (s < 0) ? 1 / (1 - s) : s + 1;

@@ -122,7 +122,9 @@ class BinarizedByteVectorValues:
     def _export(self, ord_: int, count: int = 1):
         if ord_ < 0 or ord_ + count > self._n:
             raise BbqError(10, f"向量索引 {ord_} 不存在")
-        p = (self._dim + 7) // 8
+        # indexBits == 1: packed MSB-first rows of ceil(dim/8) bytes; otherwise dim unpacked codes per row, as
+        # BinarizedByteVectorValuesImpl holds them (src/binaryQuantizationFormat.ts:221-249)
+        p = (self._dim + 7) // 8 if self._fmt.config["indexBits"] == 1 else self._dim
         packed = np.empty((count, p), np.uint8)
         corr = np.empty((count, 4), np.float64)
         _check(_native.load().bbq_index_export(self._h, ord_, count, packed.ctypes.data, corr.ctypes.data))
@@ -132,7 +134,8 @@ class BinarizedByteVectorValues:
         return self._export(ord_)[0][0]
 
     def getUnpackedVector(self, ord_: int) -> np.ndarray:
-        return np.unpackbits(self.vectorValue(ord_))[: self._dim]
+        v = self.vectorValue(ord_)
+        return np.unpackbits(v)[: self._dim] if self._fmt.config["indexBits"] == 1 else v
 
     def getCorrectiveTerms(self, ord_: int) -> dict:
         c = self._export(ord_)[1][0]

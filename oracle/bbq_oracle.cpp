@@ -626,3 +626,65 @@ int bbqo_quantization_accuracy(const float* rows, const float* queries, int64_t 
 }
 
 }  // extern "C"
+
+// ---- EXTENSION (NOT reference behaviour; "parity unpinned by construction") -------------------------------------
+// indexBits >= 2.  The reference accepts the config (src/binaryQuantizationFormat.ts:143-148) and quantises the
+// index with it (rows of D unpacked codes 0 .. 2^indexBits-1, :221-249), but its search throws: the batch path's
+// createDirectPackedBuffer rejects unpacked rows (src/batchDotProduct.ts:420-436) and the per-vector fallback only
+// knows 1- and 4-bit queries and has no 1/(2^indexBits-1) factor (src/binaryQuantizedScorer.ts:69-98).  SURVEY §8c
+// recommends the natural generalisation, which is what this build (oracle AND device) defines:
+//   qcDist = sum_d q[d] * x[d]                       (integer, unpacked codes)
+//   lx = (upper_i - lower_i) / (2^indexBits - 1),    ly = (upper_q - lower_q) / (2^queryBits - 1)
+//   score = ax*ay*D + ay*lx*x1 + ax*ly*y1 + lx*ly*qcDist        (left to right, no FMA)
+//   EUCLIDEAN max(1/(1 + addq + addi - 2*score), 0);  adj = score + addq + addi - centroidDP (centroidDP = c.c)
+//   COSINE max((1 + adj)/2, 0);  MAXIMUM_INNER_PRODUCT scaleMaxInnerProductScore(adj)  (src/utils.ts:171-176)
+// Everything around it is the reference's: quantisers, the double COSINE normalisation of the query, the f32 store
+// of the score, the heap / canonical selection.
+double score_ext(double dot, const double xc[4], const double qc[4], int d, double cdp, int sim, int query_bits,
+                 int index_bits) {
+  const double x1 = xc[3], ax = xc[0], ay = qc[0], y1 = qc[3];
+  const double lx = (xc[1] - ax) / (double)((1 << index_bits) - 1);
+  const double ly = (qc[1] - ay) / (double)((1 << query_bits) - 1);
+  const double score = ax * ay * (double)d + ay * lx * x1 + ax * ly * y1 + lx * ly * dot;
+  if (sim == SIM_EUCLIDEAN) {
+    const double e = qc[2] + xc[2] - 2 * score;
+    return js_max(1 / (1 + e), 0);
+  }
+  const double adj = score + qc[2] + xc[2] - cdp;
+  if (sim == SIM_COSINE) return js_max((1 + adj) / 2, 0);
+  return adj < 0 ? 1 / (1 - adj) : adj + 1;
+}
+
+extern "C" {
+// searchNearestNeighbors over an index of UNPACKED codes (n x d bytes, values 0 .. 2^index_bits-1), index_bits >= 2.
+int64_t bbqo_search_ext(const float* query, const float* centroid, const uint8_t* codes, const double* xcorr,
+                        int64_t n, int d, int sim, int query_bits, int index_bits, double lambda, int iters,
+                        int64_t k, int mode, int32_t* out_idx, float* out_score, float* all_scores,
+                        int32_t* all_dots) {
+  if (k <= 0) return 0;
+  std::vector<uint8_t> qcodes(d);
+  double qcorr[4];
+  bbqo_quantize_query(query, centroid, d, sim, query_bits, lambda, iters, qcodes.data(), qcorr);
+  std::vector<int32_t> dots_local;
+  int32_t* dots = all_dots;
+  if (!dots) {
+    dots_local.resize(n);
+    dots = dots_local.data();
+  }
+  for (int64_t v = 0; v < n; v++) dots[v] = bbqo_dot_unpacked(qcodes.data(), codes + v * (int64_t)d, d);
+  std::vector<float> sc_local;
+  float* sc = all_scores;
+  if (!sc) {
+    sc_local.resize(n);
+    sc = sc_local.data();
+  }
+  const double cdp = bbqo_centroid_dp(centroid, d);
+  for (int64_t v = 0; v < n; v++)
+    sc[v] = (float)score_ext((double)dots[v], xcorr + 4 * v, qcorr, d, cdp, sim, query_bits, index_bits);
+  return mode == 0 ? bbqo_topk_heap(sc, n, k, out_idx, out_score) : bbqo_topk_canonical(sc, n, k, out_idx, out_score);
+}
+double bbqo_score_ext(double dot, const double* xc, const double* qc, int d, double cdp, int sim, int query_bits,
+                      int index_bits) {
+  return score_ext(dot, xc, qc, d, cdp, sim, query_bits, index_bits);
+}
+}  // extern "C"

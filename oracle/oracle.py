@@ -78,6 +78,11 @@ def lib():
         L.bbqo_search.argtypes = [f32p, f32p, u8p, f64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double,
                                   C.c_int, C.c_int64, C.c_int, i32p, f32p, f32p, i32p]
         L.bbqo_search.restype = C.c_int64
+        L.bbqo_search_ext.argtypes = [f32p, f32p, u8p, f64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                      C.c_int, C.c_int64, C.c_int, i32p, f32p, f32p, i32p]
+        L.bbqo_search_ext.restype = C.c_int64
+        L.bbqo_score_ext.argtypes = [C.c_double, f64p, f64p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]
+        L.bbqo_score_ext.restype = C.c_double
         L.bbqo_quantize_query_once.argtypes = [f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, u8p, f64p]
         L.bbqo_score_single.argtypes = [C.c_double, f64p, f64p, C.c_int, C.c_double, C.c_int, C.c_int]
         L.bbqo_score_single.restype = C.c_double
@@ -289,7 +294,6 @@ def topk(scores, k, mode="canonical"):
 def search_nearest_neighbors(query, index: OracleIndex, k, query_bits=4, lam=0.1, iters=5,
                              mode="canonical", want_all=False):
     """-> (idx i32[<=k], score f32[<=k]) [, all_scores f32[n], all_dots i32[n]]"""
-    assert index.index_bits == 1, "reference batch path requires indexBits == 1 (SURVEY §8 a5/a11)"
     q = _f32(query)
     if q.size != index.dim:
         raise ValueError("查询向量维度与目标向量维度不匹配")
@@ -301,10 +305,18 @@ def search_nearest_neighbors(query, index: OracleIndex, k, query_bits=4, lam=0.1
     sc = np.empty(max(kk, 1), np.float32)
     alls = np.empty(n, np.float32) if want_all else None
     alld = np.empty(n, np.int32) if want_all else None
-    cnt = lib().bbqo_search(_p(q, C.c_float), _p(index.centroid, C.c_float), _p(index.packed, C.c_uint8),
-                            _p(index.corr, C.c_double), n, index.dim, SIM[index.sim], query_bits, lam, iters,
-                            k, 0 if mode == "heap" else 1, _p(idx, C.c_int32), _p(sc, C.c_float),
-                            _p(alls, C.c_float), _p(alld, C.c_int32))
+    if index.index_bits == 1:
+        cnt = lib().bbqo_search(_p(q, C.c_float), _p(index.centroid, C.c_float), _p(index.packed, C.c_uint8),
+                                _p(index.corr, C.c_double), n, index.dim, SIM[index.sim], query_bits, lam, iters,
+                                k, 0 if mode == "heap" else 1, _p(idx, C.c_int32), _p(sc, C.c_float),
+                                _p(alls, C.c_float), _p(alld, C.c_int32))
+    else:
+        # EXTENSION (the reference throws for indexBits >= 2: SURVEY §8 a5/a11): see score_ext in bbq_oracle.cpp;
+        # `packed` holds the unpacked codes (n x d bytes) as BinarizedByteVectorValuesImpl would
+        cnt = lib().bbqo_search_ext(_p(q, C.c_float), _p(index.centroid, C.c_float), _p(index.packed, C.c_uint8),
+                                    _p(index.corr, C.c_double), n, index.dim, SIM[index.sim], query_bits,
+                                    index.index_bits, lam, iters, k, 0 if mode == "heap" else 1, _p(idx, C.c_int32),
+                                    _p(sc, C.c_float), _p(alls, C.c_float), _p(alld, C.c_int32))
     if want_all:
         return idx[:cnt].copy(), sc[:cnt].copy(), alls, alld
     return idx[:cnt].copy(), sc[:cnt].copy()

@@ -35,7 +35,7 @@ def test_mma_integer_tap_bit_exact(bbq, dim, qb):
     assert np.array_equal(fmt.debugQcDist(qs[5], qv), got[5])
 
 
-def test_mma_integer_tap_rejects_wide_queries(bbq):
+def _disabled_mma_integer_tap_rejects_wide_queries(bbq):   # (8-bit queries now run on tcgen05: nibble columns)
     rows = gaussian(500, 128, 7)
     fmt = make_format(bbq, "COSINE", qb=8)
     qv = fmt.quantizeVectors(rows)["quantizedVectors"]
@@ -211,3 +211,91 @@ def test_serialize_roundtrip(bbq):
     direct = fmt.quantizeVectors(rows)["quantizedVectors"]
     a, b = fmt.searchBatch(qs, back, 10), fmt.searchBatch(qs, direct, 10)
     assert np.array_equal(a[0], b[0]) and bits_equal(a[1], b[1])
+
+
+# ---- EXTENSION: indexBits = 2 (BASELINE configs[4]; the reference throws — semantics defined in oracle/bbq_oracle.cpp) --
+def make_format_ib(bbq, sim, qb, ib, scan=None):
+    import os
+    saved = os.environ.pop("BBQ_SCAN", None)
+    if scan is not None:
+        os.environ["BBQ_SCAN"] = scan
+    try:
+        return bbq.createBinaryQuantizationFormat(
+            {"queryBits": qb, "indexBits": ib, "quantizer": {"similarityFunction": sim, "lambda": 0.1, "iters": 5}})
+    finally:
+        os.environ.pop("BBQ_SCAN", None)
+        if saved is not None:
+            os.environ["BBQ_SCAN"] = saved
+
+
+@pytest.mark.parametrize("sim", SIMS)
+@pytest.mark.parametrize("n,dim", [(700, 128), (300, 100), (257, 1536)])
+def test_two_bit_index_build_bit_exact(bbq, sim, n, dim):
+    """K5 with indexBits = 2: codes (0..3), intervals, additional correction and component sums == the oracle's
+    quantizeVectors (the reference's own quantiser, which accepts indexBits = 2), through the plane-interleaved rows."""
+    rows = gaussian(n, dim, 1001 + dim)
+    want = O.quantize_vectors(rows, sim=sim, index_bits=2, want_unpacked=False)
+    fmt = make_format_ib(bbq, sim, 8, 2)
+    qv = fmt.quantizeVectors(rows)["quantizedVectors"]
+    codes, corr = qv.exportAll()
+    assert codes.shape == (n, dim) and codes.max() <= 3
+    assert np.array_equal(codes, want.packed) and bits_equal(corr, want.corr)
+    assert bits_equal(qv.getCentroid(), want.centroid)
+    back = fmt.adoptQuantized(codes, corr, want.centroid)          # and the adopt path re-interleaves the planes
+    c2, r2 = back.exportAll()
+    assert np.array_equal(c2, codes) and bits_equal(r2, corr)
+
+
+@pytest.mark.parametrize("sim", SIMS)
+@pytest.mark.parametrize("qb", [4, 8])
+@pytest.mark.parametrize("n,dim", [(3000, 128), (1100, 100), (900, 1536)])
+def test_two_bit_index_dots_and_scores_bit_exact(bbq, sim, qb, n, dim):
+    rows, qs = gaussian(n, dim, 1101 + dim), gaussian(2, dim, 1102 + dim)
+    idx = O.quantize_vectors(rows, sim=sim, index_bits=2, want_unpacked=False)
+    fmt = make_format_ib(bbq, sim, qb, 2)
+    qv = fmt.adoptQuantized(idx.packed, idx.corr, idx.centroid)
+    for q in qs:
+        _, _, alls, alld = O.search_nearest_neighbors(q, idx, 5, query_bits=qb, want_all=True)
+        assert np.array_equal(fmt.debugQcDist(q, qv), alld)           # popcount engine over 9 (5) virtual planes
+        assert bits_equal(fmt.debugScores(q, qv), alls)
+    got = fmt.debugQcDistBatch(gaussian(21, dim, 1103), qv)           # tensor-core engine: nibble columns for 8-bit codes
+    for qi, q in enumerate(gaussian(21, dim, 1103)):
+        _, _, _, alld = O.search_nearest_neighbors(q, idx, 5, query_bits=qb, want_all=True)
+        assert np.array_equal(got[qi], alld), qi
+
+
+@pytest.mark.parametrize("sim", SIMS)
+@pytest.mark.parametrize("n,dim,nq,k,qb", [(30000, 256, 70, 10, 8), (20000, 1536, 40, 100, 8), (25000, 384, 33, 10, 4)])
+def test_two_bit_index_search_both_engines(bbq, sim, n, dim, nq, k, qb):
+    rows, qs = gaussian(n, dim, 1201 + dim), gaussian(nq, dim, 1202 + dim)
+    idx = O.quantize_vectors(rows, sim=sim, index_bits=2, want_unpacked=False, centroid=np.zeros(dim, np.float32))
+    fm, fp = make_format_ib(bbq, sim, qb, 2, scan="mma"), make_format_ib(bbq, sim, qb, 2, scan="popc")
+    qm = fm.adoptQuantized(idx.packed, idx.corr, idx.centroid)
+    qp = fp.adoptQuantized(idx.packed, idx.corr, idx.centroid)
+    mi, ms = fm.searchBatch(qs, qm, k)
+    assert fm.stats()["last_engine"] == 2 and fm.stats()["last_overflow"] == 0
+    pi, ps = fp.searchBatch(qs[:6], qp, k)
+    assert fp.stats()["last_engine"] == 1
+    assert np.array_equal(mi[:6], pi) and bits_equal(ms[:6], ps)
+    for qi in range(0, nq, max(1, nq // 5)):
+        wi, ws = O.search_nearest_neighbors(qs[qi], idx, k, query_bits=qb, mode="canonical")
+        assert mi[qi].tolist() == wi.tolist() and bits_equal(ms[qi], ws), qi
+
+
+@pytest.mark.parametrize("qb", [6, 8])
+def test_wide_queries_on_the_tensor_core_scan(bbq, qb):
+    """6..8-bit queries on a 1-bit index (reference behaviour: the 4-bit path with its 1/15 scale) now also run on
+    tcgen05: the code is split into two nibble columns."""
+    n, dim, nq, k = 30000, 256, 50, 10
+    rows, qs = gaussian(n, dim, 1301), gaussian(nq, dim, 1302)
+    idx = O.quantize_vectors(rows, sim="COSINE", want_unpacked=False)
+    fm = make_format(bbq, "COSINE", qb=qb, scan="mma")
+    qm = fm.adoptQuantized(idx.packed, idx.corr, idx.centroid)
+    mi, ms = fm.searchBatch(qs, qm, k)
+    assert fm.stats()["last_engine"] == 2
+    for qi in range(0, nq, 7):
+        wi, ws = O.search_nearest_neighbors(qs[qi], idx, k, query_bits=qb, mode="canonical")
+        assert mi[qi].tolist() == wi.tolist() and bits_equal(ms[qi], ws)
+    d = fm.debugQcDistBatch(qs[:5], qm)
+    _, _, _, alld = O.search_nearest_neighbors(qs[3], idx, 1, query_bits=qb, want_all=True)
+    assert np.array_equal(d[3], alld)

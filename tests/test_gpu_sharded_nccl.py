@@ -38,8 +38,9 @@ def _worker(rank, world, ids, out, n, dim, nq, k, sim):
     for batch in (nq, 3):                       # tensor-core batch, then a 3-query popcount batch
         cnt = fmt.searchShardedHost(hq.data_ptr(), batch, shard, k, hi.data_ptr(), hs.data_ptr())
         results.append((cnt, hi.numpy()[:batch].copy(), hs.numpy()[:batch].copy()))
-    # k larger than any single shard but not than the corpus: count = min(k, rows over all ranks)
-    kbig = r1 - r0 + 5
+    # k larger than any single shard but not than the corpus: count = min(k, rows over all ranks).  (The SAME k on
+    # every rank: the call is collective.)
+    kbig = -(-n // world) + 5
     bi = torch.empty((2, kbig), dtype=torch.int32).pin_memory()
     bs = torch.empty((2, kbig), dtype=torch.float32).pin_memory()
     cnt_big = fmt.searchShardedHost(hq.data_ptr(), 2, shard, kbig, bi.data_ptr(), bs.data_ptr()) if kbig <= 4096 else None
@@ -70,9 +71,14 @@ def test_library_sharded_search_equals_unsharded(world, sim, n, dim, nq, k):
     procs = [ctx.Process(target=_worker, args=(r, world, ids, out, n, dim, nq, k, sim)) for r in range(world)]
     for p in procs:
         p.start()
-    for p in procs:
-        p.join(300)
-        assert p.exitcode == 0
+    try:
+        for p in procs:
+            p.join(240)
+            assert p.exitcode == 0, "a rank failed or hung"
+    finally:
+        for p in procs:      # never leave a rank spinning in a collective on the GPU behind a failed test
+            if p.is_alive():
+                p.kill()
     got = dict(out.get(timeout=5) for _ in range(world))
     assert got == {r: True for r in range(world)}
 
