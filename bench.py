@@ -303,6 +303,11 @@ class Timer:
         return self._max_over_ranks(tot)
 
 
+def _stage(rank, what):
+    if os.environ.get("BBQ_BENCH_WATCHDOG"):
+        print(f"[bench r{rank} {time.time() % 1000:.1f}] {what}", file=sys.stderr, flush=True)
+
+
 def measure(args, torch, dist, bbq, w, rank, world, local_rank, steps, warmup, flush, sample_clocks):
     """Builds this rank's shard of workload w and times it.  -> dict of raw measurements (every rank), or None."""
     n, dim, k, nq = w["n"], w["dim"], w["k"], w["nq"]
@@ -312,7 +317,9 @@ def measure(args, torch, dist, bbq, w, rank, world, local_rank, steps, warmup, f
     device_gen = args.datagen == "device" or (args.datagen == "auto" and n > 4_000_000)
     shard = build_shard(torch, fmt, w, r0, r1, device_gen)
     build_s = time.perf_counter() - t_build
+    _stage(rank, "shard built")
     searcher = bbq.ShardedSearcher(fmt, shard, r0, rank, world)
+    _stage(rank, "communicator up")
     hq = torch.from_numpy(gen_queries(nq, dim)).pin_memory()
     dq = hq.cuda()
     tm = Timer(torch, dist, flush, searcher.stream)
@@ -322,17 +329,20 @@ def measure(args, torch, dist, bbq, w, rank, world, local_rank, steps, warmup, f
     for _ in range(warmup):
         searcher.search_device(dq, k)
     torch.cuda.synchronize()
+    _stage(rank, "warm-up searches done")
     fmt.resetProfiling()
     l0 = fmt.stats()["kernel_launches"]
     sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None
     if sampler:
         sampler.start()
     ms_total = tm.device(lambda: searcher.search_device(dq, k), steps, 0)
+    _stage(rank, "device-timed steps done")
     st = fmt.stats()
     launches = st["kernel_launches"] - l0
     fmt.setProfiling(False)
     # --- e2e: HOST buffers through bbq_search / bbq_search_sharded, every step --------------------------------
     e2e_ms = tm.host(lambda: searcher.search(hq, k), steps, warmup)
+    _stage(rank, "e2e steps done")
     clocks = sampler.stop() if sampler else None
     # an index smaller than L2 (C2: 11 MB of 126 MB) is L2-resident after the first query: SURVEY §8d asks for the
     # warm figure beside the cold one (`value` / `e2e` are cold: L2 flushed before every step)
@@ -460,6 +470,8 @@ def run_gpu(args, w, rank, world, local_rank):
     n, dim, sim, k, nq = w["n"], w["dim"], w["sim"], w["k"], w["nq"]
     m = measure(args, torch, dist, bbq_b200, w, rank, world, local_rank, args.steps, args.warmup, flush, True)
     comm = m["fmt"].commInfo()
+    if world > 1:
+        m["fmt"].commDestroy()       # collective and orderly, on every rank, before the ranks part ways
     qps = nq / (m["ms_step"] * 1e-3)
     e2e_qps = nq / (m["e2e_ms_step"] * 1e-3)
     h2d = nq * dim * 4 * world
@@ -632,6 +644,9 @@ def main():
     ap.add_argument("--ref-queries-per-step", type=int, default=1, help="--impl reference: queries per thread and step")
     ap.add_argument("--ref-threads", type=int, default=0, help="--impl reference: host threads (0 = all cores)")
     args = ap.parse_args()
+    if os.environ.get("BBQ_BENCH_WATCHDOG"):   # diagnostics: dump every Python stack and exit if the run blocks this long
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["BBQ_BENCH_WATCHDOG"]), exit=True)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     w = dict(WORKLOADS[args.workload])
     if args.nq > 0:

@@ -1381,6 +1381,7 @@ struct NcclApi {
   decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
   decltype(&ncclCommInitRank) CommInitRank = nullptr;
   decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclCommAbort) CommAbort = nullptr;
   decltype(&ncclAllGather) AllGather = nullptr;
   decltype(&ncclAllReduce) AllReduce = nullptr;
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
@@ -1411,6 +1412,7 @@ static NcclApi* nccl_api() {
     BBQ_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
     BBQ_NCCL_SYM(CommInitRank, "ncclCommInitRank")
     BBQ_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    BBQ_NCCL_SYM(CommAbort, "ncclCommAbort")
     BBQ_NCCL_SYM(AllGather, "ncclAllGather")
     BBQ_NCCL_SYM(AllReduce, "ncclAllReduce")
     BBQ_NCCL_SYM(GetErrorString, "ncclGetErrorString")
@@ -1426,10 +1428,14 @@ static NcclApi* nccl_api() {
     if (_r != ncclSuccess) return fail(BBQ_ERR_COMM, std::string(#expr) + ": " + nccl_api()->GetErrorString(_r)); \
   } while (0)
 
+// Implicit release (bbq_destroy, a garbage collector's finalizer): ncclCommAbort — LOCAL, never waits for a peer.
+// ncclCommDestroy synchronises with the other ranks and deadlocks when one rank's context is finalised while its
+// peers are elsewhere (seen: rank 0 in a destructor, rank 1 in a barrier).  bbq_comm_destroy is the orderly,
+// collective way out.
 static void comm_release(bbq_ctx* c) {
   if (c->comm) {
     NcclApi* a = nccl_api();
-    if (a->ok) a->CommDestroy(c->comm);
+    if (a->ok) a->CommAbort(c->comm);
     c->comm = nullptr;
   }
 }
@@ -1464,7 +1470,11 @@ extern "C" int bbq_comm_destroy(bbq_ctx* c) {
   if (!c) return fail(BBQ_ERR_NULL, "null");
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
-  comm_release(c);
+  if (c->comm) {
+    NcclApi* a = nccl_api();
+    if (a->ok) NC(a->CommDestroy(c->comm));
+    c->comm = nullptr;
+  }
   c->rank = 0;
   c->world = 1;
   return BBQ_OK;

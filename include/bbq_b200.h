@@ -147,8 +147,11 @@ int bbq_search(bbq_index* index, const float* queries, uint32_t nq, int64_t k, i
                float* out_score, uint32_t* out_count);
 
 /* Device-resident variant: d_queries nq*dim f32, outputs nq*k each, all DEVICE memory; enqueued on
- * `stream` (a cudaStream_t; NULL = the context's stream) and not synchronised.  Unused tail slots
- * (k > n) hold idx -1, score -inf. */
+ * `stream` (a cudaStream_t; NULL = the context's stream).  The call may synchronise that stream internally (one
+ * overflow-flag read per batch of <= 4096 queries) but its last kernels are left running.  Unused tail slots
+ * (k > n) hold idx -1, score -inf.  All searches of a context share its scratch buffers: use ONE stream per
+ * context at a time (finish — synchronise — the work given to one stream before calling with another, or before
+ * any host-pointer entry, which runs on the context's own stream). */
 int bbq_search_device(bbq_index* index, const float* d_queries, uint32_t nq, uint32_t k,
                       int32_t* d_out_idx, float* d_out_score, void* stream);
 
@@ -184,6 +187,8 @@ int bbq_quantization_accuracy(bbq_ctx* ctx, const float* rows, const float* quer
 #define BBQ_COMM_ID_BYTES 128
 int bbq_comm_unique_id(uint8_t* out_id /* BBQ_COMM_ID_BYTES */);
 int bbq_comm_init(bbq_ctx* ctx, const uint8_t* id /* BBQ_COMM_ID_BYTES */, int rank, int world);
+/* Collective, like bbq_comm_init: every rank calls it (ncclCommDestroy).  A context that is destroyed while it still
+ * holds a communicator aborts it locally instead (ncclCommAbort), so finalizers never wait for a peer. */
 int bbq_comm_destroy(bbq_ctx* ctx);
 int bbq_comm_info(bbq_ctx* ctx, int* rank, int* world, int* nccl_version);
 
