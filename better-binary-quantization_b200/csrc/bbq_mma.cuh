@@ -728,6 +728,154 @@ __device__ void mma_drain_ring(const HitCtx* cx, uint64_t* ring, const uint32_t*
   }
 }
 
+// ---- the expansion role (warps 4 .. 4 + 4 G): packed 1-bit row -> weighted u8 A operand, straight into TMEM ----------
+// The (tile, chunk) sequence of a pass is one flat stream of chunks f = 0 .. total-1, handed over CH at a time (all
+// CH tcgen05.st in flight before the single wait::st); hand-off h belongs to group h % G.  Every group prefetches its
+// own chunks PF deep across tile boundaries, and group 0 asks L2 for each row four tiles ahead (the 16-byte loads
+// themselves come too late to hide an HBM round trip under a busy SM).
+template <int G, int CH>
+__device__ __forceinline__ void mma_expansion(const MmaParams& p, uint64_t* a_full, uint64_t* a_empty, uint32_t tmem_base,
+                                              uint32_t a_col, int nstage, int nchunks, int warp, int lane) {
+  const int grp = (warp - 4) >> 2;
+  const int r = ((warp - 4) & 3) * 32 + lane;  // row within the tile == TMEM lane
+  const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  constexpr int PF = 4;
+  constexpr int L2_AHEAD = 4;
+  static_assert(PF % CH == 0, "the prefetch queue holds whole hand-offs");
+  const int64_t my_tiles = (p.ntiles > blockIdx.x) ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t total = my_tiles * nchunks;
+  const int64_t hands = (total + CH - 1) / CH;  // hand-offs of the pass
+  // cursor of the NEXT chunk of this group to load: tile ordinal + chunk in tile + a row pointer per tile
+  int64_t pf_tile = 0;
+  int pf_kc = 0;
+  int pf_in = 0;                  // position of the cursor inside its hand-off (0 .. CH-1)
+  const uint4* pf_ptr = nullptr;  // nullptr: the row lies past the end of the shard (zero chunks)
+  auto row_ptr = [&](int64_t t) -> const uint8_t* {
+    if (t >= my_tiles) return nullptr;
+    const int64_t row = (p.tile_first + (blockIdx.x + t * gridDim.x) * p.tile_stride) * TILE_ROWS + r;
+    return row < p.n ? p.codes + row * (int64_t)p.row_bytes : nullptr;
+  };
+  auto pf_set_tile = [&]() {
+    pf_ptr = reinterpret_cast<const uint4*>(row_ptr(pf_tile));
+    if (grp == 0 && !(p.debug & 128u)) {
+      const uint8_t* far = row_ptr(pf_tile + L2_AHEAD);
+      if (far != nullptr)
+        for (int b = 0; b < p.row_bytes; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(far + b));
+    }
+  };
+  auto pf_advance = [&](int k) {
+    pf_kc += k;
+    bool moved = false;
+    while (pf_kc >= nchunks) {
+      pf_kc -= nchunks;
+      pf_tile++;
+      moved = true;
+    }
+    if (moved) pf_set_tile();
+  };
+  auto load_next = [&]() -> uint4 {  // the chunk under the cursor; then on to this group's next chunk
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (pf_ptr != nullptr) v = __ldg(pf_ptr + pf_kc);
+    if (++pf_in == CH) {
+      pf_in = 0;
+      pf_advance((G - 1) * CH + 1);
+    } else {
+      pf_advance(1);
+    }
+    return v;
+  };
+  auto expand = [&](const uint4& x, uint32_t (&e)[32]) {
+    const uint32_t ws[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      const uint32_t lo = ws[g], hi = ws[g] >> 4;
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        e[8 * g + b] = lo & (0x01010101u << b);      // u = b     : bit b   of each packed byte, weight 2^b
+        e[8 * g + 4 + b] = hi & (0x01010101u << b);  // u = 4 + b : bit 4+b of each packed byte, weight 2^b
+      }
+    }
+  };
+  // (stage, phase) of the first chunk of this group's current hand-off; chunks are numbered through all passes
+  uint32_t stage = 0, sphase = 0;
+  auto stage_inc = [&](uint32_t& st_, uint32_t& ph_) {
+    if (++st_ == (uint32_t)nstage) {
+      st_ = 0;
+      ph_ ^= 1u;
+    }
+  };
+  for (int k = 0; k < CH * grp; k++) stage_inc(stage, sphase);
+  int exp_ev = 0;
+  for (int pass = 0; pass < p.passes; pass++) {
+    uint4 q[PF];
+    pf_tile = 0;
+    pf_kc = 0;
+    pf_in = 0;
+    pf_set_tile();
+    pf_advance(CH * grp);
+#pragma unroll
+    for (int i = 0; i < PF; i++) q[i] = load_next();
+    for (int64_t h0 = grp; h0 < hands; h0 += (PF / CH) * G) {
+#pragma unroll
+      for (int i = 0; i < PF; i += CH) {
+        const int64_t h = h0 + (i / CH) * G;  // this group's hand-off
+        if (h < hands) {
+          const bool tr = (p.debug & 32u) && blockIdx.x == 0 && warp == 4 && lane == 0 && pass == 0 && exp_ev < 1000;
+          long long x0 = tr ? clock64() : 0;
+          uint32_t e[2][32];
+          uint32_t sid[CH];
+          uint32_t st_ = stage, ph_ = sphase;
+          const int nval = (int)min((int64_t)CH, total - CH * h);  // chunks of this hand-off that exist (the stream may end short)
+#pragma unroll
+          for (int c = 0; c < CH; c++) {
+            expand(q[i + c], e[c & 1]);  // (a zero chunk past the end of the stream: loaded, never stored)
+            q[i + c] = load_next();
+            sid[c] = st_;
+            if (c < nval) {
+              mbar_wait_relaxed(a_empty + st_, ph_ ^ 1u);
+              tc_fence_after();
+              tc_st32(lane_addr + a_col + st_ * 32u, e[c & 1]);
+            }
+            stage_inc(st_, ph_);
+          }
+          long long x3 = tr ? clock64() : 0;
+          tc_wait_st();
+          long long x4 = tr ? clock64() : 0;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {  // one arrival per expansion warp and stage
+#pragma unroll
+            for (int c = 0; c < CH; c++)
+              if (c < nval) mbar_arrive(a_full + sid[c]);
+          }
+          if (tr) {
+            long long* d = p.trace + 1 * 4096 + exp_ev * 8;
+            d[0] = x0; d[1] = x0; d[2] = x0; d[3] = x3; d[4] = x4; d[5] = clock64();
+            exp_ev++;
+          }
+          for (int k = 0; k < CH * G; k++) stage_inc(stage, sphase);  // on to this group's next hand-off
+        }
+      }
+    }
+    // chunk numbers run on through the passes: re-base this group's (stage, phase) for the next pass.  The loop
+    // above advanced it in steps of CH * G from CH * grp; the next pass starts at total + CH * grp.
+    {
+      const int64_t mine = hands > grp ? (hands - grp + G - 1) / G : 0;  // hand-offs this group handled
+      const int64_t at = CH * grp + mine * CH * G;                        // where the stepping left off
+      const int64_t want = total + CH * grp;                              // first chunk of the next pass
+      for (int64_t k = at; k < want; k++) stage_inc(stage, sphase);
+      for (int64_t k = want; k < at; k++) {  // (a few positions at most)
+        if (stage == 0u) {
+          stage = (uint32_t)nstage - 1u;
+          sphase ^= 1u;
+        } else {
+          stage--;
+        }
+      }
+    }
+  }
+}
+
 // CPQ = accumulator columns per query: 1, or 2 when the query code is split into nibbles (k_query_tiles); then the
 // epilogue works on val = 16 * D_hi + D_lo = 8 * dot and every per-query table is indexed by column / 2.
 template <int MODE, int SIM, int CPQ>
@@ -884,157 +1032,16 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
     // ===== drainer: exact replay of the parked hits, candidate append, threshold tightening =====
     if (MODE == SCAN_FILTER) mma_drain_ring<SIM>(hit_s, ring_s, ring_ctl_s + 0, ring_ctl_s + 1, ring_ctl_s + 2, lane);
   } else if (warp >= 4 && warp < MMA_EPI_WARP0) {
-    // ===== expansion: packed 1-bit row -> weighted u8 A operand, straight into TMEM =====
-    // The (tile, chunk) sequence of a pass is one flat stream of chunks f = 0 .. total-1, handed over in PAIRS
-    // (both tcgen05.st in flight before the single wait::st); with two groups, pair h belongs to group h % 2.  Every
-    // group prefetches its own chunks PF deep across tile boundaries, and group 0 asks L2 for each row four tiles
-    // ahead (the 16-byte loads themselves come too late to hide an HBM round trip under a busy SM).
-    constexpr int G = MMA_EXP_GROUPS;
-    constexpr int CH = G == 1 ? 2 : 1;  // chunks per hand-off: a single group pairs them, two groups alternate single chunks
-    const int grp = (warp - 4) >> 2;
-    const int r = ((warp - 4) & 3) * 32 + lane;  // row within the tile == TMEM lane
-    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    constexpr int PF = 4;
-    constexpr int L2_AHEAD = 4;
-    const int64_t my_tiles = (p.ntiles > blockIdx.x) ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t total = my_tiles * nchunks;
-    const int64_t hands = (total + CH - 1) / CH;  // hand-offs of the pass; hand-off h belongs to group h % G
-    // cursor of the NEXT chunk of this group to load: tile ordinal + chunk in tile + a row pointer per tile
-    int64_t pf_tile = 0;
-    int pf_kc = 0;
-    int pf_in = 0;                  // position of the cursor inside its hand-off (0 .. CH-1)
-    const uint4* pf_ptr = nullptr;  // nullptr: the row lies past the end of the shard (zero chunks)
-    auto row_ptr = [&](int64_t t) -> const uint8_t* {
-      if (t >= my_tiles) return nullptr;
-      const int64_t row = (p.tile_first + (blockIdx.x + t * gridDim.x) * p.tile_stride) * TILE_ROWS + r;
-      return row < p.n ? p.codes + row * (int64_t)p.row_bytes : nullptr;
-    };
-    auto pf_set_tile = [&]() {
-      pf_ptr = reinterpret_cast<const uint4*>(row_ptr(pf_tile));
-      if (grp == 0 && !(p.debug & 128u)) {
-        const uint8_t* far = row_ptr(pf_tile + L2_AHEAD);
-        if (far != nullptr)
-          for (int b = 0; b < p.row_bytes; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(far + b));
-      }
-    };
-    auto pf_advance = [&](int k) {
-      pf_kc += k;
-      bool moved = false;
-      while (pf_kc >= nchunks) {
-        pf_kc -= nchunks;
-        pf_tile++;
-        moved = true;
-      }
-      if (moved) pf_set_tile();
-    };
-    auto load_next = [&]() -> uint4 {  // the chunk under the cursor; then on to this group's next chunk
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (pf_ptr != nullptr) v = __ldg(pf_ptr + pf_kc);
-      if (++pf_in == CH) {
-        pf_in = 0;
-        pf_advance((G - 1) * CH + 1);
-      } else {
-        pf_advance(1);
-      }
-      return v;
-    };
-    auto expand = [&](const uint4& x, uint32_t (&e)[32]) {
-      const uint32_t ws[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-      for (int g = 0; g < 4; g++) {
-        const uint32_t lo = ws[g], hi = ws[g] >> 4;
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-          e[8 * g + b] = lo & (0x01010101u << b);      // u = b     : bit b   of each packed byte, weight 2^b
-          e[8 * g + 4 + b] = hi & (0x01010101u << b);  // u = 4 + b : bit 4+b of each packed byte, weight 2^b
-        }
-      }
-    };
-    auto wait_stage = [&](uint32_t st_, uint32_t ph_) {
-      mbar_wait_relaxed(a_empty + st_, ph_ ^ 1u);
-      tc_fence_after();
-    };
-    // (stage, phase) of the first chunk of this group's current hand-off; chunks are numbered through all passes
-    uint32_t stage = 0, sphase = 0;
-    auto stage_inc = [&](uint32_t& st_, uint32_t& ph_) {
-      if (++st_ == (uint32_t)nstage) {
-        st_ = 0;
-        ph_ ^= 1u;
-      }
-    };
-    for (int k = 0; k < CH * grp; k++) stage_inc(stage, sphase);
-    int exp_ev = 0;
-    for (int pass = 0; pass < p.passes; pass++) {
-      uint4 q[PF];
-      pf_tile = 0;
-      pf_kc = 0;
-      pf_in = 0;
-      pf_set_tile();
-      pf_advance(CH * grp);
-#pragma unroll
-      for (int i = 0; i < PF; i++) q[i] = load_next();
-      for (int64_t h0 = grp; h0 < hands; h0 += (PF / CH) * G) {
-#pragma unroll
-        for (int i = 0; i < PF; i += CH) {
-          const int64_t h = h0 + (i / CH) * G;  // this group's hand-off
-          if (h < hands) {
-            const bool two = CH == 2 && CH * h + 1 < total;
-            const bool tr = (p.debug & 32u) && blockIdx.x == 0 && warp == 4 && lane == 0 && pass == 0 && exp_ev < 1000;
-            long long x0 = tr ? clock64() : 0;
-            uint32_t e0[32];
-            expand(q[i], e0);
-            q[i] = load_next();
-            const uint32_t s0 = stage, p0 = sphase;
-            uint32_t s1 = stage, p1 = sphase;
-            stage_inc(s1, p1);
-            long long x1 = tr ? clock64() : 0;
-            wait_stage(s0, p0);
-            long long x2 = tr ? clock64() : 0;
-            tc_st32(lane_addr + a_col + s0 * 32u, e0);
-            if (CH == 2) {
-              uint32_t e1[32];
-              expand(q[(i + 1) % PF], e1);  // (a zero chunk when the stream ends on an odd count: loaded, never stored)
-              q[(i + 1) % PF] = load_next();
-              if (two) {
-                wait_stage(s1, p1);
-                tc_st32(lane_addr + a_col + s1 * 32u, e1);
-              }
-            }
-            long long x3 = tr ? clock64() : 0;
-            tc_wait_st();
-            long long x4 = tr ? clock64() : 0;
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {  // one arrival per expansion warp and stage
-              mbar_arrive(a_full + s0);
-              if (two) mbar_arrive(a_full + s1);
-            }
-            if (tr) {
-              long long* d = p.trace + 1 * 4096 + exp_ev * 8;
-              d[0] = x0; d[1] = x1; d[2] = x2; d[3] = x3; d[4] = x4; d[5] = clock64();
-              exp_ev++;
-            }
-            for (int k = 0; k < CH * G; k++) stage_inc(stage, sphase);  // on to this group's next hand-off
-          }
-        }
-      }
-      // chunk numbers run on through the passes: re-base this group's (stage, phase) for the next pass.  The loop
-      // above advanced it in steps of CH * G from CH * grp; the next pass starts at total + CH * grp.
-      {
-        const int64_t mine = hands > grp ? (hands - grp + G - 1) / G : 0;  // hand-offs this group handled
-        const int64_t at = CH * grp + mine * CH * G;                        // where the stepping left off
-        const int64_t want = total + CH * grp;                              // first chunk of the next pass
-        for (int64_t k = at; k < want; k++) stage_inc(stage, sphase);
-        for (int64_t k = want; k < at; k++) {  // (a few positions at most)
-          if (stage == 0u) {
-            stage = (uint32_t)nstage - 1u;
-            sphase ^= 1u;
-          } else {
-            stage--;
-          }
-        }
-      }
-    }
+    // ===== expansion: packed 1-bit row -> weighted u8 A operand, straight into TMEM (mma_expansion above) =====
+    // Chunks per hand-off: one group pairs them; with 8 A stages (<= 128 accumulator columns per buffer: small and
+    // medium batches, wide rows) it hands over FOUR at a time — the tcgen05.wait::st round trip, not the ALU work,
+    // bounds the feed, and four stores in flight amortise it twice as well; two groups alternate single chunks.
+    if (MMA_EXP_GROUPS == 2)
+      mma_expansion<MMA_EXP_GROUPS, 1>(p, a_full, a_empty, tmem_base, a_col, nstage, nchunks, warp, lane);
+    else if (nstage >= 8 && !(p.debug & 512u))
+      mma_expansion<1, 4>(p, a_full, a_empty, tmem_base, a_col, nstage, nchunks, warp, lane);
+    else
+      mma_expansion<1, 2>(p, a_full, a_empty, tmem_base, a_col, nstage, nchunks, warp, lane);
   } else if (warp >= MMA_EPI_WARP0) {
     // ===== epilogue: first-level integer screen on the accumulators, second level + parking for what passes =====
     const int ew = warp - MMA_EPI_WARP0;           // 0 .. MMA_EPI_WARPS-1
