@@ -586,7 +586,38 @@ def secondary_results(args, torch, bbq, local_rank, flush, peaks, probe):
         except Exception as e:  # a secondary workload must never take the headline line down with it
             out.append({"workload": w["name"], "error": f"{type(e).__name__}: {e}"})
         torch.cuda.empty_cache()
+    out.append(quicksearch_c1(args, bbq))
     return out
+
+
+def quicksearch_c1(args, bbq):
+    """BASELINE configs[0], the reference's own CPU-runnable case: quickSearch(query, vectors, 10, COSINE) on a 1000 x 128
+    corpus — the index is REBUILT on every call (src/index.ts:95-111), so this is build + search latency through the
+    reference-shaped host API (host rows in, result objects out), beside the oracle's quick_search on one core."""
+    try:
+        from oracle import oracle as O
+        rng = np.random.default_rng(SEED_CORPUS)
+        base = rng.standard_normal((1000, 128), dtype=np.float32)
+        qs = rng.standard_normal((32, 128), dtype=np.float32)
+        for q in qs[:3]:
+            bbq.quickSearch(q, base, 10)
+        t0 = time.perf_counter()
+        got = [bbq.quickSearch(q, base, 10) for q in qs]
+        dt = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        want = [O.quick_search(q, base, 10, "COSINE") for q in qs[:8]]
+        dtc = time.perf_counter() - t1
+        ok = all([r["index"] for r in got[i]] == want[i][0].tolist() and
+                 [np.float32(r["score"]) for r in got[i]] == want[i][1].tolist() for i in range(8))
+        return {"workload": "quickSearch on 1000 x 128 f32, k=10, COSINE, index rebuilt per call (BASELINE configs[0])",
+                "value": len(qs) / dt, "unit": "quickSearch calls/s", "ms_per_call": 1e3 * dt / len(qs),
+                "cpu_baseline": {"value": 8 / dtc, "unit": "quickSearch calls/s", "cores": 1, "kind": "port",
+                                 "sample": f"8 calls, {dtc:.2f}s"},
+                "parity": {"calls_checked": 8, "lists_and_scores_identical": bool(ok)},
+                "note": "host API end to end: H2D of the 512 KB corpus, device index build (K5), query quantisation, "
+                        "scan, selection, D2H — per call"}
+    except Exception as e:
+        return {"workload": "quickSearch (BASELINE configs[0])", "error": f"{type(e).__name__}: {e}"}
 
 
 _REAL_STDOUT = None

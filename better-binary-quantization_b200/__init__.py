@@ -22,15 +22,28 @@ def createBinaryQuantizationFormat(config=None, device: int = -1) -> BinaryQuant
     return BinaryQuantizationFormat(config if config is not None else DEFAULT_CONFIG, device=device)
 
 
+_QUICK_FORMATS = {}
+
+
+def _quick_format(similarityFunction) -> BinaryQuantizationFormat:
+    """The reference builds a fresh format object per quick* call (src/index.ts:76-82,101-107); a format carries no
+    state between calls, so one per similarity function is kept: its device context owns the scratch buffers, and
+    re-creating those on every call costs more than the 1000-row search the helpers are meant for."""
+    fmt = _QUICK_FORMATS.get(similarityFunction)
+    if fmt is None:
+        fmt = BinaryQuantizationFormat({"quantizer": {"similarityFunction": similarityFunction, "lambda": 0.1, "iters": 5}})
+        _QUICK_FORMATS[similarityFunction] = fmt
+    return fmt
+
+
 def quickQuantize(vectors, similarityFunction=VectorSimilarityFunction.COSINE):
     """src/index.ts:72-85"""
-    fmt = BinaryQuantizationFormat({"quantizer": {"similarityFunction": similarityFunction, "lambda": 0.1, "iters": 5}})
-    return fmt.quantizeVectors(vectors)
+    return _quick_format(similarityFunction).quantizeVectors(vectors)
 
 
 def quickSearch(queryVector, targetVectors, k, similarityFunction=VectorSimilarityFunction.COSINE):
     """src/index.ts:95-111 — like the reference, re-quantises the corpus on every call."""
-    fmt = BinaryQuantizationFormat({"quantizer": {"similarityFunction": similarityFunction, "lambda": 0.1, "iters": 5}})
+    fmt = _quick_format(similarityFunction)
     qv = fmt.quantizeVectors(targetVectors)["quantizedVectors"]
     return fmt.searchNearestNeighbors(queryVector, qv, k)
 

@@ -23,6 +23,7 @@ try:
 except Exception as e:
     print("bench parse failed:", e)
 PY
+[ "${NCU:-1}" = 1 ] || exit 0
 # ncu: the same command, plain first (must exit 0), then the launch list of the search kernels and one full capture
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu --no-secondary"
 timeout -s KILL 300 $CMD > gpurun_out/${tag}_ncu_plain.log 2>&1 && \
