@@ -299,3 +299,32 @@ def test_wide_queries_on_the_tensor_core_scan(bbq, qb):
     d = fm.debugQcDistBatch(qs[:5], qm)
     _, _, _, alld = O.search_nearest_neighbors(qs[3], idx, 1, query_bits=qb, want_all=True)
     assert np.array_equal(d[3], alld)
+
+
+def test_pinned_host_buffers_and_limits(bbq):
+    """bbq_host_alloc / bbq_host_free (page-locked query / result buffers for a host) and the documented limits."""
+    import ctypes as C
+    L = bbq._native.load()
+    rows, qs = gaussian(5000, 64, 1401), gaussian(6, 64, 1402)
+    fmt = make_format(bbq, "COSINE")
+    qv = fmt.quantizeVectors(rows)["quantizedVectors"]
+    want_i, want_s = fmt.searchBatch(qs, qv, 10)
+    nbytes_q, nbytes_o = qs.nbytes, 6 * 10 * 4
+    hq, hi, hs = L.bbq_host_alloc(nbytes_q), L.bbq_host_alloc(nbytes_o), L.bbq_host_alloc(nbytes_o)
+    assert hq and hi and hs
+    try:
+        C.memmove(hq, qs.ctypes.data, nbytes_q)
+        cnt = C.c_uint32(0)
+        assert L.bbq_search(qv._h, hq, 6, 10, hi, hs, C.byref(cnt)) == 0 and cnt.value == 10
+        got_i = np.frombuffer((C.c_int32 * 60).from_address(hi), np.int32).reshape(6, 10)
+        got_s = np.frombuffer((C.c_float * 60).from_address(hs), np.float32).reshape(6, 10)
+        assert np.array_equal(got_i, want_i) and bits_equal(got_s.copy(), want_s)
+    finally:
+        for p in (hq, hi, hs):
+            L.bbq_host_free(p)
+    with pytest.raises(bbq.BbqError) as e:       # the device top-k serves k <= 4096
+        fmt.searchBatch(qs, qv, 4097)
+    assert e.value.status == 9
+    with pytest.raises(bbq.BbqError) as e:       # indexBits > 2: neither the reference's search nor this build's
+        bbq.createBinaryQuantizationFormat({"indexBits": 3, "quantizer": {"similarityFunction": "COSINE"}}).quantizeVectors(rows)
+    assert e.value.status == 9
