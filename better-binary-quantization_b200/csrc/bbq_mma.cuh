@@ -826,16 +826,25 @@ __device__ __forceinline__ void mma_expansion(const MmaParams& p, uint64_t* a_fu
           uint32_t sid[CH];
           uint32_t st_ = stage, ph_ = sphase;
           const int nval = (int)min((int64_t)CH, total - CH * h);  // chunks of this hand-off that exist (the stream may end short)
+          long long t_exp = 0, t_wait = 0, t_st = 0;  // (timeline only)
 #pragma unroll
           for (int c = 0; c < CH; c++) {
+            const long long ya = tr ? clock64() : 0;
             expand(q[i + c], e[c & 1]);  // (a zero chunk past the end of the stream: loaded, never stored)
             q[i + c] = load_next();
             sid[c] = st_;
+            const long long yb = tr ? clock64() : 0;
             if (c < nval) {
               mbar_wait_relaxed(a_empty + st_, ph_ ^ 1u);
               tc_fence_after();
+              const long long yc = tr ? clock64() : 0;
               tc_st32(lane_addr + a_col + st_ * 32u, e[c & 1]);
+              if (tr) {
+                t_wait += yc - yb;
+                t_st += clock64() - yc;
+              }
             }
+            if (tr) t_exp += yb - ya;
             stage_inc(st_, ph_);
           }
           long long x3 = tr ? clock64() : 0;
@@ -850,7 +859,7 @@ __device__ __forceinline__ void mma_expansion(const MmaParams& p, uint64_t* a_fu
           }
           if (tr) {
             long long* d = p.trace + 1 * 4096 + exp_ev * 8;
-            d[0] = x0; d[1] = x0; d[2] = x0; d[3] = x3; d[4] = x4; d[5] = clock64();
+            d[0] = x0; d[1] = t_exp; d[2] = t_wait; d[3] = t_st; d[4] = x4 - x3; d[5] = clock64() - x4; d[6] = x3 - x0;
             exp_ev++;
           }
           for (int k = 0; k < CH * G; k++) stage_inc(stage, sphase);  // on to this group's next hand-off
