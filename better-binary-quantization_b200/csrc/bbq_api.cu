@@ -92,6 +92,7 @@ struct bbq_ctx {
   int query_quantizer = 0;  // BBQ_QQUANT=thread forces the one-thread-per-query form (tests)
   int scan_engine = 0;  // BBQ_SCAN: 0 auto, 1 popcount kernel only, 2 tensor-core kernel whenever it can run
   uint32_t* h_flag = nullptr;  // pinned: [0..nq) candidate counts, [nq] overflow flag, then 2 words: first invalid query
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;  // ordering between the context's stream and a caller's stream (StreamBridge)
   // sharded search (bbq_comm_init): one NCCL communicator per context = per GPU = per process
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
@@ -129,6 +130,25 @@ struct ProfScope {  // records an event pair around a group of launches when pro
     if (!a) return;
     cudaEventRecord(b, st);
     c->ev_pending.push_back({a, b, kind});
+  }
+};
+
+// All searches of a context share its scratch buffers.  When a caller hands in a stream of its own, the work it gets
+// there is ordered AFTER everything already queued on the context's stream and BEFORE anything queued on it later, so
+// that a host-pointer call (context stream) and a device-pointer call (caller stream) can follow each other without
+// an explicit synchronisation.  Two caller streams used concurrently on one context remain the caller's business.
+struct StreamBridge {
+  bbq_ctx* c;
+  cudaStream_t st;
+  StreamBridge(bbq_ctx* c_, cudaStream_t st_) : c(c_), st(st_) {
+    if (st == c->stream) return;
+    cudaEventRecord(c->ev_in, c->stream);
+    cudaStreamWaitEvent(st, c->ev_in, 0);
+  }
+  ~StreamBridge() {
+    if (st == c->stream) return;
+    cudaEventRecord(c->ev_out, st);
+    cudaStreamWaitEvent(c->stream, c->ev_out, 0);
   }
 };
 
@@ -201,6 +221,8 @@ extern "C" int bbq_create(const bbq_config* config, bbq_ctx** out_ctx) {
   c->sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaMallocHost(&c->h_flag, (QUERY_BATCH + 4) * sizeof(uint32_t)));
+  CU(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
   if (const char* e = getenv("BBQ_FORCE_PATH")) c->force_path = atoi(e);
   if (const char* e = getenv("BBQ_SAMPLE_TILES")) c->sample_tiles_dyn = std::max(1, std::min(128, atoi(e)));
   if (const char* e = getenv("BBQ_CSA")) c->csa = atoi(e);
@@ -228,6 +250,8 @@ static void ctx_release(bbq_ctx* c) {
     b->release();
   comm_release(c);
   if (c->h_flag) cudaFreeHost(c->h_flag);
+  if (c->ev_in) cudaEventDestroy(c->ev_in);
+  if (c->ev_out) cudaEventDestroy(c->ev_out);
   for (auto& p : c->ev_pending) {
     cudaEventDestroy(p.a);
     cudaEventDestroy(p.b);
@@ -1200,6 +1224,7 @@ extern "C" int bbq_search_device(bbq_index* ix, const float* d_queries, uint32_t
   bbq_ctx* c = ix->ctx;
   CU(cudaSetDevice(c->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  StreamBridge bridge(c, st);
   for (uint32_t q0 = 0; q0 < nq; q0 += QUERY_BATCH) {
     const int nb = (int)std::min<uint32_t>(QUERY_BATCH, nq - q0);
     TRY(search_batch(ix, d_queries + (size_t)q0 * ix->dim, nb, k, d_out_idx + (size_t)q0 * k,
@@ -1523,6 +1548,7 @@ extern "C" int bbq_search_sharded_device(bbq_index* ix, const float* d_queries, 
   if (!c->comm || c->world == 1) return bbq_search_device(ix, d_queries, nq, k, d_out_idx, d_out_score, stream);
   CU(cudaSetDevice(c->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  StreamBridge bridge(c, st);  // (the local search inside builds its own, nested: harmless)
   const size_t cnt = (size_t)nq * k;
   TRY(c->loc_idx.reserve(cnt * sizeof(int32_t)));
   TRY(c->loc_score.reserve(cnt * sizeof(float)));

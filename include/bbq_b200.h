@@ -149,9 +149,10 @@ int bbq_search(bbq_index* index, const float* queries, uint32_t nq, int64_t k, i
 /* Device-resident variant: d_queries nq*dim f32, outputs nq*k each, all DEVICE memory; enqueued on
  * `stream` (a cudaStream_t; NULL = the context's stream).  The call may synchronise that stream internally (one
  * overflow-flag read per batch of <= 4096 queries) but its last kernels are left running.  Unused tail slots
- * (k > n) hold idx -1, score -inf.  All searches of a context share its scratch buffers: use ONE stream per
- * context at a time (finish — synchronise — the work given to one stream before calling with another, or before
- * any host-pointer entry, which runs on the context's own stream). */
+ * (k > n) hold idx -1, score -inf.  All searches of a context share its scratch buffers: work given to a caller's
+ * stream is ordered (by events) after what is already queued on the context's own stream and before what is queued
+ * there later, so host-pointer entries (context stream) and device-pointer entries may follow each other freely; do
+ * not run two caller streams on one context concurrently. */
 int bbq_search_device(bbq_index* index, const float* d_queries, uint32_t nq, uint32_t k,
                       int32_t* d_out_idx, float* d_out_score, void* stream);
 
