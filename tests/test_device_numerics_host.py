@@ -108,3 +108,48 @@ def test_topk_key_total_order(hn):
         assert hn.hn_key_id(k) == 123 and hn.hn_key_score(k) == np.float32(v) + np.float32(0)
     assert np.isnan(hn.hn_key_score(hn.hn_topk_key(float("nan"), 5)))
     assert hn.hn_topk_key(float("nan"), 0xFFFFFFFE) > 0   # 0 is reserved for "empty slot"
+
+
+# ---- round 2: the extension's score formula, the single-vector scorer, the accuracy statistics ------------------
+@pytest.mark.parametrize("sim", ["EUCLIDEAN", "COSINE", "MAXIMUM_INNER_PRODUCT"])
+@pytest.mark.parametrize("qb,ib", [(8, 2), (4, 2), (1, 2), (4, 1), (8, 1), (1, 1)])
+def test_scores_any_bits_bit_exact(hn, sim, qb, ib):
+    """score_f32 as the scan kernels call it (score mode, lx divisor, query terms) == the oracle: the reference's formulas
+    for a 1-bit index, the extension's (oracle/bbq_oracle.cpp:score_ext) for a 2-bit one."""
+    hn.hn_scores_bits.argtypes = [i32p, f64p, C.c_int64, f64p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, f32p]
+    rows, qs = gaussian(300, 192, 15 + ib), gaussian(3, 192, 16 + qb)
+    idx = O.quantize_vectors(rows, sim=sim, index_bits=ib)
+    cdp = O.centroid_dp(idx.centroid)
+    for q in qs:
+        _, _, alls, alld = O.search_nearest_neighbors(q, idx, 3, query_bits=qb, want_all=True)
+        _, qcorr = O.quantize_query_vector(q, idx.centroid, sim=sim, query_bits=qb)
+        got = np.empty(len(alld), np.float32)
+        hn.hn_scores_bits(alld.ctypes.data_as(i32p), idx.corr.ctypes.data_as(f64p), len(alld), qcorr.ctypes.data_as(f64p),
+                          192, cdp, O.SIM[sim], qb, ib, got.ctypes.data_as(f32p))
+        assert np.array_equal(alls.view(np.uint32), got.view(np.uint32))
+
+
+@pytest.mark.parametrize("sim", ["EUCLIDEAN", "COSINE", "MAXIMUM_INNER_PRODUCT"])
+@pytest.mark.parametrize("qb", [1, 4])
+def test_single_vector_score_and_accuracy_stats_bit_exact(hn, sim, qb):
+    """The single-vector scorer (computeQuantizedScore) and the statistics of computeQuantizationAccuracy, header vs
+    oracle, f64 bit patterns."""
+    hn.hn_score_single.argtypes = [C.c_double, f64p, f64p, C.c_int, C.c_double, C.c_int, C.c_int]
+    hn.hn_score_single.restype = C.c_double
+    hn.hn_accuracy_stats.argtypes = [f64p, f64p, C.c_int64, f64p]
+    L = O.lib()
+    rows, qs = gaussian(40, 96, 21), gaussian(40, 96, 22)
+    idx = O.quantize_vectors(rows, sim=sim)
+    cdp = O.centroid_dp(idx.centroid) if qb == 1 else 0.0
+    xc = np.ascontiguousarray(idx.corr[0])
+    for q in qs[:10]:
+        codes, qc = O.quantize_query_vector_once(q, idx.centroid, sim, qb)
+        dot = float(O.dot_unpacked(codes, idx.unpacked[0]))
+        want = L.bbqo_score_single(dot, xc.ctypes.data_as(f64p), qc.ctypes.data_as(f64p), 96, cdp, O.SIM[sim], qb)
+        got = hn.hn_score_single(dot, xc.ctypes.data_as(f64p), qc.ctypes.data_as(f64p), 96, cdp, O.SIM[sim], qb)
+        assert np.float64(want).view(np.uint64) == np.float64(got).view(np.uint64)
+    stats, orig, quant = O.compute_quantization_accuracy(rows, qs, sim, qb, want_scores=True)
+    out = np.empty(5, np.float64)
+    hn.hn_accuracy_stats(orig.ctypes.data_as(f64p), quant.ctypes.data_as(f64p), len(orig), out.ctypes.data_as(f64p))
+    want5 = np.array([stats[k] for k in ("meanError", "maxError", "minError", "stdError", "correlation")])
+    assert _same(out, want5)
