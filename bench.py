@@ -380,6 +380,8 @@ def roofline_of(w, m, world, steps, peaks, probe, workload_key):
                     "frac_of_2x_bf16_sustained": achieved / (2.0 * peaks["bf16_sustained"]),
                     "kernel": "bbqk::k_scan_mma<SCAN_FILTER>", "algorithmic_ops_per_launch": ops,
                     "queries_resident_per_pass": st["mma_n_tile"], "passes_over_shard": st["mma_passes"],
+                    "role_layout": "narrow-batch (4 epilogue warps + 2 expansion groups)" if st.get("mma_layout") else
+                                   "wide-batch (8 epilogue warps + 1 expansion group)",
                     "hbm_view": {"algorithmic_bytes_per_launch": algo_bytes, "index_GBps": index_gbps,
                                  "streamed_GBps": index_gbps * st["mma_passes"],
                                  "frac_of_hbm_peak": index_gbps / peaks["hbm"]}}

@@ -39,7 +39,7 @@ class BbqConfig(C.Structure):
 
 class BbqStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("last_candidates", C.c_uint64), ("last_path", C.c_uint32),
-                ("last_overflow", C.c_uint32), ("last_engine", C.c_uint32), ("reserved0", C.c_uint32),
+                ("last_overflow", C.c_uint32), ("last_engine", C.c_uint32), ("mma_layout", C.c_uint32),
                 ("scan_launches", C.c_uint64), ("scan_ms", C.c_double),
                 ("quantize_ms", C.c_double), ("select_ms", C.c_double), ("sample_ms", C.c_double),
                 ("mma_n_tile", C.c_uint32), ("mma_passes", C.c_uint32)]

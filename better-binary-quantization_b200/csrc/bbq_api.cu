@@ -87,6 +87,9 @@ struct bbq_ctx {
   int csa = 1;              // BBQ_CSA=0: plain popcount accumulation in the streaming scan (A/B, tests)
   int popc_form = 0;        // BBQ_POPC_FORM=tile forces the shared-memory tile form of the popcount scan (tests)
   int mma_ntile_cap = 0;    // BBQ_MMA_NTILE: cap on the queries resident per pass (tuning experiments)
+  int mma_layout = -1;      // BBQ_MMA_LAYOUT: -1 by accumulator columns (mma_plan), 0 wide-batch roles, 1 narrow-batch roles
+  int mma_issuers = 0;      // BBQ_MMA_ISSUERS: 0 by layout (mma_plan: 2 wide, 3 narrow), else 1..3 MMA issuing threads
+  int mma_narrow_max = 96;  // BBQ_MMA_NARROW_MAX: widest resident block (accumulator columns) that takes the narrow-batch roles
   uint32_t mma_debug = 0;   // BBQ_MMA_DEBUG: timing-attribution knobs of the tensor-core scan (results become wrong)
   bool dynamic_tau = true;  // BBQ_DYNTAU=0 keeps the sampled threshold fixed during the tensor-core scan (tests)
   int query_quantizer = 0;  // BBQ_QQUANT=thread forces the one-thread-per-query form (tests)
@@ -229,6 +232,9 @@ extern "C" int bbq_create(const bbq_config* config, bbq_ctx** out_ctx) {
   if (const char* e = getenv("BBQ_K1S_CTAS")) c->k1s_ctas = std::max(1, atoi(e));
   if (const char* e = getenv("BBQ_POPC_FORM")) c->popc_form = !strcmp(e, "tile") ? 1 : 0;
   if (const char* e = getenv("BBQ_MMA_NTILE")) c->mma_ntile_cap = atoi(e);
+  if (const char* e = getenv("BBQ_MMA_LAYOUT")) c->mma_layout = atoi(e);
+  if (const char* e = getenv("BBQ_MMA_NARROW_MAX")) c->mma_narrow_max = atoi(e);
+  if (const char* e = getenv("BBQ_MMA_ISSUERS")) c->mma_issuers = std::max(0, std::min(3, atoi(e)));
   if (const char* e = getenv("BBQ_MMA_DEBUG")) c->mma_debug = (uint32_t)atoi(e);
   if (const char* e = getenv("BBQ_DYNTAU")) c->dynamic_tau = atoi(e) != 0;
   if (const char* e = getenv("BBQ_QQUANT")) c->query_quantizer = !strcmp(e, "thread") ? 1 : 0;
@@ -841,6 +847,8 @@ static int quantize_queries(bbq_index* ix, const float* d_queries, int nq, cudaS
 struct MmaPlan {
   int n_tile = 0, passes = 0, nstage = 0, kbytes = 0;
   int cpq = 1;  // accumulator columns per query: 2 when the code is split into nibbles (k_query_tiles)
+  int nissuers = 2;  // MMA issuing threads
+  int layout = 0;  // MmaLayout: 0 = 8 epilogue warps + 1 expansion group, 1 = 4 + 2 (few resident queries: feed-bound)
   size_t smem = 0;
 };
 static bool mma_plan(const bbq_index* ix, int nq, MmaPlan* out) {
@@ -868,6 +876,12 @@ static bool mma_plan(const bbq_index* ix, int nq, MmaPlan* out) {
   pl.passes = (ncols + n_cap - 1) / n_cap;
   pl.n_tile = (((ncols + pl.passes - 1) / pl.passes) + 15) / 16 * 16;
   pl.nstage = std::min(8, (512 - 2 * pl.n_tile) / 32);
+  // Role layout by the width of the resident block (profiles/r02_k2_narrow_layout.txt, 1 M x 1024, ms per pass, wide -> narrow:
+  // 16 columns 0.136 -> 0.109, 64: 0.146 -> 0.127, 96: 0.151 -> 0.137, 128: 0.157 -> 0.155 (EUCLIDEAN: 0.175 -> 0.185), 208: 0.213 ->
+  // 0.218).  A narrow batch is bound by the ISSUE of its tcgen05 operations (32 MMAs + 12 commits per 128-row tile whatever
+  // the width, ~100-150 cycles each for the issuing thread), so the narrow layout also runs three issuing threads.
+  pl.layout = c->mma_layout >= 0 ? (c->mma_layout ? 1 : 0) : (pl.n_tile <= c->mma_narrow_max ? 1 : 0);
+  pl.nissuers = c->mma_issuers > 0 ? c->mma_issuers : (pl.layout == 1 ? 3 : 2);
   pl.smem = (size_t)pl.n_tile * pl.kbytes + (size_t)pl.n_tile * (sizeof(QScreen) + sizeof(bbqn::QueryTerms)) + 26 * 8 + sizeof(HitCtx) + HIT_RING * sizeof(uint64_t) + 16 + 16;
   *out = pl;
   return true;
@@ -902,17 +916,17 @@ static int prepare_mma_operands(bbq_index* ix, int nq, const MmaPlan& pl, cudaSt
   return BBQ_OK;
 }
 
-template <int MODE>
+template <int MODE, int LAYOUT>
 static int launch_mma_sim(bbq_ctx* c, int sim, int cpq, unsigned grid, size_t smem, cudaStream_t st, const MmaParams& p) {
-#define BBQ_MMA_CASE(S)                                                                                         \
-  case S:                                                                                                       \
-    if (cpq == 1) {                                                                                             \
-      CU(cudaFuncSetAttribute(k_scan_mma<MODE, S, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      LAUNCH(c, (k_scan_mma<MODE, S, 1>), grid, MMA_THREADS, smem, st, p);                                      \
-    } else {                                                                                                    \
-      CU(cudaFuncSetAttribute(k_scan_mma<MODE, S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      LAUNCH(c, (k_scan_mma<MODE, S, 2>), grid, MMA_THREADS, smem, st, p);                                      \
-    }                                                                                                           \
+#define BBQ_MMA_CASE(S)                                                                                                  \
+  case S:                                                                                                                \
+    if (cpq == 1) {                                                                                                      \
+      CU(cudaFuncSetAttribute(k_scan_mma<MODE, S, 1, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      LAUNCH(c, (k_scan_mma<MODE, S, 1, LAYOUT>), grid, MmaLayout<LAYOUT>::THREADS, smem, st, p);                       \
+    } else {                                                                                                             \
+      CU(cudaFuncSetAttribute(k_scan_mma<MODE, S, 2, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      LAUNCH(c, (k_scan_mma<MODE, S, 2, LAYOUT>), grid, MmaLayout<LAYOUT>::THREADS, smem, st, p);                       \
+    }                                                                                                                    \
     break;
   switch (sim) {
     BBQ_MMA_CASE(0)
@@ -959,6 +973,7 @@ static int launch_scan_mma(bbq_index* ix, int mode, int nq, uint32_t k, const Mm
   p.n_tile = pl.n_tile;
   p.passes = pl.passes;
   p.nstage = pl.nstage;
+  p.nissuers = pl.nissuers;
   p.dim = (double)ix->dim;
   p.cdp = ix->cdp;
   p.sim = (int)c->cfg.similarity;
@@ -978,10 +993,13 @@ static int launch_scan_mma(bbq_index* ix, int mode, int nq, uint32_t k, const Mm
   ProfScope prof(c, st, mode == SCAN_DUMP ? PROF_SAMPLE : PROF_SCAN);
   if (mode != SCAN_DUMP) c->stats.scan_launches++;
   c->stats.mma_n_tile = (uint32_t)pl.n_tile;
+  if (mode != SCAN_DUMP) c->stats.mma_layout = (uint32_t)pl.layout;
   c->stats.mma_passes = (uint32_t)pl.passes;
   const unsigned grid = (unsigned)std::min<int64_t>(ntiles, c->sm_count);
-  if (mode == SCAN_DUMP) return launch_mma_sim<SCAN_DUMP>(c, p.sim, pl.cpq, grid, pl.smem, st, p);
-  return launch_mma_sim<SCAN_FILTER>(c, p.sim, pl.cpq, grid, pl.smem, st, p);
+  // (the dump — threshold sample, parity taps — always runs the wide-batch roles: it is a few hundred tiles)
+  if (mode == SCAN_DUMP) return launch_mma_sim<SCAN_DUMP, 0>(c, p.sim, pl.cpq, grid, pl.smem, st, p);
+  if (pl.layout == 1) return launch_mma_sim<SCAN_FILTER, 1>(c, p.sim, pl.cpq, grid, pl.smem, st, p);
+  return launch_mma_sim<SCAN_FILTER, 0>(c, p.sim, pl.cpq, grid, pl.smem, st, p);
 }
 
 static ScanParams base_scan_params(bbq_index* ix, int nq) {

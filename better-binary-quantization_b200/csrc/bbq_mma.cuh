@@ -39,13 +39,22 @@ namespace bbqk {
 #endif
 constexpr int MMA_LDW = BBQ_MMA_LDW;                // accumulator columns per epilogue TMEM load (16 or 32)
 static_assert(MMA_LDW == 16 || MMA_LDW == 32, "tcgen05.ld .x16 or .x32");
-constexpr int MMA_EPI_WARPS = BBQ_MMA_EPI_WARPS;    // epilogue warps: one or two per TMEM lane quarter, alternating 16-column chunks
-constexpr int MMA_EXP_GROUPS = BBQ_MMA_EXP_GROUPS;  // expansion groups of 4 warps (one warp per TMEM lane quarter), alternating hand-offs
-constexpr int MMA_EPI_WARP0 = 4 + 4 * MMA_EXP_GROUPS;
-// warp 0 B loader, 1-2 MMA issuers (2 also allocates TMEM), 3 drainer, 4.. expansion groups, then the epilogue
-constexpr int MMA_THREADS = (MMA_EPI_WARP0 + MMA_EPI_WARPS) * 32;
-static_assert(MMA_EPI_WARPS == 4 || MMA_EPI_WARPS == 8, "one or two epilogue warps per TMEM lane quarter");
-static_assert(MMA_EXP_GROUPS == 1 || MMA_EXP_GROUPS == 2, "one or two expansion groups");
+// Role layout of the 16 (or 20) warps of a CTA: warp 0 B loader, 1-2 MMA issuers (2 also allocates TMEM), 3 drainer,
+// 4.. expansion groups of 4 warps (one warp per TMEM lane quarter, alternating hand-offs), then the epilogue (one or two
+// warps per TMEM lane quarter, alternating accumulator chunks).  Two layouts are compiled into the library:
+//   0 "wide batch"  : 8 epilogue warps + 1 expansion group (the build options above) — the per-pair screen is the load;
+//   1 "narrow batch": 4 epilogue warps + 2 expansion groups, same 512 threads / 128 registers — with few resident
+//                     queries the epilogue has almost nothing to do and the serial operand feed of ONE group is the bound.
+// mma_plan picks by the number of accumulator columns (measured crossover, profiles/r02_k2_narrow_layout.txt).
+template <int L>
+struct MmaLayout {
+  static constexpr int EPI_WARPS = L == 0 ? BBQ_MMA_EPI_WARPS : 4;
+  static constexpr int EXP_GROUPS = L == 0 ? BBQ_MMA_EXP_GROUPS : 2;
+  static constexpr int EPI_WARP0 = 4 + 4 * EXP_GROUPS;
+  static constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;
+  static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "one or two epilogue warps per TMEM lane quarter");
+  static_assert(EXP_GROUPS == 1 || EXP_GROUPS == 2, "one or two expansion groups");
+};
 constexpr int MMA_N_MAX = 224;        // 2 accumulators + >= 2 A stages must fit the 512 TMEM columns
 constexpr int MMA_CHUNK_DIMS = 128;   // dims per A stage (32 TMEM columns)
 
@@ -538,6 +547,7 @@ struct MmaParams {
   const QEnv* qenv;        // [passes] first-level envelope of each resident query block
   const bbqn::QueryTerms* qterms;
   int nq, n_tile, passes, nstage;
+  int nissuers;            // MMA issuing threads (2; 3 = the B loader's warp takes a third share: narrow batches are issue-bound)
   double dim, cdp;
   int sim, one_bit_query;  // one_bit_query: bbqn::SCORE_* mode
   double lx_div;           // 2^indexBits - 1
@@ -677,14 +687,14 @@ __device__ void mma_retighten_warp(const HitCtx* cx, int q, int lane) {  // whol
 
 template <int SIM>
 __device__ void mma_drain_ring(const HitCtx* cx, uint64_t* ring, const uint32_t* tail_s, uint32_t* head_s,
-                               const uint32_t* done_s, int lane) {
+                               const uint32_t* done_s, uint32_t epi_warps, int lane) {
   uint32_t head = 0;
   for (;;) {
     const uint64_t e = *((volatile uint64_t*)(ring + ((head + (uint32_t)lane) % HIT_RING)));
     const uint32_t valid = __ballot_sync(0xffffffffu, e != 0ull);
     const uint32_t n = (valid == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~valid) - 1);  // contiguous published prefix
     if (n == 0u) {
-      if (*((volatile const uint32_t*)done_s) == (uint32_t)MMA_EPI_WARPS && head == *((volatile const uint32_t*)tail_s)) break;
+      if (*((volatile const uint32_t*)done_s) == epi_warps && head == *((volatile const uint32_t*)tail_s)) break;
       __nanosleep(200);
       continue;
     }
@@ -887,8 +897,10 @@ __device__ __forceinline__ void mma_expansion(const MmaParams& p, uint64_t* a_fu
 
 // CPQ = accumulator columns per query: 1, or 2 when the query code is split into nibbles (k_query_tiles); then the
 // epilogue works on val = 16 * D_hi + D_lo = 8 * dot and every per-query table is indexed by column / 2.
-template <int MODE, int SIM, int CPQ>
-__global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_constant__ MmaParams p) {
+template <int MODE, int SIM, int CPQ, int LAYOUT>
+__global__ void __launch_bounds__(MmaLayout<LAYOUT>::THREADS, 1) k_scan_mma(const __grid_constant__ MmaParams p) {
+  constexpr int MMA_EPI_WARPS = MmaLayout<LAYOUT>::EPI_WARPS, MMA_EXP_GROUPS = MmaLayout<LAYOUT>::EXP_GROUPS,
+                MMA_EPI_WARP0 = MmaLayout<LAYOUT>::EPI_WARP0, MMA_THREADS = MmaLayout<LAYOUT>::THREADS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // layout: [B image n_tile*kbytes][QScreen n_tile][QueryTerms n_tile][barriers][tmem ptr]
   uint8_t* b_smem = smem_raw;
@@ -921,7 +933,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
       mbar_init(a_full + i, 4);
       mbar_init(a_empty + i, 1);
     }
-    const uint32_t nissuers = nchunks > 1 ? 2u : 1u;  // every issuer commits its own MMAs
+    const uint32_t nissuers = (uint32_t)max(1, min(p.nissuers, min(nchunks, 3)));  // every issuer commits its own MMAs
     for (int i = 0; i < 2; i++) {
       mbar_init(acc_full + i, nissuers);
       mbar_init(acc_empty + i, MMA_EPI_WARPS * 32);
@@ -966,13 +978,70 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
   const uint32_t acc_col = 0;                              // accumulators: columns [0, 2*n_tile)
   const uint32_t a_col = 2u * (uint32_t)p.n_tile;          // A stages: 32 columns each
 
+  // ===== MMA issuers =====
+  // One thread needs ~99 cycles to issue a tcgen05.mma (tools/probe/mma_issue_probe.cu: independent of N and of
+  // TS/SS), so 4 issues + the per-chunk hand-off (barrier wait, fence, commit: ~260 cycles) exceed the ~420
+  // cycles the tensor pipe needs for the chunk, and the pipe idles.  NI issuers take the chunks round-robin (warp 1
+  // chunks 0, NI, ..; warp 2 chunks 1, NI + 1, ..; with NI = 3 the B loader, idle for the whole of a pass, takes the
+  // third share); integer accumulation commutes, and the one ordering that matters — the overwriting first MMA of a
+  // tile before anything else — is enforced by a commit-signalled barrier.
+  const int NI = max(1, min(p.nissuers, min(nchunks, 3)));
+  uint32_t gchunk = 0;  // running chunk count of this CTA: stage = gchunk % nstage, phase = (gchunk / nstage) & 1
+  uint32_t tcount_i = 0;
+  int mma_ev = 0;
+  auto issue_pass = [&](int pass, int me) {  // whole warp; me = 0 issues the tile's first (overwriting) MMA
+    const uint32_t idesc = make_idesc_i8(128, p.n_tile);
+    const uint32_t lbo = (uint32_t)p.n_tile * 16u;
+    const uint32_t b_addr = smem_u32(b_smem);
+    mbar_wait(b_full, (uint32_t)(pass & 1));
+    for (int64_t i = blockIdx.x; i < p.ntiles; i += gridDim.x) {
+      const uint32_t buf = tcount_i & 1u, bphase = (tcount_i >> 1) & 1u;
+      if (me == 0) mbar_wait(acc_empty + buf, bphase ^ 1u);  // epilogue has drained this accumulator
+      else mbar_wait(tile_go + buf, bphase);                 // ... and issuer 0's overwriting MMA has completed
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc_col + buf * (uint32_t)p.n_tile;
+      for (int kc = me; kc < nchunks; kc += NI) {
+        const uint32_t g = gchunk + (uint32_t)kc;
+        const uint32_t stage = g % (uint32_t)nstage, sphase = (g / (uint32_t)nstage) & 1u;
+        const bool tr = (p.debug & 32u) && blockIdx.x == 0 && lane == 0 && pass == 0 && me == 0;
+        long long t0 = tr ? clock64() : 0;
+        mbar_wait(a_full + stage, sphase);
+        tc_fence_after();
+        long long t1 = tr ? clock64() : 0;
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint32_t a_tmem = tmem_base + a_col + stage * 32u + (uint32_t)j * 8u;
+            const uint64_t bdesc = make_kmajor_desc(b_addr + (uint32_t)((kc * 4 + j) * 2) * lbo, lbo, 128u);
+            tc_mma_i8_ts(d_tmem, a_tmem, bdesc, idesc, (kc | j) != 0 ? 1u : 0u);
+            if (kc == 0 && j == 0 && NI > 1) tc_commit(tile_go + buf);
+          }
+          tc_commit(a_empty + stage);  // frees the A stage once these MMAs have read it
+          if (tr && mma_ev < 1000) {
+            p.trace[0 * 4096 + mma_ev * 4 + 0] = t0;
+            p.trace[0 * 4096 + mma_ev * 4 + 1] = t1;
+            p.trace[0 * 4096 + mma_ev * 4 + 2] = clock64();
+            mma_ev++;
+          }
+        }
+        __syncwarp();
+      }
+      gchunk += (uint32_t)nchunks;
+      if (lane == 0) tc_commit(acc_full + buf);
+      __syncwarp();
+      tcount_i++;
+    }
+    if (lane == 0) tc_commit(b_empty);  // this issuer's MMAs of the pass are done -> B may be replaced
+    __syncwarp();
+  };
+
   if (warp == 0) {
-    // ===== B loader: one resident query block per pass =====
-    if (lane == 0) {
-      const uint32_t bytes = (uint32_t)p.n_tile * (uint32_t)p.kbytes;
-      for (int pass = 0; pass < p.passes; pass++) {
+    // ===== B loader: one resident query block per pass (and, with three issuers, the third share of the MMAs) =====
+    const uint32_t bytes = (uint32_t)p.n_tile * (uint32_t)p.kbytes;
+    for (int pass = 0; pass < p.passes; pass++) {
+      if (lane == 0) {
         // previous pass's MMAs have drained (a whole pass away: poll lazily, do not steal issue slots)
-        while (!mbar_try(b_empty, (uint32_t)((pass & 1) ^ 1))) __nanosleep(1000);
+        while (!mbar_try(b_empty, (uint32_t)((pass & 1) ^ 1))) __nanosleep(NI == 3 ? 100 : 1000);
         mbar_expect_tx(b_full, bytes);
         const uint8_t* src = p.images + (size_t)pass * bytes;
         for (uint32_t off = 0; off < bytes; off += 32768u) {
@@ -980,73 +1049,24 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_scan_mma(const __grid_consta
           bulk_g2s(b_smem + off, src + off, sz, b_full);
         }
       }
-    }
-  } else if (warp == 1 || (warp == 2 && nchunks > 1)) {
-    // ===== MMA issuers =====
-    // One thread needs ~99 cycles to issue a tcgen05.mma (tools/probe/mma_issue_probe.cu: independent of N and of
-    // TS/SS), so 4 issues + the per-chunk hand-off (barrier wait, fence, commit: ~260 cycles) exceed the ~420
-    // cycles the tensor pipe needs for the chunk, and the pipe idles.  Two issuers take alternate chunks (warp 1 the
-    // even ones, warp 2 the odd ones); integer accumulation commutes, and the one ordering that matters — the
-    // overwriting first MMA of a tile before anything else — is enforced by a commit-signalled barrier.
-    const int me = warp - 1;  // 0: even chunks (and the tile's first MMA), 1: odd chunks
-    const uint32_t idesc = make_idesc_i8(128, p.n_tile);
-    const uint32_t lbo = (uint32_t)p.n_tile * 16u;
-    const uint32_t b_addr = smem_u32(b_smem);
-    uint32_t gchunk = 0;  // running chunk count of this CTA: stage = gchunk % nstage, phase = (gchunk / nstage) & 1
-    uint32_t tcount = 0;
-    int mma_ev = 0;
-    for (int pass = 0; pass < p.passes; pass++) {
-      mbar_wait(b_full, (uint32_t)(pass & 1));
-      for (int64_t i = blockIdx.x; i < p.ntiles; i += gridDim.x) {
-        const uint32_t buf = tcount & 1u, bphase = (tcount >> 1) & 1u;
-        if (me == 0) mbar_wait(acc_empty + buf, bphase ^ 1u);  // epilogue has drained this accumulator
-        else mbar_wait(tile_go + buf, bphase);                 // ... and issuer 0's overwriting MMA has completed
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc_col + buf * (uint32_t)p.n_tile;
-        for (int kc = me; kc < nchunks; kc += 2) {
-          const uint32_t g = gchunk + (uint32_t)kc;
-          const uint32_t stage = g % (uint32_t)nstage, sphase = (g / (uint32_t)nstage) & 1u;
-          const bool tr = (p.debug & 32u) && blockIdx.x == 0 && lane == 0 && pass == 0 && me == 0;
-          long long t0 = tr ? clock64() : 0;
-          mbar_wait(a_full + stage, sphase);
-          tc_fence_after();
-          long long t1 = tr ? clock64() : 0;
-          if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const uint32_t a_tmem = tmem_base + a_col + stage * 32u + (uint32_t)j * 8u;
-              const uint64_t bdesc = make_kmajor_desc(b_addr + (uint32_t)((kc * 4 + j) * 2) * lbo, lbo, 128u);
-              tc_mma_i8_ts(d_tmem, a_tmem, bdesc, idesc, (kc | j) != 0 ? 1u : 0u);
-              if (kc == 0 && j == 0 && nchunks > 1) tc_commit(tile_go + buf);
-            }
-            tc_commit(a_empty + stage);  // frees the A stage once these MMAs have read it
-            if (tr && mma_ev < 1000) {
-              p.trace[0 * 4096 + mma_ev * 4 + 0] = t0;
-              p.trace[0 * 4096 + mma_ev * 4 + 1] = t1;
-              p.trace[0 * 4096 + mma_ev * 4 + 2] = clock64();
-              mma_ev++;
-            }
-          }
-          __syncwarp();
-        }
-        gchunk += (uint32_t)nchunks;
-        if (lane == 0) tc_commit(acc_full + buf);
-        __syncwarp();
-        tcount++;
-      }
-      if (lane == 0) tc_commit(b_empty);  // this issuer's MMAs of the pass are done -> B may be replaced
       __syncwarp();
+      if (NI == 3) issue_pass(pass, 2);
     }
+  } else if (warp == 1 || (warp == 2 && NI > 1)) {
+    for (int pass = 0; pass < p.passes; pass++) issue_pass(pass, warp - 1);
   } else if (warp == 3) {
     // ===== drainer: exact replay of the parked hits, candidate append, threshold tightening =====
-    if (MODE == SCAN_FILTER) mma_drain_ring<SIM>(hit_s, ring_s, ring_ctl_s + 0, ring_ctl_s + 1, ring_ctl_s + 2, lane);
+    if (MODE == SCAN_FILTER) mma_drain_ring<SIM>(hit_s, ring_s, ring_ctl_s + 0, ring_ctl_s + 1, ring_ctl_s + 2, (uint32_t)MMA_EPI_WARPS, lane);
   } else if (warp >= 4 && warp < MMA_EPI_WARP0) {
     // ===== expansion: packed 1-bit row -> weighted u8 A operand, straight into TMEM (mma_expansion above) =====
     // Chunks per hand-off: one group pairs them; with 8 A stages (<= 128 accumulator columns per buffer: small and
     // medium batches, wide rows) it hands over FOUR at a time — the tcgen05.wait::st round trip, not the ALU work,
-    // bounds the feed, and four stores in flight amortise it twice as well; two groups alternate single chunks.
-    if (MMA_EXP_GROUPS == 2)
-      mma_expansion<MMA_EXP_GROUPS, 1>(p, a_full, a_empty, tmem_base, a_col, nstage, nchunks, warp, lane);
+    // bounds the feed, and four stores in flight amortise it twice as well; two groups alternate pairs of chunks when 8
+    // stages exist, single chunks otherwise.
+    if (MMA_EXP_GROUPS == 2 && nstage >= 8 && !(p.debug & 1024u))
+      mma_expansion<2, 2>(p, a_full, a_empty, tmem_base, a_col, nstage, nchunks, warp, lane);
+    else if (MMA_EXP_GROUPS == 2)
+      mma_expansion<2, 1>(p, a_full, a_empty, tmem_base, a_col, nstage, nchunks, warp, lane);
     else if (nstage >= 8 && !(p.debug & 512u))
       mma_expansion<1, 4>(p, a_full, a_empty, tmem_base, a_col, nstage, nchunks, warp, lane);
     else

@@ -251,7 +251,7 @@ typedef struct {
   uint32_t last_path;         /* 0 direct (dump+select), 1 sampled threshold + filtered scan, 2 exact chunked fallback */
   uint32_t last_overflow;     /* 1 if the candidate buffer overflowed and the fallback ran */
   uint32_t last_engine;       /* scan engine of the last filtered search: 1 popcount kernel, 2 tcgen05 kernel */
-  uint32_t reserved0;
+  uint32_t mma_layout;        /* last tensor-core scan: role layout, 0 wide-batch (8 epilogue warps + 1 expansion group), 1 narrow-batch (4 + 2) */
   /* with bbq_set_profiling(ctx, 1): CUDA-event time of the dominant (scan) kernel launches, on their stream */
   uint64_t scan_launches;
   double scan_ms;

@@ -4,7 +4,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ["BBQ_MMA_DEBUG"] = os.environ.get("BBQ_MMA_DEBUG", "32")
 import torch, bbq_b200
-n, dim, nq = 400000, 1024, 1024
+n, dim, nq = 400000, 1024, int(os.environ.get("NQ", 1024))
 fmt = bbq_b200.createBinaryQuantizationFormat({"quantizer": {"similarityFunction": os.environ.get("SIM", "COSINE"), "lambda": 0.1, "iters": 5}})
 ix = fmt.reserveIndex(n, dim, np.zeros(dim, np.float32))
 g = torch.Generator(device="cuda"); g.manual_seed(1)
