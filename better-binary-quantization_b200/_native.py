@@ -42,7 +42,7 @@ class BbqStats(C.Structure):
                 ("last_overflow", C.c_uint32), ("last_engine", C.c_uint32), ("mma_layout", C.c_uint32),
                 ("scan_launches", C.c_uint64), ("scan_ms", C.c_double),
                 ("quantize_ms", C.c_double), ("select_ms", C.c_double), ("sample_ms", C.c_double),
-                ("mma_n_tile", C.c_uint32), ("mma_passes", C.c_uint32)]
+                ("mma_n_tile", C.c_uint32), ("mma_passes", C.c_uint32), ("graph_replays", C.c_uint64)]
 
 
 # every symbol include/bbq_b200.h declares: name -> (restype, argtypes)

@@ -46,11 +46,13 @@ static int fail(int status, const std::string& msg, int64_t vec = -1, int64_t po
     if (_s != BBQ_OK) return _s;  \
   } while (0)
 
+static uint64_t g_scratch_gen = 0;  // bumped whenever any scratch buffer moves: a captured launch sequence holds its address
 struct DevBuf {  // grow-only device scratch
   void* p = nullptr;
   size_t cap = 0;
   int reserve(size_t bytes) {
     if (bytes <= cap) return BBQ_OK;
+    g_scratch_gen++;
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -92,7 +94,35 @@ struct bbq_ctx {
   int mma_narrow_max = 96;  // BBQ_MMA_NARROW_MAX: widest resident block (accumulator columns) that takes the narrow-batch roles
   uint32_t mma_debug = 0;   // BBQ_MMA_DEBUG: timing-attribution knobs of the tensor-core scan (results become wrong)
   bool dynamic_tau = true;  // BBQ_DYNTAU=0 keeps the sampled threshold fixed during the tensor-core scan (tests)
-  int query_quantizer = 0;  // BBQ_QQUANT=thread forces the one-thread-per-query form (tests)
+  int query_quantizer = 0;  // BBQ_QQUANT: thread / warp / cta force one form of K4 (tests, A/B); default by batch size
+  // query screening armed by an entry point for the batch that starts at validate_base: the next K4 launches do it
+  const float* validate_base = nullptr;
+  // bbq_search keeps ONE host synchronisation per call: the filtered search leaves its overflow flag in h_flag and the
+  // entry point looks at it after the synchronisation it needs anyway for the results (pending_overflow_nq >= 0)
+  bool defer_overflow = false;
+  int pending_overflow_nq = -1;
+  // A narrow batch is launch-latency bound (a single query: ~10 stream operations around 60-90 us of kernels), and
+  // its whole device sequence — screening, K4, planes / B images, threshold sample, scan, selection, status read-back —
+  // depends only on (index, batch size, k): bbq_search captures it into a CUDA graph the second time the same key
+  // arrives and replays it from then on (BBQ_GRAPH=0 turns that off).
+  struct SearchGraphKey {
+    uint64_t ix = 0, n = 0, base = 0; const void* codes = nullptr; const void* rscreen = nullptr;
+    uint32_t nq = 0, k = 0; uint64_t scratch_gen = 0;
+    bool operator==(const SearchGraphKey& o) const {
+      return ix == o.ix && n == o.n && base == o.base && codes == o.codes && rscreen == o.rscreen && nq == o.nq && k == o.k &&
+             scratch_gen == o.scratch_gen;
+    }
+  };
+  struct SearchGraph {
+    cudaGraphExec_t exec = nullptr;
+    SearchGraphKey key, seen;   // key: what exec was captured for; seen: the key of the previous eligible call
+    uint64_t launches = 0;      // this library's kernel launches inside the captured sequence
+    int pending_nq = -1;
+    uint32_t last_path = 0, last_engine = 0;
+    uint64_t replays = 0;
+  } sgraph;
+  int graph_max_nq = 16;    // BBQ_GRAPH: 0 off, else the widest batch whose sequence is captured
+  int qquant_cta_max = -1;  // BBQ_QQUANT_CTA_MAX: largest batch quantised one CTA per query (-1: 2 x SM count)
   int scan_engine = 0;  // BBQ_SCAN: 0 auto, 1 popcount kernel only, 2 tensor-core kernel whenever it can run
   uint32_t* h_flag = nullptr;  // pinned: [0..nq) candidate counts, [nq] overflow flag, then 2 words: first invalid query
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;  // ordering between the context's stream and a caller's stream (StreamBridge)
@@ -155,8 +185,10 @@ struct StreamBridge {
   }
 };
 
+static uint64_t g_index_serial = 0;
 struct bbq_index {
   bbq_ctx* ctx = nullptr;
+  uint64_t serial = ++g_index_serial;  // never reused (an address can be): part of the key of a captured launch sequence
   uint64_t n = 0;
   uint32_t dim = 0;
   int ib = 1;             // index bits (planes per 128-dim chunk of a row)
@@ -237,7 +269,9 @@ extern "C" int bbq_create(const bbq_config* config, bbq_ctx** out_ctx) {
   if (const char* e = getenv("BBQ_MMA_ISSUERS")) c->mma_issuers = std::max(0, std::min(3, atoi(e)));
   if (const char* e = getenv("BBQ_MMA_DEBUG")) c->mma_debug = (uint32_t)atoi(e);
   if (const char* e = getenv("BBQ_DYNTAU")) c->dynamic_tau = atoi(e) != 0;
-  if (const char* e = getenv("BBQ_QQUANT")) c->query_quantizer = !strcmp(e, "thread") ? 1 : 0;
+  if (const char* e = getenv("BBQ_QQUANT")) c->query_quantizer = !strcmp(e, "thread") ? 1 : !strcmp(e, "warp") ? 2 : !strcmp(e, "cta") ? 3 : 0;
+  if (const char* e = getenv("BBQ_QQUANT_CTA_MAX")) c->qquant_cta_max = atoi(e);
+  if (const char* e = getenv("BBQ_GRAPH")) c->graph_max_nq = std::max(0, atoi(e));
   if (const char* e = getenv("BBQ_SCAN")) c->scan_engine = !strcmp(e, "popc") ? 1 : !strcmp(e, "mma") ? 2 : 0;
   *out_ctx = c;
   return BBQ_OK;
@@ -256,6 +290,7 @@ static void ctx_release(bbq_ctx* c) {
     b->release();
   comm_release(c);
   if (c->h_flag) cudaFreeHost(c->h_flag);
+  if (c->sgraph.exec) cudaGraphExecDestroy(c->sgraph.exec);
   if (c->ev_in) cudaEventDestroy(c->ev_in);
   if (c->ev_out) cudaEventDestroy(c->ev_out);
   for (auto& p : c->ev_pending) {
@@ -816,15 +851,37 @@ static int quantize_rows(bbq_ctx* c, const float* d_queries, int nq, int dim, in
   ProfScope prof(c, st, PROF_QUANT);
   const size_t per_warp = (size_t)((dim + 3) & ~3) * sizeof(float) + 14 * 33 * sizeof(double);
   const size_t smem = per_warp * OSQW_WARPS;
-  if (c->query_quantizer != 1 && smem <= 200 * 1024) {
-    // latency form: one warp per query
+  const size_t smem_cta = (size_t)OSQC_TERM_ROWS * 33 * sizeof(double) + (2 * (OSQC_PRODUCERS + 1) + 8) * sizeof(double) +
+                          (size_t)((dim + 3) & ~3) * sizeof(float);
+  // 0 = by batch size: one CTA per query for a narrow batch (K4 is the longest kernel of a single-query search and
+  // the CTA form runs each pass at the latency of the add chain), one warp per query otherwise
+  const int cta_max = c->qquant_cta_max >= 0 ? c->qquant_cta_max : 2 * c->sm_count;
+  const int form = c->query_quantizer != 0 ? c->query_quantizer : (nq <= cta_max ? 3 : 2);
+  // query screening (NaN / Infinity): armed by the entry point, done by K4 itself while it stages the query
+  unsigned long long* bad = nullptr;
+  int q_base = 0;
+  if (c->validate_base != nullptr) {
+    bad = c->bad.as<unsigned long long>();
+    q_base = (int)((d_queries - c->validate_base) / dim);
+  }
+  float* d_q = const_cast<float*>(d_queries);  // (an offending query is zeroed in place; the entry points own the buffer)
+  if (form == 3 && smem_cta <= 200 * 1024) {
+    if (smem_cta > 48 * 1024)
+      CU(cudaFuncSetAttribute(k_osq_query_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+    LAUNCH(c, k_osq_query_cta, nq, OSQC_THREADS, smem_cta, st, d_q, nq, dim, d_centroid, (int)c->cfg.similarity, nb,
+           c->cfg.lambda, (int)c->cfg.iters, ntimes, c->qcodes.as<uint8_t>(), code_ld, c->qcorr.as<double>(), bad, q_base);
+  } else if (form != 1 && smem <= 200 * 1024) {
+    // one warp per query
     if (smem > 48 * 1024)
       CU(cudaFuncSetAttribute(k_osq_query_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LAUNCH(c, k_osq_query_warp, (nq + OSQW_WARPS - 1) / OSQW_WARPS, OSQW_WARPS * 32, smem, st, d_queries, nq, dim,
+    LAUNCH(c, k_osq_query_warp, (nq + OSQW_WARPS - 1) / OSQW_WARPS, OSQW_WARPS * 32, smem, st, d_q, nq, dim,
            d_centroid, (int)c->cfg.similarity, nb, c->cfg.lambda, (int)c->cfg.iters, ntimes, c->qcodes.as<uint8_t>(),
-           code_ld, c->qcorr.as<double>());
+           code_ld, c->qcorr.as<double>(), bad, q_base);
   } else {
     // throughput form: one thread per query over the transposed scratch (same code as the index build)
+    if (bad != nullptr)
+      LAUNCH(c, k_validate_queries, (nq + 3) / 4, 128, 0, st, d_q, nq, dim, c->cfg.similarity == BBQ_SIM_COSINE ? 1 : 0, bad,
+             q_base);
     float* T = c->qT.as<float>();
     dim3 grid((nq + 31) / 32, (dim + 31) / 32), block(32, 8);
     LAUNCH(c, k_transpose, grid, block, 0, st, d_queries, (int64_t)nq, dim, T, (int64_t)nq);
@@ -1105,6 +1162,14 @@ static int search_exact_chunked(bbq_index* ix, int nq, uint32_t k, int32_t* d_ou
   return BBQ_OK;
 }
 
+// after the stream has been synchronised: did a candidate list of the last filtered search overflow?
+static bool resolve_filtered(bbq_ctx* c, int nq) {
+  uint64_t tot = 0;
+  for (int q = 0; q < nq; q++) tot += c->h_flag[q];
+  c->stats.last_candidates = tot;
+  return c->h_flag[nq] != 0;
+}
+
 // Sampled-threshold path: tau[q] = k-th best score over a strided sample of full tiles (a valid lower
 // bound of the final k-th best), then one filtered scan appends every row with score >= tau[q], then
 // the final selection.  *overflowed is set (after a sync) when a candidate list overflowed.
@@ -1204,11 +1269,13 @@ static int search_filtered(bbq_index* ix, int nq, uint32_t k, int32_t* d_out_idx
     TRY(launch_select<SEL_KEYS>(c, s, CAND_CAP, st));
   }
   CU(cudaMemcpyAsync(c->h_flag, cnt, (size_t)(nq + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (c->defer_overflow) {  // the caller synchronises once, then calls resolve_filtered
+    c->pending_overflow_nq = nq;
+    *overflowed = false;
+    return BBQ_OK;
+  }
   CU(cudaStreamSynchronize(st));
-  *overflowed = c->h_flag[nq] != 0;
-  uint64_t tot = 0;
-  for (int q = 0; q < nq; q++) tot += c->h_flag[q];
-  c->stats.last_candidates = tot;
+  *overflowed = resolve_filtered(c, nq);
   return BBQ_OK;
 }
 
@@ -1251,17 +1318,22 @@ extern "C" int bbq_search_device(bbq_index* ix, const float* d_queries, uint32_t
   return BBQ_OK;
 }
 
-// Query screening on the device (k_validate_queries): enqueue -> [search] -> finish (D2H of the verdict into the
-// pinned flag block) -> the caller's stream synchronisation -> report.
-static int enqueue_query_validation(bbq_index* ix, float* d_queries, uint32_t nq, cudaStream_t st) {
-  bbq_ctx* c = ix->ctx;
+// Query screening on the device: arm (the K4 launches that follow screen the batch while they stage it, see
+// osq_query_team) -> [search] -> finish (disarm; D2H of the verdict into the pinned flag block) -> the caller's stream
+// synchronisation -> report.
+static int enqueue_query_validation(bbq_ctx* c, const float* d_queries, cudaStream_t st) {
   TRY(c->bad.reserve(sizeof(unsigned long long)));
   CU(cudaMemsetAsync(c->bad.p, 0xFF, sizeof(unsigned long long), st));
-  LAUNCH(c, k_validate_queries, (nq + 3) / 4, 128, 0, st, d_queries, (int)nq, (int)ix->dim,
-         c->cfg.similarity == BBQ_SIM_COSINE ? 1 : 0, c->bad.as<unsigned long long>());
+  c->validate_base = d_queries;
   return BBQ_OK;
 }
+struct ValidationScope {  // an entry point that fails half-way must not leave the screening armed for the next call
+  bbq_ctx* c;
+  explicit ValidationScope(bbq_ctx* c_) : c(c_) {}
+  ~ValidationScope() { c->validate_base = nullptr; }
+};
 static int finish_query_validation(bbq_ctx* c, cudaStream_t st, bool sync) {
+  c->validate_base = nullptr;
   CU(cudaMemcpyAsync(c->h_flag + QUERY_BATCH + 2, c->bad.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   if (sync) CU(cudaStreamSynchronize(st));
   return BBQ_OK;
@@ -1294,20 +1366,96 @@ extern "C" int bbq_search(bbq_index* ix, const float* queries, uint32_t nq, int6
   CU(cudaMemcpyAsync(c->qrows.p, queries, (size_t)nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   // scalarQuantize validates the (normalised) query, optimizedScalarQuantizer.ts:138-148: done on the device, ahead
   // of the search in the same stream (an offending query is zeroed), and read back at the one synchronisation below
-  TRY(enqueue_query_validation(ix, c->qrows.as<float>(), nq, c->stream));
-  TRY(bbq_search_device(ix, c->qrows.as<float>(), nq, kk, c->out_idx.as<int32_t>(), c->out_score.as<float>(), c->stream));
-  TRY(finish_query_validation(c, c->stream, /*sync=*/false));
-  // results are written with stride kk; the caller's rows have stride k
-  if ((int64_t)kk == k) {
-    CU(cudaMemcpyAsync(out_idx, c->out_idx.p, (size_t)nq * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(out_score, c->out_score.p, (size_t)nq * kk * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  ValidationScope vscope(c);
+  // One host synchronisation per call (a single-batch call; larger ones keep the per-batch check): the overflow flag of
+  // the filtered search travels with the results and is looked at after the synchronisation below.
+  c->pending_overflow_nq = -1;
+  auto enqueue_device_sequence = [&]() -> int {  // everything between the H2D of the queries and the D2H of the results
+    TRY(enqueue_query_validation(c, c->qrows.as<float>(), c->stream));
+    c->defer_overflow = nq <= QUERY_BATCH;
+    const int st_search = bbq_search_device(ix, c->qrows.as<float>(), nq, kk, c->out_idx.as<int32_t>(), c->out_score.as<float>(), c->stream);
+    c->defer_overflow = false;
+    TRY(st_search);
+    return finish_query_validation(c, c->stream, /*sync=*/false);
+  };
+  const bool graph_ok = c->graph_max_nq > 0 && nq <= (uint32_t)c->graph_max_nq && !c->profiling && c->mma_debug == 0;
+  bbq_ctx::SearchGraphKey key;
+  key.ix = ix->serial; key.n = ix->n; key.base = ix->base; key.codes = ix->codes; key.rscreen = ix->rscreen;
+  key.nq = nq; key.k = kk; key.scratch_gen = g_scratch_gen;
+  bbq_ctx::SearchGraph& sg = c->sgraph;
+  if (graph_ok && sg.exec != nullptr && sg.key == key) {
+    CU(cudaGraphLaunch(sg.exec, c->stream));
+    c->launches += sg.launches;
+    c->pending_overflow_nq = sg.pending_nq;
+    c->stats.last_path = sg.last_path;
+    c->stats.last_engine = sg.last_engine;
+    c->stats.last_overflow = 0;
+    sg.replays++;
+    c->stats.graph_replays = sg.replays;
+  } else if (graph_ok && sg.seen == key) {
+    // second call in a row with this key: every scratch buffer has its final size (no allocation can happen inside the
+    // capture) — record the sequence, then run it
+    if (sg.exec) {
+      cudaGraphExecDestroy(sg.exec);
+      sg.exec = nullptr;
+    }
+    const uint64_t l0 = c->launches;
+    CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+    const int st_seq = enqueue_device_sequence();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ec = cudaStreamEndCapture(c->stream, &graph);
+    if (st_seq != BBQ_OK || ec != cudaSuccess || graph == nullptr || g_scratch_gen != key.scratch_gen) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      c->validate_base = nullptr;
+      sg.seen = bbq_ctx::SearchGraphKey{};  // do not try again until the key has been seen twice more
+      if (st_seq != BBQ_OK) return st_seq;
+      c->pending_overflow_nq = -1;
+      TRY(enqueue_device_sequence());       // nothing ran during the failed capture: run the sequence directly
+    } else {
+      const cudaError_t ei = cudaGraphInstantiate(&sg.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ei != cudaSuccess) {
+        sg.exec = nullptr;
+        cudaGetLastError();
+        return fail(BBQ_ERR_CUDA, "cudaGraphInstantiate failed");
+      }
+      sg.key = key;
+      sg.launches = c->launches - l0;
+      sg.pending_nq = c->pending_overflow_nq;
+      sg.last_path = c->stats.last_path;
+      sg.last_engine = c->stats.last_engine;
+      CU(cudaGraphLaunch(sg.exec, c->stream));
+    }
   } else {
-    CU(cudaMemcpy2DAsync(out_idx, (size_t)k * sizeof(int32_t), c->out_idx.p, (size_t)kk * sizeof(int32_t),
-                         (size_t)kk * sizeof(int32_t), nq, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpy2DAsync(out_score, (size_t)k * sizeof(float), c->out_score.p, (size_t)kk * sizeof(float),
-                         (size_t)kk * sizeof(float), nq, cudaMemcpyDeviceToHost, c->stream));
+    if (graph_ok) sg.seen = key;  // (if scratch grows during this call the next call's key differs and re-arms)
+    TRY(enqueue_device_sequence());
   }
-  CU(cudaStreamSynchronize(c->stream));
+  // results are written with stride kk; the caller's rows have stride k
+  auto copy_results = [&]() -> int {
+    if ((int64_t)kk == k) {
+      CU(cudaMemcpyAsync(out_idx, c->out_idx.p, (size_t)nq * kk * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaMemcpyAsync(out_score, c->out_score.p, (size_t)nq * kk * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    } else {
+      CU(cudaMemcpy2DAsync(out_idx, (size_t)k * sizeof(int32_t), c->out_idx.p, (size_t)kk * sizeof(int32_t),
+                           (size_t)kk * sizeof(int32_t), nq, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaMemcpy2DAsync(out_score, (size_t)k * sizeof(float), c->out_score.p, (size_t)kk * sizeof(float),
+                           (size_t)kk * sizeof(float), nq, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return BBQ_OK;
+  };
+  TRY(copy_results());
+  if (c->pending_overflow_nq >= 0) {
+    const bool over = resolve_filtered(c, c->pending_overflow_nq);
+    c->pending_overflow_nq = -1;
+    if (over) {  // a candidate list overflowed (adversarial input): the exact chunked path redoes the batch
+      c->stats.last_overflow = 1;
+      c->stats.last_path = 2;
+      TRY(search_exact_chunked(ix, (int)nq, kk, c->out_idx.as<int32_t>(), c->out_score.as<float>(), c->stream));
+      TRY(copy_results());
+    }
+  }
   TRY(report_query_validation(c));
   if (out_count) *out_count = kk;
   return BBQ_OK;
@@ -1352,7 +1500,8 @@ extern "C" int bbq_search_rerank(bbq_index* ix, const float* queries, uint32_t n
   TRY(c->rr_q.reserve((size_t)nq * kk * sizeof(float)));
   TRY(c->rr_t.reserve((size_t)nq * kk * sizeof(double)));
   CU(cudaMemcpyAsync(c->qrows.p, queries, (size_t)nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, st));
-  TRY(enqueue_query_validation(ix, c->qrows.as<float>(), nq, st));
+  ValidationScope vscope(c);
+  TRY(enqueue_query_validation(c, c->qrows.as<float>(), st));
   TRY(bbq_search_device(ix, c->qrows.as<float>(), nq, m, c->out_idx.as<int32_t>(), c->out_score.as<float>(), st));
   TRY(finish_query_validation(c, st, /*sync=*/false));
   {
@@ -1621,6 +1770,7 @@ extern "C" int bbq_search_sharded(bbq_index* ix, const float* queries, uint32_t 
   if (k == 0 || nq == 0) return BBQ_OK;
   if (!out_idx || !out_score) return fail(BBQ_ERR_NULL, "output buffers must not be null");
   bbq_ctx* c = ix->ctx;
+  if (!c->comm || c->world == 1) return bbq_search(ix, queries, nq, k, out_idx, out_score, out_count);  // one shard: the plain entry
   CU(cudaSetDevice(c->device));
   uint64_t n_all = 0;
   TRY(global_rows(ix, c->stream, &n_all));
@@ -1630,7 +1780,8 @@ extern "C" int bbq_search_sharded(bbq_index* ix, const float* queries, uint32_t 
   TRY(c->out_idx.reserve((size_t)nq * kk * sizeof(int32_t)));
   TRY(c->out_score.reserve((size_t)nq * kk * sizeof(float)));
   CU(cudaMemcpyAsync(c->qrows.p, queries, (size_t)nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  TRY(enqueue_query_validation(ix, c->qrows.as<float>(), nq, c->stream));
+  ValidationScope vscope(c);
+  TRY(enqueue_query_validation(c, c->qrows.as<float>(), c->stream));
   TRY(bbq_search_sharded_device(ix, c->qrows.as<float>(), nq, kk, c->out_idx.as<int32_t>(), c->out_score.as<float>(),
                                 c->stream));
   TRY(finish_query_validation(c, c->stream, /*sync=*/false));
@@ -1680,9 +1831,8 @@ extern "C" int bbq_quantize_query(bbq_ctx* c, const float* query, const float* c
   CU(cudaMemcpyAsync(c->qrows.p, query, (size_t)dim * sizeof(float), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(c->cenv.p, centroid, (size_t)dim * sizeof(float), cudaMemcpyHostToDevice, st));
   const bool cosine = c->cfg.similarity == BBQ_SIM_COSINE;
-  CU(cudaMemsetAsync(c->bad.p, 0xFF, sizeof(unsigned long long), st));
-  LAUNCH(c, k_validate_queries, 1, 128, 0, st, c->qrows.as<float>(), 1, (int)dim, cosine ? 1 : 0,
-         c->bad.as<unsigned long long>());
+  ValidationScope vscope(c);
+  TRY(enqueue_query_validation(c, c->qrows.as<float>(), st));
   TRY(quantize_rows(c, c->qrows.as<float>(), 1, (int)dim, row_bytes, c->cenv.as<float>(), cosine ? 1 : 0, st));
   if (codes) CU(cudaMemcpyAsync(codes, c->qcodes.p, dim, cudaMemcpyDeviceToHost, st));
   if (corr4) CU(cudaMemcpyAsync(corr4, c->qcorr.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1712,7 +1862,8 @@ extern "C" int bbq_quantization_accuracy(bbq_ctx* c, const float* rows, const fl
     TRY(c->cacc.reserve(5 * sizeof(double)));
     CU(cudaMemcpyAsync(c->qrows.p, queries, (size_t)n * dim * sizeof(float), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(c->rr_q.p, rows + target_ord * dim, (size_t)dim * sizeof(float), cudaMemcpyHostToDevice, st));
-    TRY(enqueue_query_validation(ix, c->qrows.as<float>(), (uint32_t)n, st));
+    ValidationScope vscope(c);
+    TRY(enqueue_query_validation(c, c->qrows.as<float>(), st));
     // 2. quantizeQueryVector(query, centroid): ONE normalisation for COSINE (:271-299)
     TRY(quantize_rows(c, c->qrows.as<float>(), (int)n, (int)dim, ix->row_bytes, ix->centroid, cosine ? 1 : 0, st));
     LAUNCH(c, k_accuracy_scores, (unsigned)((n + RERANK_WARPS - 1) / RERANK_WARPS), RERANK_WARPS * 32, 0, st,

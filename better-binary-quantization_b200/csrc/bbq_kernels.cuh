@@ -187,93 +187,266 @@ __global__ void k_osq_query(const float* __restrict__ T, int64_t ld, int nq, int
   qcorr[4 * t + 3] = qsum;
 }
 
-// K4, latency form: ONE WARP per query.  The reference's sums are strictly sequential f64 (any re-association can
-// flip a Math.round), so the per-component terms are computed by the 32 lanes in parallel and each chain is then
-// accumulated in component order by one lane reading the staged terms from shared memory — up to 7 chains run
-// side by side in lanes 0..6.  The coordinate descent is fused: the loss of a candidate interval and the grid
-// sums of that same interval (needed only if it is accepted) share one pass.  Same arithmetic, same order, same
-// bits as bbqn::osq_interval / osq_codes (tests compare both with the oracle).
+// K4, latency forms: ONE WARP per query, or ONE CTA per query.  The reference's sums are strictly sequential f64 (any
+// re-association can flip a Math.round), so the per-component terms are computed in parallel and each chain is then
+// accumulated in component order by ONE lane reading the staged terms from shared memory — up to 7 chains run side by
+// side in lanes 0..6.  The coordinate descent is fused: the loss of a candidate interval and the grid sums of that same
+// interval (needed only if it is accepted) share one pass.  Same arithmetic, same order, same bits as
+// bbqn::osq_interval / osq_codes (tests compare all forms with the oracle).
+//
+// The two forms differ in who generates the terms (a "team" policy; the quantiser body below is shared):
+//   * WarpTeam — the warp that owns the chain also generates: the generator's f64 math (~150 instructions per 32
+//     components in the fused pass, a division among them) fills the latency slots of the 32 dependent adds, but both
+//     share one warp's issue slots: ~400 cycles per 32 components.  Best throughput for large batches (4 queries per CTA).
+//   * CtaTeam  — eight producer warps generate a 256-component super-block ahead while warp 0 does nothing but the
+//     dependent adds: the pass runs at the latency of the add chain itself.  For a single query / a narrow batch,
+//     where K4 is the longest kernel of the whole search.
+struct WarpTeam {
+  int lane;
+  double (*terms)[33];  // [2 * 7][33]
+  __device__ __forceinline__ int tid() const { return lane; }
+  __device__ __forceinline__ int size() const { return 32; }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+  template <int K, class Gen>
+  __device__ __forceinline__ void seq_sums(int d, Gen gen, double (&result)[K]) const {
+    // `terms` holds TWO buffers of K rows ([2*K][33]).  While the 32 dependent adds of block b run (every lane executes
+    // them, lanes >= K on row 0 and unused), the terms of block b+1 are generated into the other buffer: the two are
+    // independent, so the f64 math of the generator fills the latency slots of the serial chain.  Elements past d are
+    // +0.0 terms: acc + 0.0 == acc bit for bit (acc is never -0.0: it starts at +0.0), so every block adds 32 terms and
+    // the loop body has no branches.
+    double acc = 0.0;
+    const int nblk = (d + 31) >> 5;
+    const int chain_row = lane < K ? lane : 0;
+    auto generate = [&](int blk, int buf) {
+      const int i = (blk << 5) + lane;
+      double t[K];
+#pragma unroll
+      for (int k = 0; k < K; k++) t[k] = 0.0;
+      if (i < d) gen(i, t);
+#pragma unroll
+      for (int k = 0; k < K; k++) terms[buf * K + k][lane] = t[k];
+    };
+    generate(0, 0);
+    __syncwarp();
+    for (int blk = 0; blk < nblk; blk++) {
+      generate(blk + 1, (blk + 1) & 1);  // past the end: all zeros, never read
+      const double* row = terms[(blk & 1) * K + chain_row];
+#pragma unroll
+      for (int m = 0; m < 32; m++) acc += row[m];
+      __syncwarp();
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) result[k] = __shfl_sync(0xffffffffu, acc, k);
+  }
+  __device__ __forceinline__ void minmax(double& mn, double& mx) const {
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = bbqn::js_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = bbqn::js_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+  }
+  __device__ __forceinline__ double sum_integers(double v) const {  // integer-valued (or NaN) terms: any order is exact
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+  __device__ __forceinline__ void min2(uint32_t& a, uint32_t& b) const {
+    for (int o = 16; o > 0; o >>= 1) {
+      a = min(a, __shfl_xor_sync(0xffffffffu, a, o));
+      b = min(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+  }
+};
+
 template <int K, class Gen>
 __device__ __forceinline__ void warp_seq_sums(int d, int lane, double (*terms)[33], Gen gen, double (&result)[K]) {
-  // `terms` holds TWO buffers of K rows ([2*K][33]).  While the 32 dependent adds of block b run (every lane executes
-  // them, lanes >= K on row 0 and unused), the terms of block b+1 are generated into the other buffer: the two are
-  // independent, so the f64 math of the generator fills the latency slots of the serial chain.  Elements past d are
-  // +0.0 terms: acc + 0.0 == acc bit for bit (acc is never -0.0: it starts at +0.0), so every block adds 32 terms and
-  // the loop body has no branches.
-  double acc = 0.0;
-  const int nblk = (d + 31) >> 5;
-  const int chain_row = lane < K ? lane : 0;
-  auto generate = [&](int blk, int buf) {
-    const int i = (blk << 5) + lane;
-    double t[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) t[k] = 0.0;
-    if (i < d) gen(i, t);
-#pragma unroll
-    for (int k = 0; k < K; k++) terms[buf * K + k][lane] = t[k];
-  };
-  generate(0, 0);
-  __syncwarp();
-  for (int blk = 0; blk < nblk; blk++) {
-    generate(blk + 1, (blk + 1) & 1);  // past the end: all zeros, never read
-    const double* row = terms[(blk & 1) * K + chain_row];
-#pragma unroll
-    for (int m = 0; m < 32; m++) acc += row[m];
-    __syncwarp();
-  }
-#pragma unroll
-  for (int k = 0; k < K; k++) result[k] = __shfl_sync(0xffffffffu, acc, k);
+  WarpTeam{lane, terms}.template seq_sums<K>(d, gen, result);
 }
 
-constexpr int OSQW_WARPS = 4;  // queries per CTA
+constexpr int OSQC_PRODUCERS = 8;                       // producer warps of the CTA form (warp 0 owns the chains)
+constexpr int OSQC_THREADS = (OSQC_PRODUCERS + 1) * 32;
+constexpr int OSQC_TERM_ROWS = 2 * OSQC_PRODUCERS * 7;  // two super-block buffers x producers x up to 7 chains
+struct CtaTeam {
+  int t, warp, lane;
+  double (*terms)[33];  // [OSQC_TERM_ROWS][33]
+  double* red;          // [2 * (OSQC_PRODUCERS + 1) + 8] cross-warp reductions and chain results
+  __device__ __forceinline__ int tid() const { return t; }
+  __device__ __forceinline__ int size() const { return OSQC_THREADS; }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+  template <int K, class Gen>
+  __device__ __forceinline__ void seq_sums(int d, Gen gen, double (&result)[K]) const {
+    // Blocks of 32 components, super-blocks of OSQC_PRODUCERS blocks.  Producer warp w generates block sb * P + (w - 1)
+    // of super-block sb + 1 while warp 0 adds the blocks of super-block sb in order: the same sequence of additions as
+    // the warp form (and as the reference's loop), zero terms past d included.
+    constexpr int P = OSQC_PRODUCERS;
+    const int nblk = (d + 31) >> 5;
+    const int nsb = (nblk + P - 1) / P;
+    auto produce = [&](int sb) {
+      const int blk = sb * P + (warp - 1);
+      if (blk < nblk) {  // blocks past the end are never read
+        const int i = (blk << 5) + lane;
+        double tt[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) tt[k] = 0.0;
+        if (i < d) gen(i, tt);
+#pragma unroll
+        for (int k = 0; k < K; k++) terms[((sb & 1) * P + (warp - 1)) * K + k][lane] = tt[k];
+      }
+    };
+    if (warp > 0) produce(0);
+    __syncthreads();
+    double acc = 0.0;
+    const int chain_row = lane < K ? lane : 0;
+    for (int sb = 0; sb < nsb; sb++) {
+      if (warp > 0) {
+        if (sb + 1 < nsb) produce(sb + 1);
+      } else {
+        const int nb = min(P, nblk - sb * P);
+        for (int b = 0; b < nb; b++) {
+          const double* row = terms[((sb & 1) * P + b) * K + chain_row];
+#pragma unroll
+          for (int m = 0; m < 32; m++) acc += row[m];
+        }
+      }
+      __syncthreads();
+    }
+    double* res = red + 2 * (P + 1);
+    if (warp == 0 && lane < K) res[lane] = acc;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; k++) result[k] = res[k];
+    __syncthreads();  // (res is rewritten by the next call's last step only, but keep the hazard analysis trivial)
+  }
+  __device__ __forceinline__ void minmax(double& mn, double& mx) const {
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = bbqn::js_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = bbqn::js_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    constexpr int W = OSQC_PRODUCERS + 1;
+    if (lane == 0) {
+      red[warp] = mn;
+      red[W + warp] = mx;
+    }
+    __syncthreads();
+    mn = red[0];
+    mx = red[W];
+    for (int w = 1; w < W; w++) {  // same order in every thread
+      mn = bbqn::js_min(mn, red[w]);
+      mx = bbqn::js_max(mx, red[W + w]);
+    }
+    __syncthreads();
+  }
+  __device__ __forceinline__ double sum_integers(double v) const {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    constexpr int W = OSQC_PRODUCERS + 1;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double s = red[0];
+    for (int w = 1; w < W; w++) s += red[w];
+    __syncthreads();
+    return s;
+  }
+  __device__ __forceinline__ void min2(uint32_t& a, uint32_t& b) const {
+    for (int o = 16; o > 0; o >>= 1) {
+      a = min(a, __shfl_xor_sync(0xffffffffu, a, o));
+      b = min(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    constexpr int W = OSQC_PRODUCERS + 1;
+    uint32_t* r32 = reinterpret_cast<uint32_t*>(red);
+    if (lane == 0) {
+      r32[warp] = a;
+      r32[W + warp] = b;
+    }
+    __syncthreads();
+    for (int w = 0; w < W; w++) {
+      a = min(a, r32[w]);
+      b = min(b, r32[W + w]);
+    }
+    __syncthreads();
+  }
+};
 
-__global__ void __launch_bounds__(OSQW_WARPS * 32) k_osq_query_warp(
-    const float* __restrict__ queries, int nq, int dim, const float* __restrict__ centroid, int sim, int bits,
-    double lambda, int iters, int normalize_times, uint8_t* __restrict__ qcodes, int code_ld,
-    double* __restrict__ qcorr) {
-  extern __shared__ __align__(16) uint8_t osqw_smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = blockIdx.x * OSQW_WARPS + warp;
-  const size_t per_warp = (size_t)((dim + 3) & ~3) * sizeof(float) + 14 * 33 * sizeof(double);
-  double(*terms)[33] = reinterpret_cast<double(*)[33]>(osqw_smem + warp * per_warp);
-  float* vec = reinterpret_cast<float*>(osqw_smem + warp * per_warp + 14 * 33 * sizeof(double));
-  if (q >= nq) return;  // whole warp
-  const float* src = queries + (int64_t)q * dim;
-  for (int i = lane; i < dim; i += 32) vec[i] = src[i];
-  __syncwarp();
+// scalarQuantize of one query by one team (src/optimizedScalarQuantizer.ts:108-227, :280-407); `vec` = the team's
+// staging copy of the query in shared memory.
+//
+// Input screening is fused in (bad != nullptr): the reference validates inside scalarQuantize
+// (src/optimizedScalarQuantizer.ts:138-148, after the COSINE normalisation of src/binaryQuantizationFormat.ts:337).
+// The team finds the query's first NaN / first Infinity while it stages the vector.  COSINE: a NaN anywhere makes the
+// normalised vector all-NaN (reported at position 0); an Infinity makes the norm infinite, so the Infinity components
+// become NaN (reported as NaN at the first of them).  Otherwise the first non-finite component is reported as NaN or
+// Infinity.  The lowest offending query wins: bad[0] = min over queries of (query << 34 | status << 32 | position),
+// status 1 = NaN, 2 = Infinity (BBQ_ERR_NAN / BBQ_ERR_INF minus 4).  An offending query is ZEROED (staging copy and the
+// device buffer it came from) so that the search already enqueued behind this kernel runs on harmless input; the host
+// reads bad[0] at its one synchronisation point and reports the error instead of the results.
+__device__ __forceinline__ unsigned long long query_verdict(long long q_global, int cosine, uint32_t first_nan,
+                                                            uint32_t first_inf) {
+  uint32_t status, pos;
+  if (cosine) {
+    status = 1u;
+    pos = first_nan != 0xFFFFFFFFu ? 0u : first_inf;
+  } else if (first_nan < first_inf) {
+    status = 1u;
+    pos = first_nan;
+  } else {
+    status = 2u;
+    pos = first_inf;
+  }
+  return ((unsigned long long)q_global << 34) | ((unsigned long long)status << 32) | pos;
+}
+
+template <class Team>
+__device__ __forceinline__ void osq_query_team(const Team& T, float* __restrict__ src, float* vec, int dim,
+                                               const float* __restrict__ centroid, int sim, int bits, double lambda,
+                                               int iters, int normalize_times, uint8_t* __restrict__ out, int code_ld,
+                                               double* __restrict__ qcorr4, unsigned long long* __restrict__ bad,
+                                               long long q_global) {
+  uint32_t first_nan = 0xFFFFFFFFu, first_inf = 0xFFFFFFFFu;
+  for (int i = T.tid(); i < dim; i += T.size()) {
+    const float x = src[i];
+    vec[i] = x;
+    if (x != x) first_nan = min(first_nan, (uint32_t)i);
+    else if (fabsf(x) == INFINITY) first_inf = min(first_inf, (uint32_t)i);
+  }
+  if (bad != nullptr) {
+    T.min2(first_nan, first_inf);
+    if (first_nan != 0xFFFFFFFFu || first_inf != 0xFFFFFFFFu) {  // (uniform across the team)
+      if (T.tid() == 0) atomicMin(bad, query_verdict(q_global, sim == bbqn::SIM_COSINE ? 1 : 0, first_nan, first_inf));
+      for (int i = T.tid(); i < dim; i += T.size()) {
+        vec[i] = 0.0f;
+        src[i] = 0.0f;
+      }
+    }
+  }
+  T.sync();
   // normalizeVector (src/vectorOperations.ts:11-34), twice for COSINE queries (binaryQuantizationFormat.ts:337,279)
   for (int rep = 0; rep < normalize_times; rep++) {
     double r1[1];
-    warp_seq_sums<1>(dim, lane, terms, [&](int i, double* t) { t[0] = (double)vec[i] * (double)vec[i]; }, r1);
+    T.template seq_sums<1>(dim, [&](int i, double* t) { t[0] = (double)vec[i] * (double)vec[i]; }, r1);
     const double n = sqrt(r1[0]);
-    for (int i = lane; i < dim; i += 32) vec[i] = (n == 0) ? 0.0f : (float)((double)vec[i] / n);
-    __syncwarp();
+    T.sync();  // (every term has been read)
+    for (int i = T.tid(); i < dim; i += T.size()) vec[i] = (n == 0) ? 0.0f : (float)((double)vec[i] / n);
+    T.sync();
   }
   auto cen = [&](int i) { return (double)__ldg(centroid + i); };
   auto w_of = [&](int i) { return (double)(float)((double)vec[i] - cen(i)); };
   // statistics: centroidDot, mean, norm (three chains) + exact min/max
   double st[3];
-  warp_seq_sums<3>(dim, lane, terms, [&](int i, double* t) {
+  T.template seq_sums<3>(dim, [&](int i, double* t) {
     const double w = w_of(i);
     t[0] = (sim != bbqn::SIM_EUCLIDEAN) ? (double)vec[i] * cen(i) : 0.0;
     t[1] = w;
     t[2] = w * w;
   }, st);
   double mn = 1.7976931348623157e308, mx = -1.7976931348623157e308;
-  for (int i = lane; i < dim; i += 32) {
+  for (int i = T.tid(); i < dim; i += T.size()) {
     const double cv = (double)vec[i] - cen(i);
     mn = bbqn::js_min(mn, cv);
     mx = bbqn::js_max(mx, cv);
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    mn = bbqn::js_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    mx = bbqn::js_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  }
+  T.minmax(mn, mx);
   const double centroidDot = (sim != bbqn::SIM_EUCLIDEAN) ? st[0] : 0.0;
   const double mean = st[1] / (double)dim;
   const double nrm = sqrt(st[2]);
   double r1[1];
-  warp_seq_sums<1>(dim, lane, terms, [&](int i, double* t) {
+  T.template seq_sums<1>(dim, [&](int i, double* t) {
     const double diff = w_of(i) - mean;
     t[0] = diff * diff;
   }, r1);
@@ -284,11 +457,11 @@ __global__ void __launch_bounds__(OSQW_WARPS * 32) k_osq_query_warp(
   const int points = 1 << bits;
   const double pm1 = (double)(points - 1);
   // one pass: loss(ai, bi) [chains 0,1] and the grid sums of (ai, bi) [chains 2..6]
-  auto fused_pass = [&](double ai, double bi, double (&out)[7]) {
+  auto fused_pass = [&](double ai, double bi, double (&res)[7]) {
     const double step = (bi - ai) / pm1;      // computeLoss: step, 1/step
     const double stepInvL = 1.0 / step;
     const double stepInvG = pm1 / (bi - ai);  // optimizeIntervals: (points-1)/(b-a)
-    warp_seq_sums<7>(dim, lane, terms, [&](int i, double* t) {
+    T.template seq_sums<7>(dim, [&](int i, double* t) {
       const double xi = w_of(i);
       const double clamped = bbqn::js_clamp(xi, ai, bi);
       const double kl = bbqn::js_round((clamped - ai) * stepInvL);
@@ -304,14 +477,14 @@ __global__ void __launch_bounds__(OSQW_WARPS * 32) k_osq_query_warp(
       t[4] = s * s;
       t[5] = xi * oms;
       t[6] = xi * s;
-    }, out);
+    }, res);
   };
   double ps[7];
   fused_pass(a, b, ps);
   double loss0 = (1.0 - lambda) * ps[0] * ps[0] / nrm + lambda * ps[1];
   const double scale = (1.0 - lambda) / nrm;
   if (bbqn::js_isfinite(scale)) {
-    for (int iter = 0; iter < iters; iter++) {
+    for (int iter = 0; iter < iters; iter++) {  // (every branch below is uniform across the team)
       const double daa = ps[2], dab = ps[3], dbb = ps[4], dax = ps[5], dbx = ps[6];
       const double m0 = scale * dax * dax + lambda * daa;
       const double m1 = scale * dax * dbx + lambda * dab;
@@ -337,9 +510,8 @@ __global__ void __launch_bounds__(OSQW_WARPS * 32) k_osq_query_warp(
   const double step = nSteps > 0 ? (b - a) / (double)nSteps : 0.0;
   const double stepInv = step > 0 ? 1.0 / step : 0.0;
   const double threshold = (a + b) / 2;
-  uint8_t* out = qcodes + (int64_t)q * code_ld;
   double qsum = 0.0;
-  for (int i = lane; i < code_ld; i += 32) {
+  for (int i = T.tid(); i < code_ld; i += T.size()) {
     uint8_t code = 0;
     if (i < dim) {
       const double clamped = bbqn::js_clamp(w_of(i), a, b);
@@ -356,13 +528,45 @@ __global__ void __launch_bounds__(OSQW_WARPS * 32) k_osq_query_warp(
     }
     out[i] = code;
   }
-  for (int o = 16; o > 0; o >>= 1) qsum += __shfl_xor_sync(0xffffffffu, qsum, o);
-  if (lane == 0) {
-    qcorr[4 * q + 0] = a;
-    qcorr[4 * q + 1] = b;
-    qcorr[4 * q + 2] = (sim == bbqn::SIM_EUCLIDEAN) ? nrm : centroidDot;
-    qcorr[4 * q + 3] = qsum;
+  qsum = T.sum_integers(qsum);
+  if (T.tid() == 0) {
+    qcorr4[0] = a;
+    qcorr4[1] = b;
+    qcorr4[2] = (sim == bbqn::SIM_EUCLIDEAN) ? nrm : centroidDot;
+    qcorr4[3] = qsum;
   }
+}
+
+constexpr int OSQW_WARPS = 4;  // queries per CTA of the warp form
+
+__global__ void __launch_bounds__(OSQW_WARPS * 32) k_osq_query_warp(
+    float* __restrict__ queries, int nq, int dim, const float* __restrict__ centroid, int sim, int bits,
+    double lambda, int iters, int normalize_times, uint8_t* __restrict__ qcodes, int code_ld,
+    double* __restrict__ qcorr, unsigned long long* __restrict__ bad, int q_base) {
+  extern __shared__ __align__(16) uint8_t osqw_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * OSQW_WARPS + warp;
+  const size_t per_warp = (size_t)((dim + 3) & ~3) * sizeof(float) + 14 * 33 * sizeof(double);
+  WarpTeam T{lane, reinterpret_cast<double(*)[33]>(osqw_smem + warp * per_warp)};
+  float* vec = reinterpret_cast<float*>(osqw_smem + warp * per_warp + 14 * 33 * sizeof(double));
+  if (q >= nq) return;  // whole warp
+  osq_query_team(T, queries + (int64_t)q * dim, vec, dim, centroid, sim, bits, lambda, iters, normalize_times,
+                 qcodes + (int64_t)q * code_ld, code_ld, qcorr + 4 * (int64_t)q, bad, (long long)q_base + q);
+}
+
+__global__ void __launch_bounds__(OSQC_THREADS) k_osq_query_cta(
+    float* __restrict__ queries, int nq, int dim, const float* __restrict__ centroid, int sim, int bits,
+    double lambda, int iters, int normalize_times, uint8_t* __restrict__ qcodes, int code_ld,
+    double* __restrict__ qcorr, unsigned long long* __restrict__ bad, int q_base) {
+  extern __shared__ __align__(16) uint8_t osqc_smem[];
+  // layout: [terms OSQC_TERM_ROWS x 33 f64][red 2*(P+1)+8 f64][vec dim f32]
+  double(*terms)[33] = reinterpret_cast<double(*)[33]>(osqc_smem);
+  double* red = reinterpret_cast<double*>(osqc_smem) + OSQC_TERM_ROWS * 33;
+  float* vec = reinterpret_cast<float*>(red + 2 * (OSQC_PRODUCERS + 1) + 8);
+  const int q = blockIdx.x;  // one CTA per query (grid = nq)
+  CtaTeam T{(int)threadIdx.x, (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31), terms, red};
+  osq_query_team(T, queries + (int64_t)q * dim, vec, dim, centroid, sim, bits, lambda, iters, normalize_times,
+                 qcodes + (int64_t)q * code_ld, code_ld, qcorr + 4 * (int64_t)q, bad, (long long)q_base + q);
 }
 
 // Threshold from the sample: tau[q] = k-th largest of the per-thread maxima over the sampled scores.  The k
@@ -915,17 +1119,10 @@ __global__ void __launch_bounds__(256) k_rerank_select(const double* __restrict_
   }
 }
 
-// Input screening of a query batch on the device (the reference validates inside scalarQuantize,
-// src/optimizedScalarQuantizer.ts:138-148, after the COSINE normalisation of src/binaryQuantizationFormat.ts:337):
-// one warp per query finds its first NaN / first Infinity.  COSINE: a NaN anywhere makes the normalised vector
-// all-NaN (reported at position 0); an Infinity makes the norm infinite, so the Infinity components become NaN
-// (reported as NaN at the first of them).  Otherwise the first non-finite component is reported as NaN or
-// Infinity.  The lowest offending query wins: bad[0] = min over queries of (query << 34 | status << 32 | position),
-// status 1 = NaN, 2 = Infinity (BBQ_ERR_NAN / BBQ_ERR_INF minus 4).  An offending query is then ZEROED in place so
-// that the search that is already enqueued behind this kernel runs on harmless input; the host reads bad[0] at its
-// one synchronisation point and reports the error instead of the results.
+// Input screening as a kernel of its own (one warp per query), for the thread-per-query form of K4 only — the warp and
+// CTA forms do it while they stage the query (osq_query_team, where the rules are stated).
 __global__ void k_validate_queries(float* __restrict__ queries, int nq, int dim, int cosine,
-                                   unsigned long long* __restrict__ bad) {
+                                   unsigned long long* __restrict__ bad, int q_base) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= nq) return;
   float* v = queries + (int64_t)warp * dim;
@@ -940,18 +1137,7 @@ __global__ void k_validate_queries(float* __restrict__ queries, int nq, int dim,
     first_inf = min(first_inf, __shfl_xor_sync(0xffffffffu, first_inf, o));
   }
   if (first_nan == 0xFFFFFFFFu && first_inf == 0xFFFFFFFFu) return;
-  uint32_t status, pos;
-  if (cosine) {
-    status = 1u;
-    pos = first_nan != 0xFFFFFFFFu ? 0u : first_inf;
-  } else if (first_nan < first_inf) {
-    status = 1u;
-    pos = first_nan;
-  } else {
-    status = 2u;
-    pos = first_inf;
-  }
-  if (lane == 0) atomicMin(bad, ((unsigned long long)warp << 34) | ((unsigned long long)status << 32) | pos);
+  if (lane == 0) atomicMin(bad, query_verdict((long long)q_base + warp, cosine, first_nan, first_inf));
   for (int i = lane; i < dim; i += 32) v[i] = 0.0f;
 }
 

@@ -389,7 +389,7 @@ class BinaryQuantizationFormat:
                 "last_path": s.last_path, "last_overflow": s.last_overflow, "last_engine": s.last_engine,
                 "scan_launches": s.scan_launches,
                 "scan_ms": s.scan_ms, "quantize_ms": s.quantize_ms, "select_ms": s.select_ms, "sample_ms": s.sample_ms,
-                "mma_n_tile": s.mma_n_tile, "mma_passes": s.mma_passes, "mma_layout": s.mma_layout}
+                "mma_n_tile": s.mma_n_tile, "mma_passes": s.mma_passes, "mma_layout": s.mma_layout, "graph_replays": s.graph_replays}
 
     def setProfiling(self, enabled: bool):
         _check(_native.load().bbq_set_profiling(self._ctx, 1 if enabled else 0))

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BBQ_B200_ABI_VERSION 2
+#define BBQ_B200_ABI_VERSION 3
 
 typedef struct bbq_ctx bbq_ctx;     /* one GPU: stream, scratch, config          */
 typedef struct bbq_index bbq_index; /* device-resident index shard (a2 in SURVEY) */
@@ -260,6 +260,7 @@ typedef struct {
   double sample_ms;           /* threshold-sample scan launches (not counted in scan_ms / scan_launches) */
   uint32_t mma_n_tile;        /* last tensor-core scan: queries resident per pass */
   uint32_t mma_passes;        /* ... and passes over the shard */
+  uint64_t graph_replays;     /* bbq_search calls served by replaying the captured launch sequence (narrow batches) */
 } bbq_stats;
 int bbq_get_stats(bbq_ctx* ctx, bbq_stats* out);
 /* Off by default.  When on, search calls bracket their kernel groups with CUDA events (recorded on the launch

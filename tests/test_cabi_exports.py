@@ -28,7 +28,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(L, n), f"{n} declared in include/bbq_b200.h but not exported"
     # and the Python binding table covers exactly the header
     assert sorted(bbq_b200._native.SYMBOLS) == names
-    assert bbq_b200._native.load().bbq_abi_version() == 2
+    assert bbq_b200._native.load().bbq_abi_version() == 3
 
 
 def test_library_holds_sm100a_code():

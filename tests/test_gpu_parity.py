@@ -30,7 +30,7 @@ def bbq():
 def make_format(bbq, sim, qb=4, lam=0.1, iters=5, force_path=None, scan=None, qquant=None, dyntau=None,
                 popc_form=None):
     """force_path / scan / qquant are test knobs read by bbq_create
-    (BBQ_FORCE_PATH, BBQ_SCAN=popc|mma, BBQ_QQUANT=thread)."""
+    (BBQ_FORCE_PATH, BBQ_SCAN=popc|mma, BBQ_QQUANT=thread|warp|cta)."""
     saved = {k: os.environ.pop(k, None) for k in ("BBQ_FORCE_PATH", "BBQ_SCAN", "BBQ_QQUANT", "BBQ_DYNTAU", "BBQ_POPC_FORM")}
     if popc_form is not None:
         os.environ["BBQ_POPC_FORM"] = popc_form
@@ -116,7 +116,7 @@ def test_index_build_degenerate_rows(bbq):
 # ---- K4: query quantisation ----------------------------------------------------------------------------
 @pytest.mark.parametrize("sim", SIMS)
 @pytest.mark.parametrize("qb", [1, 2, 4, 7, 8])
-@pytest.mark.parametrize("qquant", [None, "thread"])   # warp-per-query (default) and thread-per-query kernels
+@pytest.mark.parametrize("qquant", [None, "cta", "warp", "thread"])   # default (CTA per query for a narrow batch), and each K4 form forced
 def test_query_quantize_bit_exact(bbq, sim, qb, qquant):
     rows, qs = gaussian(400, 200, 21), gaussian(5, 200, 22)
     qs[3] = 0                      # zero query: norm == 0 branch under COSINE

@@ -328,3 +328,77 @@ def test_pinned_host_buffers_and_limits(bbq):
     with pytest.raises(bbq.BbqError) as e:       # indexBits > 2: neither the reference's search nor this build's
         bbq.createBinaryQuantizationFormat({"indexBits": 3, "quantizer": {"similarityFunction": "COSINE"}}).quantizeVectors(rows)
     assert e.value.status == 9
+
+
+# ---- narrow batches: the captured launch sequence (CUDA graph) of bbq_search ------------------------------------------
+@pytest.mark.parametrize("sim", SIMS)
+@pytest.mark.parametrize("n,nq", [(30000, 1), (30000, 3), (30000, 8), (900, 2)])   # popcount stream scan, tensor-core scan, direct path
+def test_replayed_launch_sequence_equals_oracle(bbq, sim, n, nq):
+    """bbq_search captures the device sequence of a narrow batch the second time the same (index, batch size, k) arrives
+    and replays it afterwards: every call — direct, capturing, replayed — must return the oracle's lists for ITS queries,
+    report bad queries like the reference, and survive other calls in between (which move scratch buffers)."""
+    dim, k = 96, 7
+    rows = gaussian(n, dim, 700 + nq)
+    idx = O.quantize_vectors(rows, sim=sim, want_unpacked=False)
+    fmt = make_format(bbq, sim)
+    qv = fmt.adoptQuantized(idx.packed, idx.corr, idx.centroid)
+
+    def check(seed):
+        qs = gaussian(nq, dim, seed)
+        gi, gs = fmt.searchBatch(qs, qv, k)
+        for qi in range(nq):
+            wi, ws = O.search_nearest_neighbors(qs[qi], idx, k, mode="canonical")
+            assert gi[qi].tolist() == wi.tolist() and bits_equal(gs[qi], ws), (seed, qi)
+
+    for seed in range(800, 806):
+        check(seed)
+    r0 = fmt.stats()["graph_replays"]
+    assert r0 >= 3, "the third and later calls with one key replay the captured sequence"
+    launches_before = fmt.stats()["kernel_launches"]
+    check(806)
+    assert fmt.stats()["kernel_launches"] > launches_before        # the replayed kernels are still counted
+    # a bad query through the replayed sequence: the reference's message, and the context answers as before afterwards
+    bad = gaussian(nq, dim, 807)
+    bad[nq - 1, 5] = np.nan
+    with pytest.raises(bbq.BbqError) as e:
+        fmt.searchBatch(bad, qv, k)
+    assert e.value.status == 5
+    check(808)
+    # another batch size in between moves scratch buffers: the old sequence must not be replayed on stale addresses
+    big = gaussian(300, dim, 809)
+    gi, gs = fmt.searchBatch(big, qv, k)
+    wi, ws = O.search_nearest_neighbors(big[299], idx, k, mode="canonical")
+    assert gi[299].tolist() == wi.tolist() and bits_equal(gs[299], ws)
+    for seed in range(810, 814):
+        check(seed)
+    assert fmt.stats()["graph_replays"] > r0
+    # a second index of the same shape on the same context: its own key, its own answers
+    rows2 = gaussian(n, dim, 900 + nq)
+    idx2 = O.quantize_vectors(rows2, sim=sim, want_unpacked=False)
+    qv2 = fmt.adoptQuantized(idx2.packed, idx2.corr, idx2.centroid)
+    for seed in range(820, 824):
+        qs = gaussian(nq, dim, seed)
+        gi, gs = fmt.searchBatch(qs, qv2, k)
+        wi, ws = O.search_nearest_neighbors(qs[0], idx2, k, mode="canonical")
+        assert gi[0].tolist() == wi.tolist() and bits_equal(gs[0], ws)
+        check(seed + 10)                                           # and the first index, alternating
+
+
+def test_replayed_sequence_overflow_falls_back(bbq):
+    """All rows equal: the candidate lists overflow on every call; with the overflow flag read after the call's single
+    synchronisation (and the sequence replayed from a graph) the exact path must still take over."""
+    n, dim, nq, k = 40000, 64, 2, 10
+    row = gaussian(1, dim, 131)
+    idx = O.quantize_vectors(np.concatenate([row, gaussian(3, dim, 132)]), sim="COSINE", want_unpacked=False,
+                             centroid=np.zeros(dim, np.float32))
+    packed, corr = np.repeat(idx.packed[:1], n, 0), np.repeat(idx.corr[:1], n, 0)
+    big = O.OracleIndex(idx.centroid, packed, None, corr, dim, "COSINE", 1)
+    fmt = make_format(bbq, "COSINE")
+    qv = fmt.adoptQuantized(packed, corr, idx.centroid)
+    for rep in range(5):
+        qs = gaussian(nq, dim, 133 + rep)
+        gi, gs = fmt.searchBatch(qs, qv, k)
+        st = fmt.stats()
+        assert st["last_overflow"] == 1 and st["last_path"] == 2
+        wi, ws = O.search_nearest_neighbors(qs[1], big, k, mode="canonical")
+        assert gi[1].tolist() == wi.tolist() == list(range(k)) and bits_equal(gs[1], ws)
