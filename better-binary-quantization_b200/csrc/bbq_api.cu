@@ -1,6 +1,7 @@
 // bbq_api.cu — host side of libbbq_b200.so: the C ABI declared in include/bbq_b200.h.
 // Owns device memory, the stream and the launch sequence; no torch, no CPU fallback.
 #include <cuda_runtime.h>
+#include <atomic>
 #include <dlfcn.h>
 #include <nccl.h>  // types and prototypes only: the library is dlopen'ed on first use (bbq_comm_*), never linked
 
@@ -46,7 +47,7 @@ static int fail(int status, const std::string& msg, int64_t vec = -1, int64_t po
     if (_s != BBQ_OK) return _s;  \
   } while (0)
 
-static uint64_t g_scratch_gen = 0;  // bumped whenever any scratch buffer moves: a captured launch sequence holds its address
+static std::atomic<uint64_t> g_scratch_gen{0};  // bumped whenever any scratch buffer moves: a captured launch sequence holds its address
 struct DevBuf {  // grow-only device scratch
   void* p = nullptr;
   size_t cap = 0;
@@ -185,7 +186,7 @@ struct StreamBridge {
   }
 };
 
-static uint64_t g_index_serial = 0;
+static std::atomic<uint64_t> g_index_serial{0};
 struct bbq_index {
   bbq_ctx* ctx = nullptr;
   uint64_t serial = ++g_index_serial;  // never reused (an address can be): part of the key of a captured launch sequence
