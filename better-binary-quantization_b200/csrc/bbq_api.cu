@@ -974,17 +974,17 @@ static int prepare_mma_operands(bbq_index* ix, int nq, const MmaPlan& pl, cudaSt
   return BBQ_OK;
 }
 
-template <int MODE, int LAYOUT>
+template <int MODE, int LAYOUT, bool DBG>
 static int launch_mma_sim(bbq_ctx* c, int sim, int cpq, unsigned grid, size_t smem, cudaStream_t st, const MmaParams& p) {
-#define BBQ_MMA_CASE(S)                                                                                                  \
-  case S:                                                                                                                \
-    if (cpq == 1) {                                                                                                      \
-      CU(cudaFuncSetAttribute(k_scan_mma<MODE, S, 1, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      LAUNCH(c, (k_scan_mma<MODE, S, 1, LAYOUT>), grid, MmaLayout<LAYOUT>::THREADS, smem, st, p);                       \
-    } else {                                                                                                             \
-      CU(cudaFuncSetAttribute(k_scan_mma<MODE, S, 2, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      LAUNCH(c, (k_scan_mma<MODE, S, 2, LAYOUT>), grid, MmaLayout<LAYOUT>::THREADS, smem, st, p);                       \
-    }                                                                                                                    \
+#define BBQ_MMA_CASE(S)                                                                                                       \
+  case S:                                                                                                                     \
+    if (cpq == 1) {                                                                                                           \
+      CU(cudaFuncSetAttribute(k_scan_mma<MODE, S, 1, LAYOUT, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      LAUNCH(c, (k_scan_mma<MODE, S, 1, LAYOUT, DBG>), grid, MmaLayout<LAYOUT>::THREADS, smem, st, p);                       \
+    } else {                                                                                                                  \
+      CU(cudaFuncSetAttribute(k_scan_mma<MODE, S, 2, LAYOUT, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      LAUNCH(c, (k_scan_mma<MODE, S, 2, LAYOUT, DBG>), grid, MmaLayout<LAYOUT>::THREADS, smem, st, p);                       \
+    }                                                                                                                         \
     break;
   switch (sim) {
     BBQ_MMA_CASE(0)
@@ -1054,10 +1054,15 @@ static int launch_scan_mma(bbq_index* ix, int mode, int nq, uint32_t k, const Mm
   if (mode != SCAN_DUMP) c->stats.mma_layout = (uint32_t)pl.layout;
   c->stats.mma_passes = (uint32_t)pl.passes;
   const unsigned grid = (unsigned)std::min<int64_t>(ntiles, c->sm_count);
-  // (the dump — threshold sample, parity taps — always runs the wide-batch roles: it is a few hundred tiles)
-  if (mode == SCAN_DUMP) return launch_mma_sim<SCAN_DUMP, 0>(c, p.sim, pl.cpq, grid, pl.smem, st, p);
-  if (pl.layout == 1) return launch_mma_sim<SCAN_FILTER, 1>(c, p.sim, pl.cpq, grid, pl.smem, st, p);
-  return launch_mma_sim<SCAN_FILTER, 0>(c, p.sim, pl.cpq, grid, pl.smem, st, p);
+  // (the dump — threshold sample, parity taps — always runs the wide-batch roles: it is a few hundred tiles,
+  // and without the attribution knobs; the filtered scan carries them only when BBQ_MMA_DEBUG asks for one)
+  if (mode == SCAN_DUMP) return launch_mma_sim<SCAN_DUMP, 0, false>(c, p.sim, pl.cpq, grid, pl.smem, st, p);
+  if (c->mma_debug != 0) {
+    if (pl.layout == 1) return launch_mma_sim<SCAN_FILTER, 1, true>(c, p.sim, pl.cpq, grid, pl.smem, st, p);
+    return launch_mma_sim<SCAN_FILTER, 0, true>(c, p.sim, pl.cpq, grid, pl.smem, st, p);
+  }
+  if (pl.layout == 1) return launch_mma_sim<SCAN_FILTER, 1, false>(c, p.sim, pl.cpq, grid, pl.smem, st, p);
+  return launch_mma_sim<SCAN_FILTER, 0, false>(c, p.sim, pl.cpq, grid, pl.smem, st, p);
 }
 
 static ScanParams base_scan_params(bbq_index* ix, int nq) {

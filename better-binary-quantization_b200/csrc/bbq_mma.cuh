@@ -743,9 +743,10 @@ __device__ void mma_drain_ring(const HitCtx* cx, uint64_t* ring, const uint32_t*
 // CH tcgen05.st in flight before the single wait::st); hand-off h belongs to group h % G.  Every group prefetches its
 // own chunks PF deep across tile boundaries, and group 0 asks L2 for each row four tiles ahead (the 16-byte loads
 // themselves come too late to hide an HBM round trip under a busy SM).
-template <int G, int CH>
+template <int G, int CH, bool DBG>
 __device__ __forceinline__ void mma_expansion(const MmaParams& p, uint64_t* a_full, uint64_t* a_empty, uint32_t tmem_base,
                                               uint32_t a_col, int nstage, int nchunks, int warp, int lane) {
+  const uint32_t dbg = DBG ? p.debug : 0u;     // the production instantiation carries none of the attribution knobs
   const int grp = (warp - 4) >> 2;
   const int r = ((warp - 4) & 3) * 32 + lane;  // row within the tile == TMEM lane
   const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
@@ -767,7 +768,7 @@ __device__ __forceinline__ void mma_expansion(const MmaParams& p, uint64_t* a_fu
   };
   auto pf_set_tile = [&]() {
     pf_ptr = reinterpret_cast<const uint4*>(row_ptr(pf_tile));
-    if (grp == 0 && !(p.debug & 128u)) {
+    if (grp == 0 && !(dbg & 128u)) {
       const uint8_t* far = row_ptr(pf_tile + L2_AHEAD);
       if (far != nullptr)
         for (int b = 0; b < p.row_bytes; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(far + b));
@@ -830,7 +831,7 @@ __device__ __forceinline__ void mma_expansion(const MmaParams& p, uint64_t* a_fu
       for (int i = 0; i < PF; i += CH) {
         const int64_t h = h0 + (i / CH) * G;  // this group's hand-off
         if (h < hands) {
-          const bool tr = (p.debug & 32u) && blockIdx.x == 0 && warp == 4 && lane == 0 && pass == 0 && exp_ev < 1000;
+          const bool tr = (dbg & 32u) && blockIdx.x == 0 && warp == 4 && lane == 0 && pass == 0 && exp_ev < 1000;
           long long x0 = tr ? clock64() : 0;
           uint32_t e[2][32];
           uint32_t sid[CH];
@@ -897,8 +898,12 @@ __device__ __forceinline__ void mma_expansion(const MmaParams& p, uint64_t* a_fu
 
 // CPQ = accumulator columns per query: 1, or 2 when the query code is split into nibbles (k_query_tiles); then the
 // epilogue works on val = 16 * D_hi + D_lo = 8 * dot and every per-query table is indexed by column / 2.
-template <int MODE, int SIM, int CPQ, int LAYOUT>
+// DBG = false is the production instantiation: every BBQ_MMA_DEBUG knob (timeline stamps, attribution switches,
+// first-level statistics) compiles away — the kernel is register- and layout-sensitive enough that merely CARRYING an
+// unused code path moved it by 12 % (profiles/r02_k2_paired_store_experiment.txt).
+template <int MODE, int SIM, int CPQ, int LAYOUT, bool DBG>
 __global__ void __launch_bounds__(MmaLayout<LAYOUT>::THREADS, 1) k_scan_mma(const __grid_constant__ MmaParams p) {
+  const uint32_t dbg = DBG ? p.debug : 0u;
   constexpr int MMA_EPI_WARPS = MmaLayout<LAYOUT>::EPI_WARPS, MMA_EXP_GROUPS = MmaLayout<LAYOUT>::EXP_GROUPS,
                 MMA_EPI_WARP0 = MmaLayout<LAYOUT>::EPI_WARP0, MMA_THREADS = MmaLayout<LAYOUT>::THREADS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1003,7 +1008,7 @@ __global__ void __launch_bounds__(MmaLayout<LAYOUT>::THREADS, 1) k_scan_mma(cons
       for (int kc = me; kc < nchunks; kc += NI) {
         const uint32_t g = gchunk + (uint32_t)kc;
         const uint32_t stage = g % (uint32_t)nstage, sphase = (g / (uint32_t)nstage) & 1u;
-        const bool tr = (p.debug & 32u) && blockIdx.x == 0 && lane == 0 && pass == 0 && me == 0;
+        const bool tr = (dbg & 32u) && blockIdx.x == 0 && lane == 0 && pass == 0 && me == 0;
         long long t0 = tr ? clock64() : 0;
         mbar_wait(a_full + stage, sphase);
         tc_fence_after();
@@ -1063,14 +1068,14 @@ __global__ void __launch_bounds__(MmaLayout<LAYOUT>::THREADS, 1) k_scan_mma(cons
     // medium batches, wide rows) it hands over FOUR at a time — the tcgen05.wait::st round trip, not the ALU work,
     // bounds the feed, and four stores in flight amortise it twice as well; two groups alternate pairs of chunks when 8
     // stages exist, single chunks otherwise.
-    if (MMA_EXP_GROUPS == 2 && nstage >= 8 && !(p.debug & 1024u))
-      mma_expansion<2, 2>(p, a_full, a_empty, tmem_base, a_col, nstage, nchunks, warp, lane);
+    if (MMA_EXP_GROUPS == 2 && nstage >= 8 && !(dbg & 1024u))
+      mma_expansion<2, 2, DBG>(p, a_full, a_empty, tmem_base, a_col, nstage, nchunks, warp, lane);
     else if (MMA_EXP_GROUPS == 2)
-      mma_expansion<2, 1>(p, a_full, a_empty, tmem_base, a_col, nstage, nchunks, warp, lane);
-    else if (nstage >= 8 && !(p.debug & 512u))
-      mma_expansion<1, 4>(p, a_full, a_empty, tmem_base, a_col, nstage, nchunks, warp, lane);
+      mma_expansion<2, 1, DBG>(p, a_full, a_empty, tmem_base, a_col, nstage, nchunks, warp, lane);
+    else if (nstage >= 8 && !(dbg & 512u))
+      mma_expansion<1, 4, DBG>(p, a_full, a_empty, tmem_base, a_col, nstage, nchunks, warp, lane);
     else
-      mma_expansion<1, 2>(p, a_full, a_empty, tmem_base, a_col, nstage, nchunks, warp, lane);
+      mma_expansion<1, 2, DBG>(p, a_full, a_empty, tmem_base, a_col, nstage, nchunks, warp, lane);
   } else if (warp >= MMA_EPI_WARP0) {
     // ===== epilogue: first-level integer screen on the accumulators, second level + parking for what passes =====
     const int ew = warp - MMA_EPI_WARP0;           // 0 .. MMA_EPI_WARPS-1
@@ -1146,9 +1151,8 @@ __global__ void __launch_bounds__(MmaLayout<LAYOUT>::THREADS, 1) k_scan_mma(cons
           const float Sl = S - H - fmaf(A, 1.9073486328125e-06f, 1.0f);
           T = (Sl > -1.0e9f && Sl < 1.0e9f) ? (int)floorf(Sl) : INT_MIN;  // NaN / out of range: everything passes on
           if (!valid) T = INT_MAX;
-          if (always || MODE != SCAN_FILTER || p.qenv == nullptr || (p.debug & 64u)) T = INT_MIN;
+          if (always || MODE != SCAN_FILTER || p.qenv == nullptr || (dbg & 64u)) T = INT_MIN;
         }
-        const uint32_t l2flags = (always ? 1u : 0u) | ((p.debug & 1u) ? 2u : 0u) | ((p.debug & 2u) ? 4u : 0u);
         const uint64_t rv2 = f2_pack(rv, rv), x1f2 = f2_pack(x1f, x1f), gv2 = f2_pack(gv, gv), iv2 = f2_pack(iv, iv);
         // f64 correctives: issued now, consumed only by the dump
         RowTerms rt{0.0, 0.0, 0.0, 0u};
@@ -1181,7 +1185,7 @@ __global__ void __launch_bounds__(MmaLayout<LAYOUT>::THREADS, 1) k_scan_mma(cons
           tc_ldw(d_addr + (uint32_t)c0, acc);
           tc_wait_ld();
         }
-        if (p.debug & 4u) c0 = nv;
+        if (dbg & 4u) c0 = nv;
         auto chunk = [&](int (&cur)[W], int (&nx)[W], int cc) -> bool {
           const int c1 = cc + NSUB * W;
           if (c1 < nv) tc_ldw(d_addr + (uint32_t)c1, nx);
@@ -1226,7 +1230,7 @@ __global__ void __launch_bounds__(MmaLayout<LAYOUT>::THREADS, 1) k_scan_mma(cons
               }
               const int m = max(max(mm[0], mm[1]), max(mm[2], mm[3]));
               go = m >= T;
-              if (p.debug & 256u) {
+              if (dbg & 256u) {
                 dbg_tested++;
                 dbg_passed += go ? 1ull : 0ull;
                 const bool any_go = __any_sync(0xffffffffu, go);  // (every lane votes: no short-circuit around it)
@@ -1234,7 +1238,7 @@ __global__ void __launch_bounds__(MmaLayout<LAYOUT>::THREADS, 1) k_scan_mma(cons
               }
             }
             uint32_t mask = 0u;
-            if (go && !(p.debug & 1u)) {
+            if (go && !(dbg & 1u)) {
 #pragma unroll
               for (int j = 0; j < NVC / 2; j++) {  // two queries per step
                 const int pj = (qc >> 1) + j;
@@ -1259,7 +1263,7 @@ __global__ void __launch_bounds__(MmaLayout<LAYOUT>::THREADS, 1) k_scan_mma(cons
             const uint32_t vmask = (nvq - qc >= 32) ? 0xFFFFFFFFu : ((1u << (nvq - qc)) - 1u);  // never a padding slot: its query id would alias
             if (always) mask = 0xFFFFFFFFu;
             mask &= vmask;
-            if (p.debug & 2u) mask = 0u;
+            if (dbg & 2u) mask = 0u;
             auto v_at = [&](int j) { return j < NVC ? val[j < NVC ? j : 0] : 0; };
             if ((mask & 0xFFFFu) != 0u)  // park the hits for the drainer warp
               mma_park_hits(ring_s, ring_ctl_s + 0, ring_ctl_s + 1, mask & 0xFFFFu, (uint32_t)row, q0q + qc, v_at(0), v_at(1),
@@ -1295,7 +1299,7 @@ __global__ void __launch_bounds__(MmaLayout<LAYOUT>::THREADS, 1) k_scan_mma(cons
         tcount++;
       }
     }
-    if (p.debug & 256u) {
+    if (dbg & 256u) {
       atomicAdd(reinterpret_cast<unsigned long long*>(p.trace) + 3 * 4096 + 0, dbg_tested);
       atomicAdd(reinterpret_cast<unsigned long long*>(p.trace) + 3 * 4096 + 1, dbg_passed);
       atomicAdd(reinterpret_cast<unsigned long long*>(p.trace) + 3 * 4096 + 2, dbg_warps);
