@@ -64,3 +64,26 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cc", ".ts", ".js", ".json")):
                 src = open(os.path.join(dp, f), encoding="utf-8").read()
                 assert not pat.search(src), f"{os.path.join(dp, f)} references the oracle"
+
+
+def test_ctypes_structs_mirror_the_header(tmp_path):
+    """The ctypes mirrors of bbq_config / bbq_stats (what every Python caller and the tests pass across the C ABI) have
+    the header's size and field offsets: a tiny C program compiled against include/bbq_b200.h prints them."""
+    fields = {"bbq_config": [f for f, _ in bbq_b200._native.BbqConfig._fields_],
+              "bbq_stats": [f for f, _ in bbq_b200._native.BbqStats._fields_]}
+    cname = {"lambda_": "lambda"}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "bbq_b200.h"', "int main(void) {"]
+    for st, fs in fields.items():
+        lines.append(f'  printf("{st} %zu\\n", sizeof({st}));')
+        for f in fs:
+            lines.append(f'  printf("{st}.{f} %zu\\n", offsetof({st}, {cname.get(f, f)}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for st, cls in (("bbq_config", bbq_b200._native.BbqConfig), ("bbq_stats", bbq_b200._native.BbqStats)):
+        assert int(got[st]) == C.sizeof(cls), st
+        for f, _ in cls._fields_:
+            assert int(got[f"{st}.{f}"]) == getattr(cls, f).offset, (st, f)
