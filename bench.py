@@ -57,12 +57,48 @@ SEED_CORPUS, SEED_QUERY = 20260101, 20260201
 METRIC, UNIT = "QPS (4b x 1b BBQ score+top-k)", "queries/s"
 
 
+# --corpus clustered: a Gaussian mixture (the recall harness's corpus, tools/recall_harness.py --clusters): every row and
+# every query is a centre plus noise, so the rankings the parity checks compare are about real neighbours (cluster-mates),
+# not about the noise floor of an i.i.d. Gaussian corpus.  The analytic centroid is still 0 (explicit zero centroid).
+CORPUS = "gaussian"
+N_CENTRES, CLUSTER_NOISE, SEED_CENTRES = 1000, 0.5, 20260301
+_centres_cache = {}
+
+
+def centres_host(dim):
+    if dim not in _centres_cache:
+        _centres_cache[dim] = np.random.default_rng(SEED_CENTRES).standard_normal((N_CENTRES, dim), dtype=np.float32)
+    return _centres_cache[dim]
+
+
 def gen_chunk_host(c, dim, rows):
-    return np.random.default_rng(SEED_CORPUS + c).standard_normal((rows, dim), dtype=np.float32)
+    x = np.random.default_rng(SEED_CORPUS + c).standard_normal((rows, dim), dtype=np.float32)
+    if CORPUS == "clustered":
+        pick = np.random.default_rng(SEED_CORPUS + c + (1 << 20)).integers(0, N_CENTRES, rows)
+        x = centres_host(dim)[pick] + np.float32(CLUSTER_NOISE) * x
+    return x
+
+
+def gen_chunk_device(torch, c, dim, rows, device="cuda"):
+    """The device-side twin of gen_chunk_host (its own random stream: the two are different corpora of one family)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(SEED_CORPUS + c)
+    x = torch.randn((rows, dim), generator=g, device=device, dtype=torch.float32)
+    if CORPUS == "clustered":
+        key = ("t", dim, str(device))
+        if key not in _centres_cache:
+            _centres_cache[key] = torch.from_numpy(centres_host(dim)).to(device)
+        pick = torch.randint(0, N_CENTRES, (rows,), generator=g, device=device)
+        x = _centres_cache[key][pick] + CLUSTER_NOISE * x
+    return x
 
 
 def gen_queries(nq, dim):
-    return np.random.default_rng(SEED_QUERY).standard_normal((nq, dim), dtype=np.float32)
+    q = np.random.default_rng(SEED_QUERY).standard_normal((nq, dim), dtype=np.float32)
+    if CORPUS == "clustered":
+        pick = np.random.default_rng(SEED_QUERY + 1).integers(0, N_CENTRES, nq)
+        q = centres_host(dim)[pick] + np.float32(CLUSTER_NOISE) * q
+    return q
 
 
 def load_peaks():
@@ -238,9 +274,7 @@ def build_shard(torch, fmt, w, r0, r1, device_gen):
         c0 = c * CHUNK
         lo, hi = max(pos, c0), min(r1, c0 + CHUNK)
         if device_gen:
-            g = torch.Generator(device="cuda")
-            g.manual_seed(SEED_CORPUS + c)
-            rows = torch.randn((min(CHUNK, n - c0), dim), generator=g, device="cuda", dtype=torch.float32)
+            rows = gen_chunk_device(torch, c, dim, min(CHUNK, n - c0))
             part = rows[lo - c0:hi - c0].contiguous()
             fmt.appendRows(shard, d_rows_ptr=part.data_ptr(), n=hi - lo)
             del rows, part
@@ -517,7 +551,9 @@ def run_gpu(args, w, rank, world, local_rank):
                                     f"libbbq_b200.so (bbq_search_sharded, NCCL {comm['nccl_version']}, {comm['world']} ranks) + merge"
                                     if world > 1 else "single shard"),
                        "l2": "256 MB flush buffer written between timed iterations",
-                       "corpus": f"N(0,1) f32, {'device' if m['device_gen'] else 'host'}-generated per 65536-row chunk, "
+                       "corpus": ("N(0,1) f32" if CORPUS == "gaussian" else
+                                  f"Gaussian mixture f32 ({N_CENTRES} centres ~ N(0,1), noise {CLUSTER_NOISE}; queries drawn the same way)") +
+                                 f", {'device' if m['device_gen'] else 'host'}-generated per 65536-row chunk, "
                                  f"explicit zero centroid; index build {m['build_s']:.1f}s (untimed)",
                        "path": {0: "direct", 1: "sampled threshold + filtered scan", 2: "exact chunked"}[st["last_path"]],
                        "remaining_fixed_costs": "per step: one query validation+quantisation, one threshold sample, one "
@@ -663,6 +699,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--datagen", default="auto", choices=["auto", "host", "device"])
+    ap.add_argument("--corpus", default="gaussian", choices=["gaussian", "clustered"],
+                    help="clustered: 1000-centre Gaussian mixture (rows and queries), so that the checked rankings are about real neighbours")
     ap.add_argument("--nq", type=int, default=0, help="override the queries per step of the workload (experiments)")
     ap.add_argument("--rows", type=int, default=0, help="override the corpus rows of the workload (experiments)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs")
@@ -688,6 +726,10 @@ def main():
     if args.rows > 0:
         w["n"] = args.rows
         w["name"] += f" [rows overridden: {args.rows}]"
+    if args.corpus != "gaussian":
+        global CORPUS
+        CORPUS = args.corpus
+        w["name"] += f" [corpus: {args.corpus}]"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
