@@ -2,20 +2,24 @@
 //
 // For a batch of queries the scan is the integer contraction  dot[v][q] = sum_d bit_d(x_v) * q_code[q][d]
 // (src/utils/computeBatchFourBitDotProductDirectPacked.ts:10-53, one call per query in the reference).
-// Here it is ONE persistent, warp-specialised kernel per query batch:
+// Here it is ONE persistent, warp-specialised kernel per query batch (512 threads, one CTA per SM):
 //
-//   * B operand  = a block of <= 224 queries' codes, resident in shared memory for a whole pass over the
-//                  index shard (no-swizzle K-major core-matrix image, loaded with cp.async.bulk);
-//   * A operand  = the 1-bit index rows, expanded on the fly by 4 "expansion" warps (one thread per row,
-//                  1 SHF + 8 LOP3 per 32 dims) and written STRAIGHT INTO TENSOR MEMORY with tcgen05.st —
-//                  the packed index is the only thing streamed from HBM (128 B/row), the expanded bytes
-//                  never touch shared memory;
-//   * D          = s32 accumulators in TMEM, double buffered: tcgen05.mma.kind::i8 (M=128, N<=224, K=32)
-//                  issued by one elected thread; exact integers (<= 15*8*dim, far below 2^31);
-//   * epilogue   = 8 warps read D with tcgen05.ld (thread = index row, columns = queries), screen every
-//                  pair with a 4-FMA fp32 bound against the query's running k-th score, and replay the
-//                  reference's f64 corrective formula (src/batchDotProduct.ts:554-617) only for the pairs
-//                  the screen cannot exclude; survivors are appended to the per-query candidate lists.
+//   * B operand  = a block of <= 224 accumulator columns (one per query; two for codes wider than 5 bits), resident
+//                  in shared memory for a whole pass over the index shard (no-swizzle K-major core-matrix image,
+//                  loaded with cp.async.bulk by warp 0);
+//   * A operand  = the 1-bit index rows, expanded on the fly by one or two "expansion" groups of 4 warps (one thread
+//                  per row, 1 SHF + 8 LOP3 per 32 dims) and written STRAIGHT INTO TENSOR MEMORY with tcgen05.st —
+//                  the packed index is the only thing streamed from HBM (128 B/row), the expanded bytes never touch
+//                  shared memory;
+//   * D          = s32 accumulators in TMEM, double buffered: tcgen05.mma.kind::i8 (M=128, N<=224, K=32) issued by two
+//                  or three elected threads on alternate 128-dim chunks; exact integers (<= 15*8*dim, far below 2^31);
+//   * epilogue   = 8 (wide batches) or 4 (narrow batches) warps read D with tcgen05.ld (thread = index row, columns =
+//                  queries), screen the pairs — COSINE / MIP first with an integer test on the accumulators against a
+//                  per-block envelope, then with a 4-FMA fp32 bound against the query's running k-th score — and PARK
+//                  the few pairs the screens cannot exclude; a drainer warp replays those with the reference's f64
+//                  corrective formula (src/batchDotProduct.ts:554-617) and appends survivors to the candidate lists.
+//   Role layouts: MmaLayout<0> "wide" = 8 epilogue warps + 1 expansion group + 2 issuers, MmaLayout<1> "narrow" = 4 + 2
+//   + 3 issuers (the B loader's warp takes a third share), picked per launch by the width of the resident block.
 //
 // A is expanded with weights: K position 32g + 4u + j (u = 4s + b) holds  2^b * bit(4s+b of packed byte j of
 // word g)  and B holds  code[dim] * 2^(3-b), so every product is 8 * code * bit and D = 8 * dot exactly;
