@@ -6,13 +6,22 @@
 // tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs may load it; nothing under better-binary-quantization_b200/ links or calls it.
 //
-// PARITY STATUS: "parity unpinned" for exact score / interval / index-list values.
-// The reference cannot be executed in the build container (no node/tsc/vitest,
-// no cargo, no wasm runtime) and its own tests hold no golden score vectors, so the
-// oracle is pinned only by (tests/test_oracle_kat.py):
+// PARITY STATUS: PINNED BY FIXTURES GENERATED FROM THE REFERENCE'S OWN SOURCE TEXT (round 2), with one caveat.
+// No JavaScript / TypeScript runtime exists in the build container or on the GPU box (profiles/r02_js_runtime_probe.txt)
+// and the reference's own tests hold no golden score vectors.  tests/golden/from_ts/tsinterp.py — a TypeScript-subset
+// interpreter written for this purpose — executes the UNMODIFIED /root/reference/src/index.ts (every module on the
+// path) on seeded inputs; tests/golden/from_ts/*.ts.json are its outputs (each records the SHA-256 of the reference
+// files), and tests/test_golden_from_ts.py requires this oracle to reproduce them BIT FOR BIT: centroid, every row's
+// code and correctives (f64 bit patterns), every row's f32 score, the heap-ordered top-k lists, quantizeQueryVector,
+// the statistics of computeQuantizationAccuracy, getOversampledTopKWithHeap — all three similarity functions, 4-bit and
+// 1-bit queries, dim % 8 != 0, iters = 20.  Caveat: the executing engine is that interpreter, not V8; its ECMAScript
+// number semantics are tested separately (tests/test_tsinterp.py).  Two independent derivations from the same text — a
+// hand restatement in C++ and a mechanical execution — agree on every bit.
+// Also pinned by (tests/test_oracle_kat.py):
 //   * the four exact known-answer tests in rust-wasm/src/*.rs,
 //   * the deterministic sin/cos recall fixtures + thresholds of tests/recall*.ts,
 //   * the behavioural properties the reference tests assert (k=0, k>N, ordering...).
+// The indexBits = 2 EXTENSION below has no reference behaviour to be pinned to ("parity unpinned by construction").
 //
 // Build: g++ -O2 -std=c++17 -ffp-contract=off -fno-fast-math (see oracle/Makefile).
 // -ffp-contract=off is REQUIRED: JS never fuses a*b+c.

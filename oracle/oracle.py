@@ -3,7 +3,8 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may
 import this module.  Nothing under better-binary-quantization_b200/ does.
 
-PARITY STATUS: "parity unpinned" for exact values — see the header of bbq_oracle.cpp.
+PARITY STATUS: pinned bit for bit by fixtures generated from the reference's own source text
+(tests/golden/from_ts/*.ts.json, tests/test_golden_from_ts.py) — see the header of bbq_oracle.cpp.
 
 Function names follow the reference (leolee9086/Better-Binary-Quantization, TypeScript):
   normalize_vector      src/vectorOperations.ts:11-34

@@ -1,0 +1,135 @@
+"""Golden fixtures FROM THE REFERENCE'S OWN SOURCE TEXT.
+
+No JavaScript / TypeScript runtime exists in this image or on the GPU box (profiles/r02_js_runtime_probe.txt), so
+`make_golden_from_ts.mjs` (which needs Node) has never run.  This script does the same job with `tsinterp.py`, a
+TypeScript-subset interpreter written for exactly this purpose: it loads the UNMODIFIED `<reference>/src/index.ts`
+(every module it imports; only the async WASM bridge `src/wasm/index.ts` is loaded as an empty module — it is outside
+the path), calls the reference's public API on the seeded inputs of `tests/golden/make_golden.py`, and writes
+`<case>.ts.json` in the schema of the .mjs generator plus a few more members of the class:
+
+  createBinaryQuantizationFormat(config)                       src/index.ts
+  format.quantizeVectors(base)                                 src/binaryQuantizationFormat.ts:165-263
+      -> centroid, every row's packed code + four corrective terms
+  format.searchNearestNeighbors(q, qv, k) and (q, qv, n)       :308-412  -> top-k list, every row's f32 score
+  format.quantizeQueryVector(q, centroid)                      :271-299  -> codes + correctives (ONE normalisation)
+  format.computeQuantizationAccuracy(rows[:nq], queries)       :420-475  -> the five statistics
+  getOversampledTopKWithHeap(q, qv, base, k, 3, format)        src/topKSelector.ts:29-78
+
+Nothing of the reference is copied into the repository: the sources are read where they lie, the fixture records their
+SHA-256 so that it is clear which text produced it.  `tests/test_golden_from_ts.py` compares the oracle with the
+fixtures bit for bit; `tests/test_tsinterp.py` tests the interpreter itself.
+
+    python tests/golden/from_ts/make_golden_with_interp.py [--reference /root/reference] [case ...]
+"""
+import argparse
+import hashlib
+import json
+import os
+import struct
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+import tsinterp as T  # noqa: E402
+from tests.fixtures import gaussian, sincos_dataset  # noqa: E402
+from tests.golden.make_golden import CASES  # noqa: E402
+
+OVERSAMPLE = 3
+
+
+def f64bits(x):
+    return struct.pack(">d", float(x)).hex()
+
+
+def f32bits(x):
+    return struct.unpack("<I", struct.pack("<f", float(x)))[0]
+
+
+def inputs(name):
+    n, dim, sim, qb, k, nq, lam, iters, data = CASES[name]
+    if data == "gauss":
+        seed = 20260101 + sum(map(ord, name))
+        return gaussian(n, dim, seed), gaussian(nq, dim, seed + 100)
+    return sincos_dataset(dim, n, nq)
+
+
+def load_reference(ref_root, console):
+    interp = T.Interp(log=lambda *a: console.append(" ".join(map(str, a))), stub_modules=["/src/wasm/index.ts"])
+    index = interp.load(os.path.join(ref_root, "src", "index.ts"))
+    selector = interp.load(os.path.join(ref_root, "src", "topKSelector.ts"))
+    files = {}
+    for path in sorted(interp.modules):
+        if path not in interp.stubbed:
+            files[os.path.relpath(path, ref_root)] = hashlib.sha256(open(path, "rb").read()).hexdigest()
+    return interp, index, selector, files
+
+
+def run_case(name, ref_root):
+    n, dim, sim, qb, k, nq, lam, iters, data = CASES[name]
+    base, queries = inputs(name)
+    console = []
+    I, ex, sel, files = load_reference(ref_root, console)
+    t0 = time.time()
+    fmt = I.call(ex["createBinaryQuantizationFormat"], args=[
+        {"queryBits": float(qb), "indexBits": 1.0, "quantizer": {"similarityFunction": sim, "lambda": lam, "iters": float(iters)}}])
+    rows = [I.float32(r.tolist()) for r in base]
+    qv = I.call(I.get(fmt, "quantizeVectors"), fmt, [rows])["quantizedVectors"]
+    centroid = I.call(I.get(qv, "getCentroid"), qv, [])
+    out = {"n": n, "dim": dim, "nq": nq, "k": k, "queryBits": qb, "sim": sim, "lambda": lam, "iters": iters,
+           "engine": "tests/golden/from_ts/tsinterp.py (Python interpreter of the TypeScript subset) executing the unmodified "
+                     "reference sources listed in reference_sha256; src/wasm/index.ts loaded as an empty module",
+           "reference_sha256": files,
+           "centroid_bits": [f32bits(x) for x in centroid.a], "corrections_bits": [], "packed_sum": 0, "packed_head": [],
+           "queries": []}
+    for i in range(n):
+        c = I.call(I.get(qv, "getCorrectiveTerms"), qv, [float(i)])
+        out["corrections_bits"].append([f64bits(c[f]) for f in ("lowerInterval", "upperInterval", "additionalCorrection",
+                                                                "quantizedComponentSum")])
+        packed = I.call(I.get(qv, "vectorValue"), qv, [float(i)]).a
+        out["packed_sum"] += int(sum(packed))
+        if i < 16:
+            out["packed_head"].append(list(packed))
+    t_build = time.time() - t0
+    for q in queries:
+        qa = I.float32(q.tolist())
+        res = I.call(I.get(fmt, "searchNearestNeighbors"), fmt, [qa, qv, float(k)])
+        every = I.call(I.get(fmt, "searchNearestNeighbors"), fmt, [qa, qv, float(n)])     # every row's f32 score, via k = n
+        by_index = [None] * n
+        for r in every:
+            by_index[int(r["index"])] = f32bits(r["score"])
+        once = I.call(I.get(fmt, "quantizeQueryVector"), fmt, [qa, centroid])
+        qc = once["queryCorrections"]
+        over = I.call(sel["getOversampledTopKWithHeap"], args=[qa, qv, rows, float(k), float(OVERSAMPLE), fmt])
+        out["queries"].append({
+            "top_index": [int(r["index"]) for r in res], "top_score_bits": [f32bits(r["score"]) for r in res],
+            "all_score_bits": by_index,
+            "quantize_query_once": {"codes": [int(x) for x in once["quantizedQuery"].a],
+                                    "corrections_bits": [f64bits(qc[f]) for f in ("lowerInterval", "upperInterval", "additionalCorrection",
+                                                                                  "quantizedComponentSum")]},
+            "oversampled_heap": {"factor": OVERSAMPLE, "index": [int(c["index"]) for c in over],
+                                 "quantized_score_bits": [f32bits(c["quantizedScore"]) for c in over],
+                                 "true_score_bits": [f64bits(c["trueScore"]) for c in over]}})
+    m = min(nq, n)   # the member wants as many original vectors as queries (it re-quantises them): the first nq rows
+    acc = I.call(I.get(fmt, "computeQuantizationAccuracy"), fmt, [rows[:m], [I.float32(q.tolist()) for q in queries]])
+    out["accuracy"] = {"rows": m, **{f: f64bits(acc[f]) for f in ("meanError", "maxError", "minError", "stdError", "correlation")}}
+    out["console"] = console          # the reference logs nothing on this path; a '批量计算失败' warning here would mean a fallback ran
+    if any("失败" in line for line in console):
+        raise RuntimeError(f"{name}: the reference fell back from its batch path: {console[:3]}")
+    with open(os.path.join(HERE, name + ".ts.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    print(f"wrote {name}.ts.json  (quantizeVectors {t_build:.1f}s, total {time.time() - t0:.1f}s, top of query 0: {out['queries'][0]['top_index'][:5]})",
+          flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reference", default="/root/reference")
+    ap.add_argument("cases", nargs="*", default=list(CASES))
+    a = ap.parse_args()
+    for nm in a.cases:
+        run_case(nm, a.reference)

@@ -1,9 +1,9 @@
 """Generates tests/golden/*.npz from the CPU oracle (run here, committed with its outputs).
 
-The reference itself cannot be executed in this environment (TypeScript; no node/tsc/vitest, no cargo,
-no wasm runtime), so these are ORACLE outputs on seeded inputs, not reference outputs — "parity unpinned"
-for exact values (see oracle/bbq_oracle.cpp).  They pin (a) the oracle against drift between compilers /
-boxes and (b) the CUDA path on the GPU box, where /root/reference does not exist.
+These are ORACLE outputs on seeded inputs.  They pin (a) the oracle against drift between compilers / boxes and (b) the
+CUDA path on the GPU box, where /root/reference does not exist.  The oracle itself is pinned to the reference by
+tests/golden/from_ts/*.ts.json — the same seeded inputs run through the reference's own source text
+(tests/golden/from_ts/make_golden_with_interp.py, tests/test_golden_from_ts.py).
 
     python tests/golden/make_golden.py
 """

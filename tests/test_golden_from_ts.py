@@ -1,10 +1,19 @@
-"""Oracle vs fixtures generated by the REAL TypeScript reference (tests/golden/from_ts/make_golden_from_ts.mjs).
-No JS runtime exists on the build container or the GPU box (profiles/r02_js_runtime_probe.txt), so no such fixture has
-been generated and this test is skipped — it is here so that the moment a `<case>.ts.json` appears the oracle is pinned
-by it: centroid, every row's correctives (f64 bit patterns), every row's f32 score and the returned index lists."""
+"""Oracle vs fixtures generated FROM THE REFERENCE'S OWN SOURCE TEXT.
+
+`tests/golden/from_ts/*.ts.json` were produced by executing the unmodified `/root/reference/src/index.ts` (and every
+module it imports) with `tests/golden/from_ts/tsinterp.py` — a TypeScript-subset interpreter written for this purpose,
+because no JavaScript runtime exists in the image or on the GPU box (profiles/r02_js_runtime_probe.txt) — through
+`tests/golden/from_ts/make_golden_with_interp.py`.  Each fixture records the SHA-256 of the reference files that produced
+it.  The oracle must reproduce them bit for bit: centroid (f32), every row's packed code and correctives (f64 bit
+patterns), every row's f32 score, the heap-ordered top-k lists, `quantizeQueryVector` called directly, the statistics
+of `computeQuantizationAccuracy`, and `getOversampledTopKWithHeap`.
+
+`make_golden_from_ts.mjs` (the Node version of the generator) writes the same schema minus the extra members; a
+fixture without them is accepted too."""
 import glob
 import json
 import os
+import struct
 
 import numpy as np
 import pytest
@@ -17,24 +26,93 @@ HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "from_
 FIXTURES = sorted(glob.glob(os.path.join(HERE, "*.ts.json")))
 
 
-@pytest.mark.skipif(not FIXTURES, reason="no reference-run fixture: no node/bun/deno anywhere (profiles/r02_js_runtime_probe.txt)")
-@pytest.mark.parametrize("path", FIXTURES or ["none"])
+def _inputs(name):
+    n, dim, sim, qb, k, nq, lam, iters, data = CASES[name]
+    if data == "gauss":
+        seed = 20260101 + sum(map(ord, name))
+        return gaussian(n, dim, seed), gaussian(nq, dim, seed + 100)
+    return sincos_dataset(dim, n, nq)
+
+
+def _f64_from_hex(rows):
+    return np.array([[struct.unpack(">d", bytes.fromhex(h))[0] for h in row] for row in rows], np.float64)
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+def test_fixtures_from_the_reference_source_exist():
+    assert len(FIXTURES) >= 4, "run tests/golden/from_ts/make_golden_with_interp.py (needs /root/reference)"
+    sims = {json.load(open(p))["sim"] for p in FIXTURES}
+    assert sims == {"EUCLIDEAN", "COSINE", "MAXIMUM_INNER_PRODUCT"}
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[:-len(".ts.json")] for p in FIXTURES])
 def test_oracle_equals_the_typescript_reference(path):
     d = json.load(open(path))
     name = os.path.basename(path)[:-len(".ts.json")]
     n, dim, sim, qb, k, nq, lam, iters, data = CASES[name]
-    if data == "gauss":
-        seed = 20260101 + sum(map(ord, name))
-        base, queries = gaussian(n, dim, seed), gaussian(nq, dim, seed + 100)
-    else:
-        base, queries = sincos_dataset(dim, n, nq)
+    assert (d["n"], d["dim"], d["sim"], d["queryBits"], d["k"]) == (n, dim, sim, qb, k)
+    assert not d.get("console"), "the reference logged something (a fallback ran?)"
+    base, queries = _inputs(name)
     idx = O.quantize_vectors(base, sim=sim, index_bits=1, lam=lam, iters=iters)
+    # quantizeVectors: centroid, correctives, codes
     assert idx.centroid.view(np.uint32).tolist() == d["centroid_bits"]
-    want_corr = np.array([[int(h, 16) for h in row] for row in d["corrections_bits"]], np.uint64)
-    assert np.array_equal(idx.corr.view(np.uint64), want_corr)
+    assert np.array_equal(_u64(idx.corr), _u64(_f64_from_hex(d["corrections_bits"])))
     assert int(idx.packed.astype(np.uint64).sum()) == d["packed_sum"]
+    if "packed_head" in d:
+        assert idx.packed[:16].tolist() == d["packed_head"]
     for q, ref in zip(queries, d["queries"]):
+        # searchNearestNeighbors: every row's f32 score and the heap-ordered list
         _, _, alls, _ = O.search_nearest_neighbors(q, idx, k, query_bits=qb, lam=lam, iters=iters, mode="heap", want_all=True)
         assert alls.view(np.uint32).tolist() == ref["all_score_bits"]
         hi, hs = O.search_nearest_neighbors(q, idx, k, query_bits=qb, lam=lam, iters=iters, mode="heap")
         assert hi.tolist() == ref["top_index"] and hs.view(np.uint32).tolist() == ref["top_score_bits"]
+        # the canonical rule (score desc, id asc) returns the same SET whenever no exact tie straddles the k-th place
+        ci, cs = O.search_nearest_neighbors(q, idx, k, query_bits=qb, lam=lam, iters=iters, mode="canonical")
+        if len(alls) > k and np.sort(alls)[::-1][k - 1] != np.sort(alls)[::-1][k]:
+            assert sorted(ci.tolist()) == sorted(ref["top_index"])
+        if "quantize_query_once" in ref:      # quantizeQueryVector(query, centroid) as a direct member call
+            codes, corr = O.quantize_query_vector_once(q, idx.centroid, sim, qb, lam, iters)
+            assert codes.tolist() == ref["quantize_query_once"]["codes"]
+            assert np.array_equal(_u64(corr), _u64(_f64_from_hex([ref["quantize_query_once"]["corrections_bits"]])[0]))
+        if "oversampled_heap" in ref:         # getOversampledTopKWithHeap
+            ov = ref["oversampled_heap"]
+            oi, oq, ot = O.oversampled_topk(q, base, idx, k, ov["factor"], query_bits=qb, lam=lam, iters=iters, mode="heap")
+            assert oi.tolist() == ov["index"] and oq.view(np.uint32).tolist() == ov["quantized_score_bits"]
+            assert np.array_equal(_u64(ot), _u64(_f64_from_hex([ov["true_score_bits"]])[0]))
+    if "accuracy" in d:                        # computeQuantizationAccuracy(rows[:nq], queries)
+        m = d["accuracy"]["rows"]
+        stats = O.compute_quantization_accuracy(base[:m], queries, sim, qb, lam, iters)
+        for f in ("meanError", "maxError", "minError", "stdError", "correlation"):
+            want = struct.unpack(">d", bytes.fromhex(d["accuracy"][f]))[0]
+            assert np.float64(stats[f]).view(np.uint64) == np.float64(want).view(np.uint64), f
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="the reference sources are not on this box")
+@pytest.mark.parametrize("sim,qb,n,dim", [("COSINE", 4, 40, 24), ("EUCLIDEAN", 1, 30, 20), ("MAXIMUM_INNER_PRODUCT", 4, 36, 36)])
+def test_reference_source_interpreted_live_equals_oracle(sim, qb, n, dim):
+    """Where /root/reference exists (the build container), run the reference source through the interpreter NOW on a
+    tiny seeded case and compare with the oracle — guards the committed fixtures against a stale interpreter."""
+    import sys
+    sys.path.insert(0, HERE)
+    import tsinterp as T
+    console = []
+    interp = T.Interp(log=lambda *a: console.append(a), stub_modules=["/src/wasm/index.ts"])
+    ex = interp.load("/root/reference/src/index.ts")
+    base, queries = gaussian(n, dim, 4242 + n), gaussian(2, dim, 4343 + n)
+    fmt = interp.call(ex["createBinaryQuantizationFormat"], args=[
+        {"queryBits": float(qb), "indexBits": 1.0, "quantizer": {"similarityFunction": sim, "lambda": 0.1, "iters": 5.0}}])
+    rows = [interp.float32(r.tolist()) for r in base]
+    qv = interp.call(interp.get(fmt, "quantizeVectors"), fmt, [rows])["quantizedVectors"]
+    idx = O.quantize_vectors(base, sim=sim, index_bits=1)
+    corr = np.array([[interp.call(interp.get(qv, "getCorrectiveTerms"), qv, [float(i)])[f] for f in
+                      ("lowerInterval", "upperInterval", "additionalCorrection", "quantizedComponentSum")] for i in range(n)], np.float64)
+    assert np.array_equal(_u64(corr), _u64(idx.corr))
+    for q in queries:
+        res = interp.call(interp.get(fmt, "searchNearestNeighbors"), fmt, [interp.float32(q.tolist()), qv, 5.0])
+        hi, hs = O.search_nearest_neighbors(q, idx, 5, query_bits=qb, mode="heap")
+        assert [int(r["index"]) for r in res] == hi.tolist()
+        assert np.array([r["score"] for r in res], np.float32).view(np.uint32).tolist() == hs.view(np.uint32).tolist()
+    assert not console
