@@ -34,3 +34,20 @@ def true_topk_cosine(q, base, k):
     qq = q.astype(np.float64)
     s = (b @ qq) / (np.linalg.norm(b, axis=1) * np.linalg.norm(qq))
     return np.argsort(-s, kind="stable")[:k]
+
+
+def edge_dataset(n, dim, nq, seed):
+    """Rows and queries with the degenerate shapes the reference has to cope with: an all-zero row, duplicated rows
+    (exact score ties: the order the reference's MinHeap returns them in is part of its behaviour), a constant row, a
+    negated pair; a query equal to a duplicated row and an all-zero query."""
+    base, queries = gaussian(n, dim, seed), gaussian(nq, dim, seed + 1)
+    base[7] = 0
+    base[9] = base[8]
+    base[20] = base[8]
+    base[11] = 0.5
+    base[13] = -base[12]
+    if nq > 1:
+        queries[1] = base[8]
+    if nq > 2:
+        queries[2] = 0
+    return base, queries

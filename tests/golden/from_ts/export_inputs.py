@@ -9,18 +9,13 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, ROOT)
-from tests.fixtures import gaussian, sincos_dataset  # noqa: E402
-from tests.golden.make_golden import CASES  # noqa: E402
+from tests.golden.make_golden import CASES, case_inputs  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SIM = {"EUCLIDEAN": 0, "COSINE": 1, "MAXIMUM_INNER_PRODUCT": 2}
 
 for name, (n, dim, sim, qb, k, nq, lam, iters, data) in CASES.items():
-    if data == "gauss":
-        seed = 20260101 + sum(map(ord, name))
-        base, queries = gaussian(n, dim, seed), gaussian(nq, dim, seed + 100)
-    else:
-        base, queries = sincos_dataset(dim, n, nq)
+    base, queries = case_inputs(name)
     with open(os.path.join(HERE, name + ".in.bin"), "wb") as f:
         f.write(struct.pack("<7id", n, dim, nq, k, qb, SIM[sim], iters, lam))
         f.write(np.ascontiguousarray(base, "<f4").tobytes())

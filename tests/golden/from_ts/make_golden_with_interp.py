@@ -36,8 +36,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 import tsinterp as T  # noqa: E402
-from tests.fixtures import gaussian, sincos_dataset  # noqa: E402
-from tests.golden.make_golden import CASES  # noqa: E402
+from tests.golden.make_golden import CASES, case_inputs  # noqa: E402
 
 OVERSAMPLE = 3
 
@@ -48,14 +47,6 @@ def f64bits(x):
 
 def f32bits(x):
     return struct.unpack("<I", struct.pack("<f", float(x)))[0]
-
-
-def inputs(name):
-    n, dim, sim, qb, k, nq, lam, iters, data = CASES[name]
-    if data == "gauss":
-        seed = 20260101 + sum(map(ord, name))
-        return gaussian(n, dim, seed), gaussian(nq, dim, seed + 100)
-    return sincos_dataset(dim, n, nq)
 
 
 def load_reference(ref_root, console):
@@ -71,7 +62,7 @@ def load_reference(ref_root, console):
 
 def run_case(name, ref_root):
     n, dim, sim, qb, k, nq, lam, iters, data = CASES[name]
-    base, queries = inputs(name)
+    base, queries = case_inputs(name)
     console = []
     I, ex, sel, files = load_reference(ref_root, console)
     t0 = time.time()
@@ -102,12 +93,15 @@ def run_case(name, ref_root):
         by_index = [None] * n
         for r in every:
             by_index[int(r["index"])] = f32bits(r["score"])
+        beyond = I.call(I.get(fmt, "searchNearestNeighbors"), fmt, [qa, qv, float(n + 5)]) if n <= 200 else None   # k > n
         once = I.call(I.get(fmt, "quantizeQueryVector"), fmt, [qa, centroid])
         qc = once["queryCorrections"]
         over = I.call(sel["getOversampledTopKWithHeap"], args=[qa, qv, rows, float(k), float(OVERSAMPLE), fmt])
         out["queries"].append({
             "top_index": [int(r["index"]) for r in res], "top_score_bits": [f32bits(r["score"]) for r in res],
             "all_score_bits": by_index,
+            **({"k_beyond_n": {"k": n + 5, "index": [int(r["index"]) for r in beyond],
+                               "score_bits": [f32bits(r["score"]) for r in beyond]}} if beyond is not None else {}),
             "quantize_query_once": {"codes": [int(x) for x in once["quantizedQuery"].a],
                                     "corrections_bits": [f64bits(qc[f]) for f in ("lowerInterval", "upperInterval", "additionalCorrection",
                                                                                   "quantizedComponentSum")]},

@@ -15,7 +15,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import oracle as O  # noqa: E402
-from tests.fixtures import gaussian, sincos_dataset  # noqa: E402
+from tests.fixtures import edge_dataset, gaussian, sincos_dataset  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -26,18 +26,29 @@ CASES = {
     "euclid_2000x100": (2000, 100, "EUCLIDEAN", 4, 10, 3, 0.1, 5, "gauss"),           # dim % 8 != 0
     "cosine_1bit_query_500x64": (500, 64, "COSINE", 1, 10, 3, 0.1, 5, "gauss"),
     "sincos_recall_100x128": (100, 128, "COSINE", 4, 10, 10, 0.001, 20, "sincos"),    # tests/recall.test.ts fixture
+    # degenerate rows / exact ties / zero query (tests/fixtures.py:edge_dataset) — fixtures from the reference source only
+    # (tests/golden/from_ts/*.ts.json); no .npz is generated for them
+    "edge_cosine_60x40": (60, 40, "COSINE", 4, 8, 3, 0.1, 5, "edge"),
+    "edge_euclid_60x40": (60, 40, "EUCLIDEAN", 4, 8, 3, 0.1, 5, "edge"),
+    "edge_mip_1bit_query_60x40": (60, 40, "MAXIMUM_INNER_PRODUCT", 1, 8, 3, 0.1, 5, "edge"),
 }
+
+
+def case_inputs(name):
+    """-> (base f32[n, dim], queries f32[nq, dim]) of a case; every generator and test goes through here."""
+    n, dim, sim, qb, k, nq, lam, iters, data = CASES[name]
+    seed = 20260101 + sum(map(ord, name))
+    if data == "gauss":
+        return gaussian(n, dim, seed), gaussian(nq, dim, seed + 100)
+    if data == "edge":
+        return edge_dataset(n, dim, nq, seed)
+    return sincos_dataset(dim, n, nq)
 
 
 def make(name):
     n, dim, sim, qb, k, nq, lam, iters, data = CASES[name]
-    if data == "gauss":
-        seed = 20260101 + sum(map(ord, name))
-        base, queries = gaussian(n, dim, seed), gaussian(nq, dim, seed + 100)
-        gen = {"seed": seed}
-    else:
-        base, queries = sincos_dataset(dim, n, nq)
-        gen = {"seed": -1}
+    base, queries = case_inputs(name)
+    gen = {"seed": 20260101 + sum(map(ord, name)) if data != "sincos" else -1}
     idx = O.quantize_vectors(base, sim=sim, index_bits=1, lam=lam, iters=iters)
     out = {"n": n, "dim": dim, "sim": sim, "query_bits": qb, "k": k, "lam": lam, "iters": iters, **gen,
            "centroid": idx.centroid, "packed_head": idx.packed[:16], "corr_head": idx.corr[:16],
@@ -58,4 +69,5 @@ def make(name):
 
 if __name__ == "__main__":
     for nm in CASES:
-        make(nm)
+        if CASES[nm][-1] != "edge":
+            make(nm)

@@ -19,19 +19,11 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from tests.fixtures import gaussian, sincos_dataset
-from tests.golden.make_golden import CASES
+from tests.fixtures import gaussian
+from tests.golden.make_golden import CASES, case_inputs
 
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "from_ts")
 FIXTURES = sorted(glob.glob(os.path.join(HERE, "*.ts.json")))
-
-
-def _inputs(name):
-    n, dim, sim, qb, k, nq, lam, iters, data = CASES[name]
-    if data == "gauss":
-        seed = 20260101 + sum(map(ord, name))
-        return gaussian(n, dim, seed), gaussian(nq, dim, seed + 100)
-    return sincos_dataset(dim, n, nq)
 
 
 def _f64_from_hex(rows):
@@ -43,7 +35,7 @@ def _u64(a):
 
 
 def test_fixtures_from_the_reference_source_exist():
-    assert len(FIXTURES) >= 4, "run tests/golden/from_ts/make_golden_with_interp.py (needs /root/reference)"
+    assert len(FIXTURES) >= 8, "run tests/golden/from_ts/make_golden_with_interp.py (needs /root/reference)"
     sims = {json.load(open(p))["sim"] for p in FIXTURES}
     assert sims == {"EUCLIDEAN", "COSINE", "MAXIMUM_INNER_PRODUCT"}
 
@@ -55,7 +47,7 @@ def test_oracle_equals_the_typescript_reference(path):
     n, dim, sim, qb, k, nq, lam, iters, data = CASES[name]
     assert (d["n"], d["dim"], d["sim"], d["queryBits"], d["k"]) == (n, dim, sim, qb, k)
     assert not d.get("console"), "the reference logged something (a fallback ran?)"
-    base, queries = _inputs(name)
+    base, queries = case_inputs(name)
     idx = O.quantize_vectors(base, sim=sim, index_bits=1, lam=lam, iters=iters)
     # quantizeVectors: centroid, correctives, codes
     assert idx.centroid.view(np.uint32).tolist() == d["centroid_bits"]
@@ -73,6 +65,9 @@ def test_oracle_equals_the_typescript_reference(path):
         ci, cs = O.search_nearest_neighbors(q, idx, k, query_bits=qb, lam=lam, iters=iters, mode="canonical")
         if len(alls) > k and np.sort(alls)[::-1][k - 1] != np.sort(alls)[::-1][k]:
             assert sorted(ci.tolist()) == sorted(ref["top_index"])
+        if "k_beyond_n" in ref:               # k > vectorCount: min(k, n) results, the whole index in heap order
+            bi, bs = O.search_nearest_neighbors(q, idx, ref["k_beyond_n"]["k"], query_bits=qb, lam=lam, iters=iters, mode="heap")
+            assert bi.tolist() == ref["k_beyond_n"]["index"] and bs.view(np.uint32).tolist() == ref["k_beyond_n"]["score_bits"]
         if "quantize_query_once" in ref:      # quantizeQueryVector(query, centroid) as a direct member call
             codes, corr = O.quantize_query_vector_once(q, idx.centroid, sim, qb, lam, iters)
             assert codes.tolist() == ref["quantize_query_once"]["codes"]
