@@ -111,3 +111,43 @@ def test_reference_source_interpreted_live_equals_oracle(sim, qb, n, dim):
         assert [int(r["index"]) for r in res] == hi.tolist()
         assert np.array([r["score"] for r in res], np.float32).view(np.uint32).tolist() == hs.view(np.uint32).tolist()
     assert not console
+
+
+class _OracleBackedFormat:
+    """The host interface's shape (quantizeVectors / searchBatch / debugScores / exportAll), answered by the oracle in
+    CANONICAL order — a stand-in for the GPU format, so that the GPU-side checker of the reference fixtures
+    (tests/test_zz_gpu_vs_reference_fixtures.py:check_against_fixture) is itself exercised on the CPU."""
+
+    def __init__(self, sim, qb, lam, iters):
+        self.sim, self.qb, self.lam, self.iters = sim, qb, lam, iters
+
+    def quantizeVectors(self, base):
+        idx = O.quantize_vectors(base, sim=self.sim, index_bits=1, lam=self.lam, iters=self.iters)
+
+        class QV:
+            def getCentroid(self_inner):
+                return idx.centroid
+
+            def exportAll(self_inner):
+                return idx.packed, idx.corr
+        qv = QV()
+        qv.idx = idx
+        return {"quantizedVectors": qv}
+
+    def searchBatch(self, queries, qv, k):
+        out = [O.search_nearest_neighbors(q, qv.idx, k, query_bits=self.qb, lam=self.lam, iters=self.iters, mode="canonical")
+               for q in queries]
+        return np.stack([o[0] for o in out]), np.stack([o[1] for o in out])
+
+    def debugScores(self, q, qv):
+        return O.search_nearest_neighbors(q, qv.idx, 1, query_bits=self.qb, lam=self.lam, iters=self.iters, mode="canonical",
+                                          want_all=True)[2]
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[:-len(".ts.json")] for p in FIXTURES])
+def test_gpu_side_checker_dry_run_with_the_oracle(path):
+    from tests.test_zz_gpu_vs_reference_fixtures import check_against_fixture
+    d = json.load(open(path))
+    name = os.path.basename(path)[:-len(".ts.json")]
+    n, dim, sim, qb, k, nq, lam, iters, data = CASES[name]
+    check_against_fixture(_OracleBackedFormat(sim, qb, lam, iters), d, name)
