@@ -21,7 +21,9 @@
 //   * the four exact known-answer tests in rust-wasm/src/*.rs,
 //   * the deterministic sin/cos recall fixtures + thresholds of tests/recall*.ts,
 //   * the behavioural properties the reference tests assert (k=0, k>N, ordering...).
-// The indexBits = 2 EXTENSION below has no reference behaviour to be pinned to ("parity unpinned by construction").
+// indexBits = 2: the index BUILD is pinned the same way (tests/golden/from_ts/index_bits_2.behaviour.json); the SEARCH
+// extension below has no reference behaviour to be pinned to — executed, the reference throws for queryBits = 8 and
+// falls back to a per-vector formula for queryBits = 4 that this extension deliberately does not follow.
 //
 // Build: g++ -O2 -std=c++17 -ffp-contract=off -fno-fast-math (see oracle/Makefile).
 // -ffp-contract=off is REQUIRED: JS never fuses a*b+c.

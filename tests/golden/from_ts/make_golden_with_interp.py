@@ -108,9 +108,10 @@ def run_case(name, ref_root):
             "oversampled_heap": {"factor": OVERSAMPLE, "index": [int(c["index"]) for c in over],
                                  "quantized_score_bits": [f32bits(c["quantizedScore"]) for c in over],
                                  "true_score_bits": [f64bits(c["trueScore"]) for c in over]}})
-    m = min(nq, n)   # the member wants as many original vectors as queries (it re-quantises them): the first nq rows
-    acc = I.call(I.get(fmt, "computeQuantizationAccuracy"), fmt, [rows[:m], [I.float32(q.tolist()) for q in queries]])
-    out["accuracy"] = {"rows": m, **{f: f64bits(acc[f]) for f in ("meanError", "maxError", "minError", "stdError", "correlation")}}
+    if qb in (1, 4):     # (the single-vector scorer behind this member knows 1- and 4-bit queries only: it throws otherwise)
+        m = min(nq, n)   # the member wants as many original vectors as queries (it re-quantises them): the first nq rows
+        acc = I.call(I.get(fmt, "computeQuantizationAccuracy"), fmt, [rows[:m], [I.float32(q.tolist()) for q in queries]])
+        out["accuracy"] = {"rows": m, **{f: f64bits(acc[f]) for f in ("meanError", "maxError", "minError", "stdError", "correlation")}}
     out["console"] = console          # the reference logs nothing on this path; a '批量计算失败' warning here would mean a fallback ran
     if any("失败" in line for line in console):
         raise RuntimeError(f"{name}: the reference fell back from its batch path: {console[:3]}")
@@ -120,10 +121,56 @@ def run_case(name, ref_root):
           flush=True)
 
 
+def run_index_bits_2(ref_root):
+    """What the reference DOES for indexBits = 2 (BASELINE configs[4] names queryBits = 8 / indexBits = 2), observed by
+    executing it: the index build works (2-bit codes, one per byte, + correctives) and is recorded here for the oracle
+    to reproduce; searchNearestNeighbors fails inside the batch path (createDirectPackedBuffer: offset out of bounds),
+    logs the fallback warning and goes through the per-vector scorer — which THROWS for queryBits = 8 and, for
+    queryBits = 4, returns scores of its own formula (recorded as an observation; this repository's extension follows
+    SURVEY §8c's generalisation instead and does not reproduce them)."""
+    from tests.fixtures import gaussian
+    n, dim = 40, 32
+    base, queries = gaussian(n, dim, 5), gaussian(2, dim, 6)
+    out = {"n": n, "dim": dim, "seed_base": 5, "seed_queries": 6, "lambda": 0.1, "iters": 5, "index_build": {}, "search": {}}
+    for sim in ("EUCLIDEAN", "COSINE", "MAXIMUM_INNER_PRODUCT"):
+        for qb in (8, 4):
+            console = []
+            I, ex, sel, files = load_reference(ref_root, console)
+            out["reference_sha256"] = files
+            fmt = I.call(ex["createBinaryQuantizationFormat"], args=[
+                {"queryBits": float(qb), "indexBits": 2.0, "quantizer": {"similarityFunction": sim, "lambda": 0.1, "iters": 5.0}}])
+            rows = [I.float32(r.tolist()) for r in base]
+            qv = I.call(I.get(fmt, "quantizeVectors"), fmt, [rows])["quantizedVectors"]
+            if qb == 8:
+                corr, codes = [], []
+                for i in range(n):
+                    c = I.call(I.get(qv, "getCorrectiveTerms"), qv, [float(i)])
+                    corr.append([f64bits(c[f]) for f in ("lowerInterval", "upperInterval", "additionalCorrection", "quantizedComponentSum")])
+                    codes.append([int(x) for x in I.call(I.get(qv, "vectorValue"), qv, [float(i)]).a])
+                out["index_build"][sim] = {"centroid_bits": [f32bits(x) for x in I.call(I.get(qv, "getCentroid"), qv, []).a],
+                                           "corrections_bits": corr, "codes": codes}
+            try:
+                res = I.call(I.get(fmt, "searchNearestNeighbors"), fmt, [I.float32(queries[0].tolist()), qv, float(n)])
+                by_index = [None] * n
+                for r in res:
+                    by_index[int(r["index"])] = f32bits(r["score"])
+                observed = {"threw": None, "all_score_bits_of_the_fallback": by_index}
+            except T.JSThrow as e:
+                observed = {"threw": str(e)}
+            observed["console"] = console
+            out["search"][f"{sim} queryBits={qb}"] = observed
+    with open(os.path.join(HERE, "index_bits_2.behaviour.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"), ensure_ascii=False)
+    print("wrote index_bits_2.behaviour.json:", {k: (v["threw"] or "fallback scores") for k, v in out["search"].items()}, flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
-    ap.add_argument("cases", nargs="*", default=list(CASES))
+    ap.add_argument("cases", nargs="*", default=list(CASES) + ["index_bits_2"])
     a = ap.parse_args()
     for nm in a.cases:
-        run_case(nm, a.reference)
+        if nm == "index_bits_2":
+            run_index_bits_2(a.reference)
+        else:
+            run_case(nm, a.reference)

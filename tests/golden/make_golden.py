@@ -31,7 +31,13 @@ CASES = {
     "edge_cosine_60x40": (60, 40, "COSINE", 4, 8, 3, 0.1, 5, "edge"),
     "edge_euclid_60x40": (60, 40, "EUCLIDEAN", 4, 8, 3, 0.1, 5, "edge"),
     "edge_mip_1bit_query_60x40": (60, 40, "MAXIMUM_INNER_PRODUCT", 1, 8, 3, 0.1, 5, "edge"),
+    # other query widths on a 1-bit index (the reference's batch path takes its "4-bit" branch for every width != 1)
+    "qb8_cosine_60x40": (60, 40, "COSINE", 8, 8, 2, 0.1, 5, "gauss"),
+    "qb2_euclid_60x40": (60, 40, "EUCLIDEAN", 2, 8, 2, 0.1, 5, "gauss"),
+    "qb7_mip_50x48": (50, 48, "MAXIMUM_INNER_PRODUCT", 7, 8, 2, 0.1, 5, "gauss"),
 }
+FROM_TS_ONLY = {"edge_cosine_60x40", "edge_euclid_60x40", "edge_mip_1bit_query_60x40", "qb8_cosine_60x40", "qb2_euclid_60x40",
+                "qb7_mip_50x48"}      # fixtures from the reference source only: no .npz
 
 
 def case_inputs(name):
@@ -69,5 +75,5 @@ def make(name):
 
 if __name__ == "__main__":
     for nm in CASES:
-        if CASES[nm][-1] != "edge":
+        if nm not in FROM_TS_ONLY:
             make(nm)

@@ -35,7 +35,7 @@ def _u64(a):
 
 
 def test_fixtures_from_the_reference_source_exist():
-    assert len(FIXTURES) >= 8, "run tests/golden/from_ts/make_golden_with_interp.py (needs /root/reference)"
+    assert len(FIXTURES) >= 11, "run tests/golden/from_ts/make_golden_with_interp.py (needs /root/reference)"
     sims = {json.load(open(p))["sim"] for p in FIXTURES}
     assert sims == {"EUCLIDEAN", "COSINE", "MAXIMUM_INNER_PRODUCT"}
 
@@ -151,3 +151,28 @@ def test_gpu_side_checker_dry_run_with_the_oracle(path):
     name = os.path.basename(path)[:-len(".ts.json")]
     n, dim, sim, qb, k, nq, lam, iters, data = CASES[name]
     check_against_fixture(_OracleBackedFormat(sim, qb, lam, iters), d, name)
+
+
+def test_index_bits_2_build_equals_the_reference_and_its_search_behaviour_is_recorded():
+    """indexBits = 2 (BASELINE configs[4] is queryBits = 8 / indexBits = 2).  Executed, the reference BUILDS such an index
+    (2-bit codes, one per byte, + correctives) — the oracle reproduces that bit for bit — but cannot search it: the batch
+    path fails, the per-vector fallback throws for queryBits = 8 (the recorded message) and, for queryBits = 4, scores
+    with a formula that ignores the number of levels.  This repository's search over 2-bit indexes is therefore an
+    EXTENSION (SURVEY §8c's generalisation, oracle/bbq_oracle.cpp:score_ext), and deliberately not that fallback."""
+    d = json.load(open(os.path.join(HERE, "index_bits_2.behaviour.json")))
+    base, queries = gaussian(d["n"], d["dim"], d["seed_base"]), gaussian(2, d["dim"], d["seed_queries"])
+    for sim, ref in d["index_build"].items():
+        idx = O.quantize_vectors(base, sim=sim, index_bits=2, lam=d["lambda"], iters=d["iters"])
+        assert idx.centroid.view(np.uint32).tolist() == ref["centroid_bits"]
+        assert np.array_equal(_u64(idx.corr), _u64(_f64_from_hex(ref["corrections_bits"])))
+        assert idx.unpacked.tolist() == ref["codes"]
+    for key, obs in d["search"].items():
+        assert any("批量计算失败" in line for line in obs["console"])           # the batch path failed in every case
+        if key.endswith("queryBits=8"):
+            assert obs["threw"] == "Error: 不支持的查询位数: 8，只支持1位和4位"
+        else:
+            assert obs["threw"] is None
+            sim = key.split()[0]
+            idx = O.quantize_vectors(base, sim=sim, index_bits=2, lam=d["lambda"], iters=d["iters"])
+            _, _, ext, _ = O.search_nearest_neighbors(queries[0], idx, 5, query_bits=4, mode="heap", want_all=True)
+            assert ext.view(np.uint32).tolist() != obs["all_score_bits_of_the_fallback"]   # the extension is NOT the fallback
