@@ -1527,8 +1527,9 @@ CONT = ("c",)
 
 
 class Interp:
-    def __init__(self, log=None, stub_modules=()):
+    def __init__(self, log=None, stub_modules=(), virtual_modules=None):
         self.modules = {}
+        self.virtual_modules = dict(virtual_modules or {})   # bare specifier -> exports dict provided by the host (e.g. 'vitest')
         self.stub_modules = tuple(stub_modules)   # path suffixes loaded as EMPTY modules (e.g. the async WASM bridge)
         self.stubbed = []
         self.log = log if log is not None else (lambda *a: None)
@@ -1538,6 +1539,8 @@ class Interp:
 
     # -- host entry points -------------------------------------------------------------------------------------
     def load(self, path):
+        if path in self.modules:
+            return self.modules[path]
         path = os.path.realpath(path)
         if path in self.modules:
             return self.modules[path]
@@ -1554,6 +1557,10 @@ class Interp:
         return exports
 
     def resolve(self, base, spec):
+        if spec in self.virtual_modules:
+            key = "virtual:" + spec
+            self.modules[key] = self.virtual_modules[spec]
+            return key
         if not spec.startswith("."):
             raise ImportError(f"{base}: bare module specifier {spec!r} is not supported")
         p = os.path.normpath(os.path.join(os.path.dirname(base), spec))

@@ -177,3 +177,16 @@ def test_modules_and_errors(tmp_path):
                 "class A {} class B extends A {} export function main() {}"):
         with pytest.raises(SyntaxError):
             run(tmp_path, bad)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tests"), reason="the reference is not on this box")
+@pytest.mark.parametrize("name,tests", [("utils.test.ts", 27), ("computeCentroid-correctness.test.ts", 2), ("recall.test.ts", 8)])
+def test_reference_own_test_files_pass_under_the_interpreter(name, tests):
+    """The reference's OWN vitest files, executed against the reference's own sources by the interpreter (a minimal
+    describe / it / expect in vitest_shim.py; Math.random seeded): every test in them passes.  (The performance-sized
+    files — batch-*.test.ts, simple-quantized-query.test.ts, recall-all-dimensions.test.ts: thousands of 1024-d vectors —
+    are not run: an interpreter in Python is the wrong tool for those.)"""
+    import vitest_shim as V
+    passed, failed, assertions, console = V.run_test_file(os.path.join("/root/reference/tests", name))
+    assert not failed, failed[:3]
+    assert len(passed) == tests and assertions > 0
