@@ -245,9 +245,9 @@ def run_reference(args, w, rank):
     line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "int32 dot + f64 epilogue", "data": "synthetic",
-            "config": {"workload": w["name"], "note": "CPU restatement of the reference TypeScript path (oracle port); "
-                       "the TypeScript reference cannot run here (no node/tsc on the build image or the GPU box: "
-                       "profiles/r02_js_runtime_probe.txt)"},
+            "config": {"workload": w["name"], "note": "CPU restatement of the reference TypeScript path (oracle port, C++; pinned bit "
+                       "for bit to the reference's own source text by tests/golden/from_ts); the TypeScript reference itself "
+                       "cannot be timed here (no node/tsc on the build image or the GPU box: profiles/r02_js_runtime_probe.txt)"},
             "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -537,7 +537,8 @@ def run_gpu(args, w, rank, world, local_rank):
                    "sample": f"{done} of {nq} queries over {sample_rows} of the {n} rows of the GPU-built index, 1 thread, "
                              f"{dt:.1f}s" + (f", per-query time scaled x{scale:.0f} to the full corpus (extrapolated)"
                                              if scale != 1 else "")
-                             + " (oracle = C++ restatement of the reference TypeScript path, not V8)"}
+                             + " (oracle = C++ restatement of the reference TypeScript path, bit-identical to the reference's "
+                               "own source on the fixtures of tests/golden/from_ts; not V8)"}
         if world == 1:
             parity = verify_timed_run(w, m, packed, corr, res, done, args)
 
