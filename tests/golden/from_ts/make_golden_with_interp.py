@@ -164,13 +164,71 @@ def run_index_bits_2(ref_root):
     print("wrote index_bits_2.behaviour.json:", {k: (v["threw"] or "fallback scores") for k, v in out["search"].items()}, flush=True)
 
 
+def run_errors(ref_root):
+    """Which Error the reference throws for invalid inputs, observed by executing it (message text, and for NaN / Infinity
+    the position it names: under COSINE the vector is normalised before the check, so a NaN anywhere is reported at
+    position 0 and an Infinity turns into a NaN at its own position)."""
+    import numpy as np
+    from tests.fixtures import gaussian
+    rows, qs = gaussian(300, 64, 11), gaussian(6, 64, 12)
+    out = {"rows_seed": 11, "queries_seed": 12, "n": 300, "dim": 64, "cases": []}
+
+    def attempt(label, spec, fn):
+        try:
+            fn()
+            msg = None
+        except T.JSThrow as e:
+            v = e.value
+            msg = T.to_str(I.get(v, "message")) if isinstance(v, T.JSObj) else T.to_str(v)
+        out["cases"].append({"label": label, **spec, "message": msg})
+
+    for sim in ("EUCLIDEAN", "COSINE", "MAXIMUM_INNER_PRODUCT"):
+        I, ex, sel, files = load_reference(ref_root, [])
+        out["reference_sha256"] = files
+        fmt = I.call(ex["createBinaryQuantizationFormat"], args=[
+            {"queryBits": 4.0, "indexBits": 1.0, "quantizer": {"similarityFunction": sim, "lambda": 0.1, "iters": 5.0}}])
+        quantize, search = I.get(fmt, "quantizeVectors"), I.get(fmt, "searchNearestNeighbors")
+        qv = I.call(quantize, fmt, [[I.float32(r.tolist()) for r in rows]])["quantizedVectors"]
+        for label, edits in (("query NaN@30 + Infinity@7", {30: np.nan, 7: np.inf}), ("query -Infinity@12", {12: -np.inf}),
+                             ("query NaN@5", {5: np.nan})):
+            q = qs[2].copy()
+            for pos, val in edits.items():
+                q[pos] = val
+            attempt(label, {"sim": sim, "what": "search", "edits": {str(k): str(v) for k, v in edits.items()}},
+                    lambda q=q: I.call(search, fmt, [I.float32(q.tolist()), qv, 5.0]))
+        for label, (r, pos, val) in (("build NaN row 3 @9", (3, 9, np.nan)), ("build Infinity row 2 @4", (2, 4, np.inf))):
+            b = rows[:5].copy()
+            b[r, pos] = val
+            attempt(label, {"sim": sim, "what": "build", "row": r, "pos": pos, "value": str(val)},
+                    lambda b=b: I.call(quantize, fmt, [[I.float32(x.tolist()) for x in b]]))
+        if sim == "COSINE":
+            q0 = I.float32(qs[0].tolist())
+            attempt("k = -1", {"sim": sim, "what": "search"}, lambda: I.call(search, fmt, [q0, qv, -1.0]))
+            attempt("k = 0 (returns [])", {"sim": sim, "what": "search"}, lambda: I.call(search, fmt, [q0, qv, 0.0]))
+            attempt("dimension mismatch", {"sim": sim, "what": "search"}, lambda: I.call(search, fmt, [I.float32(qs[0][:10].tolist()), qv, 3.0]))
+            attempt("null query", {"sim": sim, "what": "search"}, lambda: I.call(search, fmt, [None, qv, 3.0]))
+            attempt("null targets", {"sim": sim, "what": "search"}, lambda: I.call(search, fmt, [q0, None, 3.0]))
+            attempt("empty vector set", {"sim": sim, "what": "build"}, lambda: I.call(quantize, fmt, [[]]))
+            attempt("ragged rows (row 1 has 10 of 64 dims)", {"sim": sim, "what": "build"},
+                    lambda: I.call(quantize, fmt, [[I.float32(rows[0].tolist()), I.float32(rows[1][:10].tolist())]]))
+            attempt("queryBits = 9", {"sim": sim, "what": "create"}, lambda: I.call(ex["createBinaryQuantizationFormat"], args=[
+                {"queryBits": 9.0, "quantizer": {"similarityFunction": "COSINE"}}]))
+            attempt("indexBits = 0", {"sim": sim, "what": "create"}, lambda: I.call(ex["createBinaryQuantizationFormat"], args=[
+                {"indexBits": 0.0, "quantizer": {"similarityFunction": "COSINE"}}]))
+    with open(os.path.join(HERE, "errors.behaviour.json"), "w") as f:
+        json.dump(out, f, indent=1, ensure_ascii=False)
+    print("wrote errors.behaviour.json:", len(out["cases"]), "cases", flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
-    ap.add_argument("cases", nargs="*", default=list(CASES) + ["index_bits_2"])
+    ap.add_argument("cases", nargs="*", default=list(CASES) + ["index_bits_2", "errors"])
     a = ap.parse_args()
     for nm in a.cases:
         if nm == "index_bits_2":
             run_index_bits_2(a.reference)
+        elif nm == "errors":
+            run_errors(a.reference)
         else:
             run_case(nm, a.reference)

@@ -176,3 +176,30 @@ def test_index_bits_2_build_equals_the_reference_and_its_search_behaviour_is_rec
             idx = O.quantize_vectors(base, sim=sim, index_bits=2, lam=d["lambda"], iters=d["iters"])
             _, _, ext, _ = O.search_nearest_neighbors(queries[0], idx, 5, query_bits=4, mode="heap", want_all=True)
             assert ext.view(np.uint32).tolist() != obs["all_score_bits_of_the_fallback"]   # the extension is NOT the fallback
+
+
+def test_host_messages_equal_the_executed_reference():
+    """errors.behaviour.json holds the messages the reference throws (observed by executing it).  The parts of the host
+    interface that need no GPU — the message templates the C-ABI status codes are mapped to, and the checks made in
+    Python before any call — produce exactly those strings.  (The GPU-side half, which status and position the library
+    reports for NaN / Infinity under each similarity function, is tests/test_zz_gpu_vs_reference_fixtures.py.)"""
+    import importlib
+    import bbq_b200  # noqa: F401  (registers the package under its importable name)
+    fm = importlib.import_module("better_binary_quantization_b200.host.format")
+    d = json.load(open(os.path.join(HERE, "errors.behaviour.json")))
+    by = {(c["sim"], c["label"]): c["message"] for c in d["cases"]}
+    assert fm._message(5, 3, 9, "build") == by[("EUCLIDEAN", "build NaN row 3 @9")]
+    assert fm._message(6, 2, 4, "build") == by[("EUCLIDEAN", "build Infinity row 2 @4")]
+    assert fm._message(5, 3, 0, "build") == by[("COSINE", "build NaN row 3 @9")]          # normalised first: NaN everywhere
+    assert fm._message(5, 2, 4, "build") == by[("COSINE", "build Infinity row 2 @4")]     # Infinity / Infinity = NaN, in place
+    assert fm._message(6, -1, 7, "search") == by[("EUCLIDEAN", "query NaN@30 + Infinity@7")]
+    assert fm._message(6, -1, 12, "search") == by[("MAXIMUM_INNER_PRODUCT", "query -Infinity@12")]
+    assert fm._message(5, -1, 5, "search") == by[("EUCLIDEAN", "query NaN@5")]
+    assert fm._message(5, -1, 0, "search") == by[("COSINE", "query -Infinity@12")]
+    assert fm._message(7, -1, -1, "search") == by[("COSINE", "k = -1")]
+    assert fm._message(3, -1, -1, "build") == by[("COSINE", "empty vector set")]
+    assert fm._message(4, -1, -1, "search") == by[("COSINE", "dimension mismatch")]
+    assert fm._message(1, -1, -1, "") == by[("COSINE", "queryBits = 9")] and fm._message(2, -1, -1, "") == by[("COSINE", "indexBits = 0")]
+    with pytest.raises(fm.BbqError) as e:
+        fm._as_matrix([np.zeros(64, np.float32), np.zeros(10, np.float32)])
+    assert str(e.value) == by[("COSINE", "ragged rows (row 1 has 10 of 64 dims)")]

@@ -59,3 +59,60 @@ def test_gpu_equals_the_typescript_reference(bbq, path):
     name = os.path.basename(path)[:-len(".ts.json")]
     n, dim, sim, qb, k, nq, lam, iters, data = CASES[name]
     check_against_fixture(make_format(bbq, sim, qb=qb, lam=lam, iters=iters), d, name)
+
+
+def test_error_behaviour_equals_the_executed_reference(bbq):
+    """tests/golden/from_ts/errors.behaviour.json: which Error the reference throws for invalid inputs (message text and,
+    for NaN / Infinity, the position it names under each similarity function), observed by executing its source.  The
+    host interface over the C ABI must raise the same messages."""
+    from tests.fixtures import gaussian
+    d = json.load(open(os.path.join(HERE, "errors.behaviour.json")))
+    rows, qs = gaussian(d["n"], d["dim"], d["rows_seed"]), gaussian(6, d["dim"], d["queries_seed"])
+    formats = {}
+
+    def setup(sim):
+        if sim not in formats:
+            fmt = make_format(bbq, sim)
+            formats[sim] = (fmt, fmt.quantizeVectors(rows)["quantizedVectors"])
+        return formats[sim]
+
+    def run_case(c):
+        sim, label = c["sim"], c["label"]
+        fmt, qv = setup(sim)
+        if c["what"] == "search" and "edits" in c:
+            q = qs[2].copy()
+            for pos, val in c["edits"].items():
+                q[int(pos)] = float(val)
+            return fmt.searchNearestNeighbors(q, qv, 5)
+        if c["what"] == "build" and "row" in c:
+            b = rows[:5].copy()
+            b[c["row"], c["pos"]] = float(c["value"])
+            return fmt.quantizeVectors(b)
+        if label == "k = -1":
+            return fmt.searchNearestNeighbors(qs[0], qv, -1)
+        if label.startswith("k = 0"):
+            assert fmt.searchNearestNeighbors(qs[0], qv, 0) == []
+            return None
+        if label == "dimension mismatch":
+            return fmt.searchNearestNeighbors(qs[0][:10], qv, 3)
+        if label == "null query":
+            return fmt.searchNearestNeighbors(None, qv, 3)
+        if label == "null targets":
+            return fmt.searchNearestNeighbors(qs[0], None, 3)
+        if label == "empty vector set":
+            return fmt.quantizeVectors([])
+        if label.startswith("ragged rows"):
+            return fmt.quantizeVectors([rows[0], rows[1][:10]])
+        if label == "queryBits = 9":
+            return bbq.createBinaryQuantizationFormat({"queryBits": 9, "quantizer": {"similarityFunction": "COSINE"}})
+        if label == "indexBits = 0":
+            return bbq.createBinaryQuantizationFormat({"indexBits": 0, "quantizer": {"similarityFunction": "COSINE"}})
+        raise AssertionError(f"unknown case {label}")
+
+    for c in d["cases"]:
+        if c["message"] is None:
+            run_case(c)
+            continue
+        with pytest.raises(bbq.BbqError) as e:
+            run_case(c)
+        assert str(e.value) == c["message"], (c["sim"], c["label"])
