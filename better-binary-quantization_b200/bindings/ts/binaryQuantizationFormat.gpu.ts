@@ -21,6 +21,7 @@ import type {
 } from './types';
 import { VectorSimilarityFunction } from './types';
 import { QUERY_BITS, INDEX_BITS } from './constants';
+import type { OptimizedScalarQuantizer } from './optimizedScalarQuantizer';
 import { BinaryQuantizationFormat as ReferenceBinaryQuantizationFormat } from './binaryQuantizationFormat.cpu';
 import { toReferenceError } from './errors';
 
@@ -114,14 +115,15 @@ export class BinaryQuantizationFormat extends ReferenceBinaryQuantizationFormat 
   }
 
   public override quantizeVectors(vectors: Float32Array[]): {              // :165-263
-    quantizedVectors: BinarizedByteVectorValues; queryQuantizer: BinaryQuantizationFormat;
+    quantizedVectors: BinarizedByteVectorValues; queryQuantizer: OptimizedScalarQuantizer;
   } {
     if (vectors.length === 0) throw new Error('向量集合不能为空');
     const dim = vectors[0]!.length;
     const flat = flatten(vectors, dim);
     try {
       const handle = addon.build(this.ctx, flat, vectors.length, dim, null);
-      return { quantizedVectors: new DeviceBinarizedByteVectorValues(handle), queryQuantizer: this };
+      // :261 hands out `this.quantizer` (an OptimizedScalarQuantizer): the inherited helper object, as getQuantizer() does
+      return { quantizedVectors: new DeviceBinarizedByteVectorValues(handle), queryQuantizer: this.getQuantizer() };
     } catch (e) { throw toReferenceError(e, 'build'); }
   }
 

@@ -881,8 +881,8 @@ static int quantize_rows(bbq_ctx* c, const float* d_queries, int nq, int dim, in
   } else {
     // throughput form: one thread per query over the transposed scratch (same code as the index build)
     if (bad != nullptr)
-      LAUNCH(c, k_validate_queries, (nq + 3) / 4, 128, 0, st, d_q, nq, dim, c->cfg.similarity == BBQ_SIM_COSINE ? 1 : 0, bad,
-             q_base);
+      LAUNCH(c, k_validate_queries, (nq + 3) / 4, 128, 0, st, d_q, nq, dim, c->cfg.similarity == BBQ_SIM_COSINE ? 1 : 0, ntimes,
+             bad, q_base);
     float* T = c->qT.as<float>();
     dim3 grid((nq + 31) / 32, (dim + 31) / 32), block(32, 8);
     LAUNCH(c, k_transpose, grid, block, 0, st, d_queries, (int64_t)nq, dim, T, (int64_t)nq);

@@ -371,17 +371,19 @@ struct CtaTeam {
 // (src/optimizedScalarQuantizer.ts:138-148, after the COSINE normalisation of src/binaryQuantizationFormat.ts:337).
 // The team finds the query's first NaN / first Infinity while it stages the vector.  COSINE: a NaN anywhere makes the
 // normalised vector all-NaN (reported at position 0); an Infinity makes the norm infinite, so the Infinity components
-// become NaN (reported as NaN at the first of them).  Otherwise the first non-finite component is reported as NaN or
-// Infinity.  The lowest offending query wins: bad[0] = min over queries of (query << 34 | status << 32 | position),
+// become NaN — after ONE normalisation (quantizeQueryVector called directly, :271-299) that NaN sits at the position of
+// the first Infinity; on the SEARCH path the query is normalised TWICE (:337, then :279), the second norm is NaN and
+// everything is NaN: position 0.  (Observed by executing the reference: tests/golden/from_ts/errors.behaviour.json.)
+// Otherwise the first non-finite component is reported as NaN or Infinity.  The lowest offending query wins: bad[0] = min over queries of (query << 34 | status << 32 | position),
 // status 1 = NaN, 2 = Infinity (BBQ_ERR_NAN / BBQ_ERR_INF minus 4).  An offending query is ZEROED (staging copy and the
 // device buffer it came from) so that the search already enqueued behind this kernel runs on harmless input; the host
 // reads bad[0] at its one synchronisation point and reports the error instead of the results.
-__device__ __forceinline__ unsigned long long query_verdict(long long q_global, int cosine, uint32_t first_nan,
-                                                            uint32_t first_inf) {
+__device__ __forceinline__ unsigned long long query_verdict(long long q_global, int cosine, int normalize_times,
+                                                            uint32_t first_nan, uint32_t first_inf) {
   uint32_t status, pos;
   if (cosine) {
     status = 1u;
-    pos = first_nan != 0xFFFFFFFFu ? 0u : first_inf;
+    pos = (first_nan != 0xFFFFFFFFu || normalize_times >= 2) ? 0u : first_inf;
   } else if (first_nan < first_inf) {
     status = 1u;
     pos = first_nan;
@@ -408,7 +410,7 @@ __device__ __forceinline__ void osq_query_team(const Team& T, float* __restrict_
   if (bad != nullptr) {
     T.min2(first_nan, first_inf);
     if (first_nan != 0xFFFFFFFFu || first_inf != 0xFFFFFFFFu) {  // (uniform across the team)
-      if (T.tid() == 0) atomicMin(bad, query_verdict(q_global, sim == bbqn::SIM_COSINE ? 1 : 0, first_nan, first_inf));
+      if (T.tid() == 0) atomicMin(bad, query_verdict(q_global, sim == bbqn::SIM_COSINE ? 1 : 0, normalize_times, first_nan, first_inf));
       for (int i = T.tid(); i < dim; i += T.size()) {
         vec[i] = 0.0f;
         src[i] = 0.0f;
@@ -1121,7 +1123,7 @@ __global__ void __launch_bounds__(256) k_rerank_select(const double* __restrict_
 
 // Input screening as a kernel of its own (one warp per query), for the thread-per-query form of K4 only — the warp and
 // CTA forms do it while they stage the query (osq_query_team, where the rules are stated).
-__global__ void k_validate_queries(float* __restrict__ queries, int nq, int dim, int cosine,
+__global__ void k_validate_queries(float* __restrict__ queries, int nq, int dim, int cosine, int normalize_times,
                                    unsigned long long* __restrict__ bad, int q_base) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= nq) return;
@@ -1137,7 +1139,7 @@ __global__ void k_validate_queries(float* __restrict__ queries, int nq, int dim,
     first_inf = min(first_inf, __shfl_xor_sync(0xffffffffu, first_inf, o));
   }
   if (first_nan == 0xFFFFFFFFu && first_inf == 0xFFFFFFFFu) return;
-  if (lane == 0) atomicMin(bad, query_verdict((long long)q_base + warp, cosine, first_nan, first_inf));
+  if (lane == 0) atomicMin(bad, query_verdict((long long)q_base + warp, cosine, normalize_times, first_nan, first_inf));
   for (int i = lane; i < dim; i += 32) v[i] = 0.0f;
 }
 

@@ -63,10 +63,38 @@ class JSObj:
 
 
 class JSClass:
-    __slots__ = ("name", "ctor", "methods", "statics", "fields", "native_new")
+    __slots__ = ("name", "ctor", "methods", "statics", "fields", "native_new", "parent")
 
     def __init__(self, name):
         self.name, self.ctor, self.methods, self.statics, self.fields, self.native_new = name, None, {}, {}, [], None
+        self.parent = None
+
+    def find_method(self, key):
+        c = self
+        while c is not None:
+            f = c.methods.get(key)
+            if f is not None:
+                return f
+            c = c.parent
+        return None
+
+    def find_static(self, key):
+        c = self
+        while c is not None:
+            if key in c.statics:
+                return c.statics[key]
+            c = c.parent
+        return UNDEF
+
+
+class JSRegExp:
+    __slots__ = ("source", "flags", "rx")
+
+    def __init__(self, source, flags):
+        f = 0
+        for ch in flags:
+            f |= {"i": re.I, "m": re.M, "s": re.S}.get(ch, 0)
+        self.source, self.flags, self.rx = source, flags, re.compile(source.replace("(?<", "(?P<"), f)
 
 
 class JSFunction:
@@ -555,6 +583,35 @@ def lex(src, fname="<ts>"):
             nl = False
             i = j + 1
             continue
+        if src[i] == "/" and src[i + 1:i + 2] not in ("/", "*"):   # division or a regular-expression literal?
+            prev = toks[-1] if toks else None
+            postfix_bang = prev is not None and prev.kind == "punc" and prev.val == "!" and len(toks) >= 2 and \
+                (toks[-2].kind in ("id", "num", "str", "tpl") or (toks[-2].kind == "punc" and toks[-2].val in (")", "]")))   # x! / y
+            starts = prev is None or (prev.kind == "punc" and prev.val not in (")", "]", "}") and not postfix_bang) or \
+                (prev.kind == "id" and prev.val in ("return", "typeof", "case", "do", "else", "in", "of", "void", "delete", "throw", "new"))
+            if starts:
+                j, in_class = i + 1, False
+                while True:
+                    if j >= n or src[j] == "\n":
+                        raise SyntaxError(f"{fname}: unterminated regular expression at {i}")
+                    c = src[j]
+                    if c == "\\":
+                        j += 2
+                        continue
+                    if c == "[":
+                        in_class = True
+                    elif c == "]":
+                        in_class = False
+                    elif c == "/" and not in_class:
+                        break
+                    j += 1
+                k = j + 1
+                while k < n and src[k].isalpha():
+                    k += 1
+                toks.append(Tok("regex", (src[i + 1:j], src[j + 1:k]), i, nl))
+                nl = False
+                i = k
+                continue
         m = TOKEN_RE.match(src, i)
         if not m:
             raise SyntaxError(f"{fname}: cannot tokenise at {i}: {src[i:i + 30]!r}")
@@ -1059,8 +1116,11 @@ class Parser:
         name = self.ident() if self.peek().kind == "id" and not self.at_id("implements") and not self.at_id("extends") else None
         if self.at("<"):
             self.skip_type_args()
+        parent = None
         if self.eat_id("extends"):
-            self.fail("class inheritance is not supported")
+            parent = self.member_only()
+            if self.at("<"):
+                self.skip_type_args()
         if self.eat_id("implements"):
             while not self.at("{"):
                 self.i += 1
@@ -1094,7 +1154,7 @@ class Parser:
             init = self.assignment() if self.eat("=") else None
             self.semi()
             members.append(("field", key, init, static))
-        return ("cdecl", name, members)
+        return ("cdecl", name, members, parent)
 
     def enum_decl(self):
         self.i += 1
@@ -1437,6 +1497,8 @@ class Parser:
                     sub = Parser(p, self.fname)
                     parts.append(sub.expression())
             return ("tpl", parts)
+        if k == "regex":
+            return ("regex", tok.val[0], tok.val[1])
         if k == "id":
             v = tok.val
             if v == "this":
@@ -1457,9 +1519,9 @@ class Parser:
             if v == "class":
                 self.i -= 1
                 d = self.class_decl()
-                return ("class", d[1], d[2])
+                return ("class", d[1], d[2], d[3])
             if v == "super":
-                self.fail("super is not supported")
+                return ("super",)
             return ("id", v)
         if k == "punc":
             v = tok.val
@@ -1527,8 +1589,10 @@ CONT = ("c",)
 
 
 class Interp:
-    def __init__(self, log=None, stub_modules=(), virtual_modules=None):
+    def __init__(self, log=None, stub_modules=(), virtual_modules=None, require=None, path_overrides=None):
         self.modules = {}
+        self.require = require                        # host hook behind the global require(spec) (e.g. a fake native addon)
+        self.path_overrides = dict(path_overrides or {})   # module location (as resolved) -> the file whose text is loaded there
         self.virtual_modules = dict(virtual_modules or {})   # bare specifier -> exports dict provided by the host (e.g. 'vitest')
         self.stub_modules = tuple(stub_modules)   # path suffixes loaded as EMPTY modules (e.g. the async WASM bridge)
         self.stubbed = []
@@ -1549,7 +1613,7 @@ class Interp:
         if any(path.endswith(sfx) for sfx in self.stub_modules):
             self.stubbed.append(path)
             return exports
-        src = open(path, encoding="utf-8").read()
+        src = open(self.path_overrides.get(path, path), encoding="utf-8").read()
         ast = Parser(lex(src, path), path).program()
         env = Env(self.globals)
         env.vars["this"] = UNDEF
@@ -1565,8 +1629,8 @@ class Interp:
             raise ImportError(f"{base}: bare module specifier {spec!r} is not supported")
         p = os.path.normpath(os.path.join(os.path.dirname(base), spec))
         for cand in (p, p + ".ts", p + ".js", os.path.join(p, "index.ts")):
-            if os.path.isfile(cand):
-                return cand
+            if cand in self.path_overrides or os.path.isfile(cand):
+                return cand      # (an overridden module keeps its VIRTUAL location: its own imports resolve from there)
         if p.endswith(".js") and os.path.isfile(p[:-3] + ".ts"):
             return p[:-3] + ".ts"
         raise ImportError(f"{base}: cannot resolve {spec!r}")
@@ -1590,6 +1654,13 @@ class Interp:
         g["NaN"] = math.nan
         g["Infinity"] = math.inf
         g["globalThis"] = g
+        g["process"] = {"env": {}, "argv": []}
+
+        def _require(spec=UNDEF):
+            if self.require is None:
+                throw_type_error("require is not available")
+            return self.require(to_str(spec))
+        g["require"] = _require
         M = {"PI": math.pi, "E": math.e, "LN2": math.log(2), "LN10": math.log(10), "LOG2E": 1 / math.log(2), "LOG10E": 1 / math.log(10),
              "SQRT2": math.sqrt(2), "SQRT1_2": math.sqrt(0.5),
              "abs": lambda x=UNDEF: abs(to_number(x)), "floor": lambda x=UNDEF: _floor(to_number(x)),
@@ -1857,8 +1928,10 @@ def get_prop(obj, key):
         if k in p:
             return p[k]
         cls = obj.cls
-        if cls is not None and k in cls.methods:
-            return BoundMethod(obj, cls.methods[k])
+        if cls is not None:
+            f = cls.find_method(k)
+            if f is not None:
+                return BoundMethod(obj, f)
         if k == "constructor":
             return cls
         if k == "toString":
@@ -1892,10 +1965,19 @@ def get_prop(obj, key):
         return UNDEF
     if t is JSClass:
         k = key if type(key) is str else prop_key(key)
-        if k in obj.statics:
-            return obj.statics[k]
-        if k == "name":
+        v = obj.find_static(k)
+        if v is UNDEF and k == "name":
             return obj.name
+        return v
+    if t is JSRegExp:
+        if key == "source":
+            return obj.source
+        if key == "flags":
+            return obj.flags
+        if key == "exec":
+            return BoundMethod(obj, _regexp_exec)
+        if key == "test":
+            return BoundMethod(obj, lambda this, s=UNDEF: this.rx.search(to_str(s)) is not None)
         return UNDEF
     if t is JSMap or t is JSSet:
         if key == "size":
@@ -1921,6 +2003,13 @@ def get_prop(obj, key):
     if callable(obj):
         return UNDEF
     raise RuntimeError(f"get_prop on unsupported host value {type(obj)}")
+
+
+def _regexp_exec(this, s=UNDEF):
+    m = this.rx.search(to_str(s))
+    if m is None:
+        return None
+    return [m.group(0)] + [UNDEF if g is None else g for g in m.groups()]
 
 
 def set_prop(obj, key, val):
@@ -2015,21 +2104,8 @@ def construct(cls, args):
         if cls.native_new is not None:
             return cls.native_new(args)
         obj = JSObj(cls)
-        ctor = cls.ctor
-        env = None
-        if ctor is not None:      # TypeScript's emit order: parameter properties, then field initialisers, then the body
-            env = Env(ctor.env)
-            env.vars["this"] = obj
-            bind_params(ctor.params, args, env)
-            for name in ctor.param_props:
-                obj.props[name] = env.vars[name]
-        for name, init in cls.fields:
-            obj.props[name] = init(obj) if init is not None else UNDEF
-        if ctor is not None:
-            r = ctor.body(env)
-            if r is not None and isinstance(r[1], (JSObj, dict, list)):
-                return r[1]
-        return obj
+        r = init_instance(cls, obj, args)
+        return r if r is not None else obj
     if t is Native and cls.construct is not None:
         return cls.construct(args)
     if t is JSFunction:
@@ -2037,6 +2113,47 @@ def construct(cls, args):
         r = call_function(cls, obj, args)
         return r if isinstance(r, (JSObj, dict, list)) else obj
     throw_type_error(f"{to_str(cls)} is not a constructor")
+
+
+def init_instance(cls, obj, args):
+    """Runs the construction steps of `cls` on obj — TypeScript's emit order: [super(...)], parameter properties, field
+    initialisers, then the rest of the constructor body.  -> an object the constructor returned explicitly, or None."""
+    ctor, parent = cls.ctor, cls.parent
+
+    def own_fields():
+        for name, init in cls.fields:
+            obj.props[name] = init(obj) if init is not None else UNDEF
+    if ctor is None:
+        if parent is not None:      # implicit constructor(...args) { super(...args); }
+            init_instance(parent, obj, args)
+        own_fields()
+        return None
+    env = Env(ctor.env)
+    env.vars["this"] = obj
+    bind_params(ctor.params, args, env)
+
+    def own_start():
+        for name in ctor.param_props:
+            obj.props[name] = env.vars[name]
+        own_fields()
+    if parent is None:
+        own_start()
+    else:
+        called = [False]
+
+        def super_ctor(*a):
+            if called[0]:
+                raise JSThrow(JSObj(ERR.get("ReferenceError"), {"message": "Super constructor may only be called once",
+                                                                "name": "ReferenceError", "stack": ""}))
+            called[0] = True
+            init_instance(parent, obj, list(a))
+            own_start()
+            return UNDEF
+        env.vars["%super_ctor"] = super_ctor
+    r = ctor.body(env)
+    if r is not None and isinstance(r[1], (JSObj, dict, list)):
+        return r[1]
+    return None
 
 
 def bind_params(params, args, env):
@@ -2310,7 +2427,9 @@ def _typed_set(this, src, offset=UNDEF):
 
 
 def _typed_subarray(this, a=UNDEF, b=UNDEF):
-    raise NotImplementedError("TypedArray.prototype.subarray (a view on shared memory) is not supported")
+    # a COPY, not a view on shared memory: enough for read-only uses (the drop-in class reads rows through it); code
+    # that writes through a subarray would need real views — the reference's sources never call subarray
+    return _arr_slice(this, a, b)
 
 
 TYPED_METHODS = {k: ARRAY_METHODS[k] for k in ("map", "filter", "reduce", "forEach", "slice", "sort", "reverse", "join", "fill", "indexOf",
@@ -2726,7 +2845,7 @@ class Compiler:
                 return None
             return run_fdecl
         if k == "cdecl":
-            mk = self.make_class(st[1], st[2])
+            mk = self.make_class(st[1], st[2], st[3])
             name = st[1]
 
             def run_cdecl(env):
@@ -2778,7 +2897,8 @@ class Compiler:
             return JSFunction(cparams, cbody, env, is_arrow, is_expr, name, simple, pprops)
         return mk
 
-    def make_class(self, name, members):
+    def make_class(self, name, members, parent=None):
+        parent_expr = self.expr(parent) if parent is not None else None
         methods, statics_m, fields, statics_f, ctor = [], [], [], [], None
         for m in members:
             if m[0] == "method":
@@ -2796,6 +2916,11 @@ class Compiler:
             cenv = Env(env)
             if name:
                 cenv.vars[name] = cls
+            cenv.vars["%home"] = cls              # the class a method was defined in: what super.* is relative to
+            if parent_expr is not None:
+                cls.parent = parent_expr(env)
+                if type(cls.parent) is not JSClass:
+                    throw_type_error("Class extends value is not a class defined in the interpreted program")
             for key, f in methods:
                 cls.methods[key] = f(cenv)
             if ctor is not None:
@@ -2891,7 +3016,14 @@ class Compiler:
         return self.make_function(e)
 
     def x_class(self, e):
-        return self.make_class(e[1], e[2])
+        return self.make_class(e[1], e[2], e[3])
+
+    def x_regex(self, e):
+        source, flags = e[1], e[2]
+        return lambda env: JSRegExp(source, flags)
+
+    def x_super(self, e):
+        raise SyntaxError(f"{self.path}: 'super' is only supported as super(...) and super.method(...)")
 
     def x_seq(self, e):
         parts = [self.expr(p) for p in e[1]]
@@ -3292,6 +3424,20 @@ class Compiler:
 
     def x_call(self, e):
         callee, args, optional = e[1], self.args(e[2]), e[3]
+        if callee[0] == "super":
+            look = self.x_id(("id", "%super_ctor"))
+            return lambda env: look(env)(*args(env))
+        if callee[0] == "mem" and callee[1][0] == "super":
+            name = callee[2]
+            home, this = self.x_id(("id", "%home")), self.x_id(("id", "this"))
+
+            def call_super_method(env):
+                parent = home(env).parent
+                f = parent.find_method(name) if parent is not None else None
+                if f is None:
+                    throw_type_error(f"(intermediate value).{name} is not a function")
+                return call_function(f, this(env), args(env))
+            return call_super_method
         if callee[0] in ("mem", "idx"):
             o = self.expr(callee[1])
             key = (lambda env, name=callee[2]: name) if callee[0] == "mem" else self.expr(callee[2])
@@ -3306,7 +3452,7 @@ class Compiler:
                 if t is JSObj:
                     f = obj.props.get(k)
                     if f is None:
-                        f = obj.cls.methods.get(k) if obj.cls is not None else None
+                        f = obj.cls.find_method(k) if (obj.cls is not None and type(k) is str) else None
                         if f is None:
                             f = get_prop(obj, k)
                 elif t is Native:
@@ -3369,7 +3515,12 @@ def _delete(obj, key):
 def _instanceof(v, cls):
     if type(cls) is JSClass:
         if type(v) is JSObj:
-            return v.cls is cls or (cls.name == "Error" and v.cls is not None and v.cls.name.endswith("Error"))
+            c = v.cls
+            while c is not None:
+                if c is cls:
+                    return True
+                c = c.parent
+            return cls.name == "Error" and v.cls is not None and v.cls.name.endswith("Error")
         return False
     if type(cls) is Native:
         if cls.name == "Array":
@@ -3390,7 +3541,7 @@ def _has_prop(obj, key):
         return prop_key(key) in obj
     if type(obj) is JSObj:
         k = prop_key(key)
-        return k in obj.props or (obj.cls is not None and k in obj.cls.methods)
+        return k in obj.props or (obj.cls is not None and obj.cls.find_method(k) is not None)
     if type(obj) in (list, TypedArray):
         n = len(obj.a) if type(obj) is TypedArray else len(obj)
         return 0 <= idx_int(key) < n or key == "length"

@@ -197,12 +197,13 @@ def seeded_random(seed=12345):
     return rnd
 
 
-def run_test_file(path, reference_stub=("/src/wasm/index.ts",), seed=12345, log=None):
-    """Loads one *.test.ts of the reference (its imports resolve to the reference's own src/), runs it -> (passed, failed, assertions, console)"""
+def run_test_file(path, reference_stub=("/src/wasm/index.ts",), seed=12345, log=None, **interp_kwargs):
+    """Loads one *.test.ts of the reference (its imports resolve to the reference's own src/ — or to whatever
+    path_overrides / require in interp_kwargs put there), runs it -> (passed, failed, assertions, console)"""
     console = []
     vt = Vitest()
     interp = T.Interp(log=(log or (lambda *a: console.append(" ".join(map(str, a))))), stub_modules=reference_stub,
-                      virtual_modules={"vitest": vt.exports()})
+                      virtual_modules={"vitest": vt.exports()}, **interp_kwargs)
     interp.globals.vars["Math"].props["random"] = seeded_random(seed)
     interp.load(path)
     passed, failed = vt.run()

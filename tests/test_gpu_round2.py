@@ -90,8 +90,8 @@ def test_query_validation_on_device_reports_like_the_reference(bbq):
         only_inf[3, 12] = -np.inf
         with pytest.raises(bbq.BbqError) as e:
             fmt.searchBatch(only_inf, qv, 5)
-        if sim == "COSINE":   # Inf / Inf = NaN at that position after normalisation
-            assert e.value.status == 5 and str(e.value) == "向量位置 12 包含NaN值"
+        if sim == "COSINE":   # the search path normalises twice: Inf / Inf = NaN, then x / NaN = NaN everywhere -> position 0
+            assert e.value.status == 5 and str(e.value) == "向量位置 0 包含NaN值"      # (tests/golden/from_ts/errors.behaviour.json)
         else:
             assert e.value.status == 6 and str(e.value) == "向量位置 12 包含Infinity值"
         # the context is still usable and answers as before

@@ -174,7 +174,7 @@ def test_modules_and_errors(tmp_path):
         run(tmp_path, "export function main() { throw new Error('向量集合不能为空'); }")
     assert str(e.value) == "Error: 向量集合不能为空"
     for bad in ("export async function main() { await 1; }", "export function* main() { yield 1; }",
-                "class A {} class B extends A {} export function main() {}"):
+                "export function main() { outer: for (;;) { break outer; } }"):
         with pytest.raises(SyntaxError):
             run(tmp_path, bad)
 
