@@ -174,3 +174,34 @@ def test_reference_own_recall_tests_pass_on_the_dropin_class():
     assert not failed, failed[:3]
     assert len(passed) == 8 and assertions > 100
     assert addon.calls.count("search") > 50 and "build" in addon.calls
+
+
+def test_dropin_additive_members_execute():
+    """searchBatch (one call for several queries) and attachOriginalVectors + searchOversampled (the device form of
+    src/topKSelector.ts) — members the reference does not have: row i of searchBatch equals searchNearestNeighbors of
+    query i, and the oversampled search returns what the reference's getOversampledTopKWithSort computes with the
+    reference's own class (true cosine scores bit for bit)."""
+    T, (ref, ref_ex, _), (gpu, gpu_ex, _), addon = _packages()
+    n, dim, k, factor = 60, 32, 5, 3
+    base, queries = gaussian(n, dim, 9300), gaussian(3, dim, 9301)
+    fmt = gpu.call(gpu_ex["createBinaryQuantizationFormat"], args=[_config("COSINE", 4)])
+    rows = [gpu.float32(r.tolist()) for r in base]
+    qv = gpu.call(gpu.get(fmt, "quantizeVectors"), fmt, [rows])["quantizedVectors"]
+    qs = [gpu.float32(q.tolist()) for q in queries]
+    batch = gpu.call(gpu.get(fmt, "searchBatch"), fmt, [qs, qv, float(k)])
+    assert len(batch) == 3
+    for i, q in enumerate(qs):
+        single = gpu.call(gpu.get(fmt, "searchNearestNeighbors"), fmt, [q, qv, float(k)])
+        assert [(r["index"], r["score"]) for r in batch[i]] == [(r["index"], r["score"]) for r in single]
+    gpu.call(gpu.get(fmt, "attachOriginalVectors"), fmt, [qv, rows])
+    over = gpu.call(gpu.get(fmt, "searchOversampled"), fmt, [qs[0], qv, float(k), float(factor)])
+    # the reference's selector over the reference's class
+    sel = ref.load(os.path.join(REF, "src", "topKSelector.ts"))
+    rfmt = ref.call(ref_ex["createBinaryQuantizationFormat"], args=[_config("COSINE", 4)])
+    rrows = [ref.float32(r.tolist()) for r in base]
+    rqv = ref.call(ref.get(rfmt, "quantizeVectors"), rfmt, [rrows])["quantizedVectors"]
+    want = ref.call(sel["getOversampledTopKWithSort"], args=[ref.float32(queries[0].tolist()), rqv, rrows, float(k), float(factor), rfmt])
+    assert [c["index"] for c in over] == [c["index"] for c in want]
+    assert [_bits64(c["trueScore"]) for c in over] == [_bits64(c["trueScore"]) for c in want]
+    assert [c["quantizedScore"] for c in over] == [c["quantizedScore"] for c in want]
+    assert {"attachRows", "searchRerank"} <= set(addon.calls)
