@@ -183,6 +183,8 @@ class BinaryQuantizationFormat:
         cen = np.ascontiguousarray(centroid, np.float32) if centroid is not None else None
         _check(_native.load().bbq_index_build(self._ctx, m.ctypes.data, m.shape[0], m.shape[1],
                                               cen.ctypes.data if cen is not None else None, C.byref(h)), "build")
+        # (the reference hands out its OptimizedScalarQuantizer helper as queryQuantizer, :261, and so does the TypeScript
+        # drop-in; this Python stand-in has no such host-side object: the format itself quantises queries)
         return {"quantizedVectors": BinarizedByteVectorValues(self, h), "queryQuantizer": self}
 
     def quantizeVectorsDevice(self, d_rows_ptr: int, n: int, dim: int, centroid: Optional[np.ndarray] = None):
