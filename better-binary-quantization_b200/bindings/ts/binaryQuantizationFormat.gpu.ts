@@ -81,6 +81,7 @@ class DeviceBinarizedByteVectorValues implements BinarizedByteVectorValues {
     return addon.rows(this.handle, ord, 1).packed;
   }
   getUnpackedVector(ord: number): Uint8Array {                              // :68
+    if (ord < 0 || ord >= this.meta.size) throw new Error(`未打包向量索引 ${ord} 不存在`);
     const packed = this.vectorValue(ord);
     const out = new Uint8Array(this.meta.dimension);
     for (let i = 0; i < out.length; i++) out[i] = (packed[i >> 3]! >> (7 - (i & 7))) & 1;
@@ -146,7 +147,8 @@ export class BinaryQuantizationFormat extends ReferenceBinaryQuantizationFormat 
     if (queryVector.length !== targetVectors.dimension()) throw new Error('查询向量维度与目标向量维度不匹配');
     if (k === 0) return [];
     try {
-      const r = addon.search(deviceHandle(targetVectors), queryVector, 1, k);
+      // a fractional k: the reference's heap loop (`size() < k2`, :386-389) ends up with ceil(k) results
+      const r = addon.search(deviceHandle(targetVectors), queryVector, 1, Math.ceil(k));
       const out = new Array(r.count);
       for (let i = 0; i < r.count; i++) out[i] = { index: r.indices[i]!, score: r.scores[i]! };
       return out;

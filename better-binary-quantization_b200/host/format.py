@@ -14,6 +14,7 @@ Everything numeric happens in libbbq_b200.so on the GPU; this file only marshals
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 from typing import List, Optional, Sequence
 
@@ -134,6 +135,8 @@ class BinarizedByteVectorValues:
         return self._export(ord_)[0][0]
 
     def getUnpackedVector(self, ord_: int) -> np.ndarray:
+        if ord_ < 0 or ord_ >= self._n:
+            raise BbqError(10, f"未打包向量索引 {ord_} 不存在")
         v = self.vectorValue(ord_)
         return np.unpackbits(v)[: self._dim] if self._fmt.config["indexBits"] == 1 else v
 
@@ -312,6 +315,7 @@ class BinaryQuantizationFormat:
             raise BbqError(8, "目标向量集合不能为空")
         if k < 0:
             raise BbqError(7, "k值不能为负数")
+        k = int(math.ceil(k))      # a fractional k: the reference's heap loop (`size() < k2`) ends up with ceil(k) results
         q = np.ascontiguousarray(queryVector, np.float32).ravel()
         if q.size != targetVectors.dimension():
             raise BbqError(4, "查询向量维度与目标向量维度不匹配")

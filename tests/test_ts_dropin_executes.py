@@ -67,11 +67,18 @@ def test_dropin_class_is_indistinguishable_from_the_reference_class(sim, qb):
             qa = I.float32(q.tolist())
             o["search"].append([(r["index"], r["score"]) for r in I.call(I.get(fmt, "searchNearestNeighbors"), fmt, [qa, qv, float(k)])])
             assert I.call(I.get(fmt, "searchNearestNeighbors"), fmt, [qa, qv, 0.0]) == []
+            assert len(I.call(I.get(fmt, "searchNearestNeighbors"), fmt, [qa, qv, 2.5])) == 3                 # fractional k -> ceil(k)
             assert len(I.call(I.get(fmt, "searchNearestNeighbors"), fmt, [qa, qv, float(n + 9)])) == n        # k > n -> n results
             once = I.call(I.get(fmt, "quantizeQueryVector"), fmt, [qa, I.call(I.get(qv, "getCentroid"), qv, [])])
             qc = once["queryCorrections"]
             o["once"].append((list(once["quantizedQuery"].a), [_bits64(qc[f]) for f in ("lowerInterval", "upperInterval",
                                                                                         "additionalCorrection", "quantizedComponentSum")]))
+        o["range"] = []
+        for member, bad_ord in (("vectorValue", float(n)), ("vectorValue", -1.0), ("getCorrectiveTerms", float(n)), ("getUnpackedVector", float(n + 51))):
+            with pytest.raises(T.JSThrow) as e:
+                I.call(I.get(qv, member), qv, [bad_ord])
+            o["range"].append(str(e.value))
+        o["cdp_q"] = I.call(I.get(qv, "getCentroidDP"), qv, [I.float32(queries[0].tolist())])
         acc = I.call(I.get(fmt, "computeQuantizationAccuracy"), fmt, [rows[:3], [I.float32(q.tolist()) for q in queries]])
         o["acc"] = [_bits64(acc[f]) for f in ("meanError", "maxError", "minError", "stdError", "correlation")]
         # serializeVectorData -> deserializeVectorData.  Executed, the REFERENCE's serializeVectorData throws on any real
@@ -93,7 +100,7 @@ def test_dropin_class_is_indistinguishable_from_the_reference_class(sim, qb):
             assert isinstance(I.call(I.get(fmt, member), fmt, []), T.JSObj)
         out[name] = o
     r, g = out["ref"], out["gpu"]
-    for key in ("size", "dim", "centroid", "cdp", "corr", "packed", "unpacked", "once", "acc"):
+    for key in ("size", "dim", "centroid", "cdp", "cdp_q", "corr", "packed", "unpacked", "once", "acc", "range"):
         assert r[key] == g[key], key
     assert r["config"]["queryBits"] == g["config"]["queryBits"] and r["config"]["quantizer"] == g["config"]["quantizer"]
     for a, b in zip(r["search"] + [r["roundtrip"]], g["search"] + [g["roundtrip"]]):
