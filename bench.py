@@ -50,7 +50,8 @@ WORKLOADS = {
                name="100M x 1024 COSINE k=10 batch of 4096 queries, row-sharded (BASELINE configs[3])"),
     "c5": dict(n=10_000_000, dim=1536, sim="COSINE", k=100, nq=1024, qb=8, ib=2, cpu_rows=200_000,
                name="10M x 1536 COSINE k=100 batch of 1024 queries, queryBits=8/indexBits=2 (BASELINE configs[4]; "
-                    "EXTENSION: the reference throws for this config, parity unpinned by construction)"),
+                    "EXTENSION: the reference, executed, throws for this config — tests/golden/from_ts/index_bits_2.behaviour.json; "
+                    "the index build equals the reference's, the search semantics are this repository's)"),
 }
 CHUNK = 65536            # corpus generation granularity: chunk c is seeded by (SEED + c) whatever N is
 SEED_CORPUS, SEED_QUERY = 20260101, 20260201
