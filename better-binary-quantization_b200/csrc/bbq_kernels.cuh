@@ -240,8 +240,8 @@ struct WarpTeam {
   }
   __device__ __forceinline__ void minmax(double& mn, double& mx) const {
     for (int o = 16; o > 0; o >>= 1) {
-      mn = bbqn::js_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-      mx = bbqn::js_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mn = bbqn::js_minz(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = bbqn::js_maxz(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
   }
   __device__ __forceinline__ double sum_integers(double v) const {  // integer-valued (or NaN) terms: any order is exact
@@ -317,8 +317,8 @@ struct CtaTeam {
   }
   __device__ __forceinline__ void minmax(double& mn, double& mx) const {
     for (int o = 16; o > 0; o >>= 1) {
-      mn = bbqn::js_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-      mx = bbqn::js_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mn = bbqn::js_minz(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = bbqn::js_maxz(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
     constexpr int W = OSQC_PRODUCERS + 1;
     if (lane == 0) {
@@ -329,8 +329,8 @@ struct CtaTeam {
     mn = red[0];
     mx = red[W];
     for (int w = 1; w < W; w++) {  // same order in every thread
-      mn = bbqn::js_min(mn, red[w]);
-      mx = bbqn::js_max(mx, red[W + w]);
+      mn = bbqn::js_minz(mn, red[w]);
+      mx = bbqn::js_maxz(mx, red[W + w]);
     }
     __syncthreads();
   }
@@ -440,8 +440,8 @@ __device__ __forceinline__ void osq_query_team(const Team& T, float* __restrict_
   double mn = 1.7976931348623157e308, mx = -1.7976931348623157e308;
   for (int i = T.tid(); i < dim; i += T.size()) {
     const double cv = (double)vec[i] - cen(i);
-    mn = bbqn::js_min(mn, cv);
-    mx = bbqn::js_max(mx, cv);
+    mn = bbqn::js_minz(mn, cv);
+    mx = bbqn::js_maxz(mx, cv);
   }
   T.minmax(mn, mx);
   const double centroidDot = (sim != bbqn::SIM_EUCLIDEAN) ? st[0] : 0.0;

@@ -42,8 +42,22 @@ BBQ_HD double js_nan() { return (double)NAN; }
 // Math.min / Math.max: NaN-propagating
 BBQ_HD double js_min(double a, double b) { return (a != a || b != b) ? js_nan() : (a < b ? a : b); }
 BBQ_HD double js_max(double a, double b) { return (a != a || b != b) ? js_nan() : (a > b ? a : b); }
+// ... and with ECMAScript's zero rule (Math.min(+0, -0) = -0, Math.max(-0, +0) = +0): what the QUANTISERS use — the min / max
+// over the centred components and clamp() — so that a vector holding signed zeros gets the reference's interval bit for
+// bit (found by fuzzing the oracle against the executed reference).  The score formulas keep the plain forms above:
+// their only use is Math.max(x, 0), for which the plain form already returns +0.
+BBQ_HD double js_minz(double a, double b) {
+  if (a != a || b != b) return js_nan();
+  if (a == 0.0 && b == 0.0) return copysign(1.0, a) < 0.0 ? a : b;
+  return a < b ? a : b;
+}
+BBQ_HD double js_maxz(double a, double b) {
+  if (a != a || b != b) return js_nan();
+  if (a == 0.0 && b == 0.0) return copysign(1.0, a) < 0.0 ? b : a;
+  return a > b ? a : b;
+}
 // src/utils.ts:79-81
-BBQ_HD double js_clamp(double x, double lo, double hi) { return js_min(js_max(x, lo), hi); }
+BBQ_HD double js_clamp(double x, double lo, double hi) { return js_minz(js_maxz(x, lo), hi); }
 // ECMAScript Math.round: nearest integer, ties toward +infinity
 BBQ_HD double js_round(double x) {
   if (!(fabs(x) < 4503599627370496.0)) return x;
@@ -93,8 +107,8 @@ BBQ_HD OsqResult osq_interval(const V& v, const Cn& c, int d, int bits, int sim,
   double sum = 0.0, n2 = 0.0;
   for (int i = 0; i < d; i++) {
     const double cv = (double)v(i) - (double)c(i);
-    mn = js_min(mn, cv);
-    mx = js_max(mx, cv);
+    mn = js_minz(mn, cv);
+    mx = js_maxz(mx, cv);
     const double w = (double)(float)cv;
     sum += w;      // computeMean  (src/utils.ts:41-50)
     n2 += w * w;   // computeL2Norm (src/utils.ts:25-34) — independent chains, same per-chain order

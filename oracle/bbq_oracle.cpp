@@ -53,12 +53,14 @@ const double kGrid[8] = {0.798, 1.493, 2.051, 2.514, 2.916, 3.278, 3.611, 3.922}
 // src/constants.ts:20
 const double kFourBitScale = 1.0 / 15.0;
 
-inline double js_min(double a, double b) {  // Math.min: NaN-propagating
+inline double js_min(double a, double b) {  // Math.min: NaN-propagating, and -0 < +0
   if (std::isnan(a) || std::isnan(b)) return std::numeric_limits<double>::quiet_NaN();
+  if (a == 0 && b == 0) return std::signbit(a) ? a : b;
   return a < b ? a : b;
 }
-inline double js_max(double a, double b) {
+inline double js_max(double a, double b) {  // Math.max: NaN-propagating, and +0 > -0
   if (std::isnan(a) || std::isnan(b)) return std::numeric_limits<double>::quiet_NaN();
+  if (a == 0 && b == 0) return std::signbit(a) ? b : a;
   return a > b ? a : b;
 }
 // src/utils.ts:79-81

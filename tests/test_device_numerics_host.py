@@ -59,7 +59,12 @@ def test_osq_degenerate_bit_exact(hn):
              (np.full(16, 2.5, np.float32), np.full(16, 2.5, np.float32)),
              (np.array([1, -1, .5, -.5], np.float32), np.zeros(4, np.float32)),
              (np.array([1e30, -1e30, 3, 4], np.float32), np.zeros(4, np.float32)),
-             (np.array([1e-30, 2e-30, -1e-30, 0], np.float32), np.zeros(4, np.float32))]
+             (np.array([1e-30, 2e-30, -1e-30, 0], np.float32), np.zeros(4, np.float32)),
+             # signed zeros: Math.min(+0, -0) = -0 and Math.max(-0, +0) = +0 decide the sign of a zero interval
+             (np.array([0, 0, 0, -0.0, 0, 0, 0, -0.0], np.float32), np.zeros(8, np.float32)),
+             (np.array([-0.0, 0, -0.0, 0], np.float32), np.zeros(4, np.float32)),
+             (np.array([-0.0, -0.0, -0.0, -0.0], np.float32), np.zeros(4, np.float32)),
+             (np.array([0, -0.0, 1, -1], np.float32), np.array([0, 0, 1, -1], np.float32))]
     for v, c in cases:
         for bits in (1, 4):
             for sim in ("EUCLIDEAN", "COSINE"):

@@ -209,7 +209,8 @@ def test_host_messages_equal_the_executed_reference():
 def test_fuzz_reference_source_interpreted_live_equals_oracle():
     """150 random small configurations, reference source (interpreted, now) vs oracle: every similarity function, query
     bits 1..8, dims 1..70 (below and across the 8-dim packing boundary), 1..40 rows, lambda in {0, 0.001, 0.1, 0.5, 1},
-    0 / 1 / 5 / 20 iterations, component scales 1e-3..1e3, duplicated and all-zero rows.  Correctives (f64 bit patterns),
+    0 / 1 / 5 / 20 iterations, component scales 1e-3..1e3, duplicated and all-zero rows; every sixth case each made of
+    signed zeros only, of integers, or of values near the top of the f32 range.  Correctives (f64 bit patterns),
     packed codes, the heap-ordered top-k list and its f32 scores must be identical in every case.  (Four other seeds x
     150 cases were run by hand when this was written: no mismatch.)"""
     import sys
@@ -231,7 +232,16 @@ def test_fuzz_reference_source_interpreted_live_equals_oracle():
             base[rng.integers(n)] = base[0]
         if rng.random() < 0.2:
             base[rng.integers(n)] = 0
-        tag = (case, sim, qb, dim, n, lam, iters, k, scale)
+        kind = case % 6                                  # every sixth case each: an extreme shape
+        if kind == 1:                                    # signed zeros only (Math.min(+0, -0) = -0 decides the interval's sign)
+            base[:, ::2] = 0
+            base[:, 1::2] = np.float32(-0.0) * base[:, 1::2]
+        elif kind == 2:                                  # integers: exact ties and .5 roundings
+            base, q = np.round(base).astype(np.float32), np.round(q).astype(np.float32)
+        elif kind == 3:                                  # near the top of the f32 range
+            base = (rng.standard_normal((n, dim)) * 1e30).astype(np.float32)
+            q[0] = np.float32(3e38)
+        tag = (case, kind, sim, qb, dim, n, lam, iters, k, scale)
         fmt = interp.call(ex["createBinaryQuantizationFormat"], args=[
             {"queryBits": float(qb), "indexBits": 1.0, "quantizer": {"similarityFunction": sim, "lambda": lam, "iters": float(iters)}}])
         qv = interp.call(interp.get(fmt, "quantizeVectors"), fmt, [[interp.float32(r.tolist()) for r in base]])["quantizedVectors"]
